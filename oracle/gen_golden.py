@@ -1,0 +1,179 @@
+"""Generate the golden fixtures under tests/golden/ by running the REAL reference.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference, which does not
+exist on the GPU box):
+
+    python oracle/gen_golden.py [--out tests/golden] [--only NAME]
+
+For every case it (1) builds a seeded weight set with oracle/weights.py, (2) loads it with
+``load_state_dict(strict=True)`` into the reference's own model (this also checks the
+state_dict key contract of SURVEY 8b), (3) drives the reference's own eval engine
+(``build_engine(..., phase='eval')``) through the evaluator's per-frame protocol
+(evaluator.py:315-422) on seeded synthetic clips, (4) stores the reference outputs, and
+(5) prints how far oracle/aot_oracle.py is from them (the pin).
+
+The only patch applied to the reference is the one SURVEY 0.4 documents:
+``transformer.MultiheadLocalAttentionV3 := attention.MultiheadLocalAttentionV2`` (the
+reference's no-sampler fallback V3 is broken at this commit; V2's unfold branch is the
+mathematical definition).  Nothing from the reference is copied into the repo.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("AOT_REFERENCE", "/root/reference")
+sys.path.insert(0, REPO)
+sys.path.insert(0, REF)
+
+from oracle import aot_oracle as O  # noqa: E402
+from oracle import weights as OW  # noqa: E402
+
+import networks.layers.attention as RA  # noqa: E402  (reference)
+import networks.layers.transformer as RT  # noqa: E402
+
+RT.MultiheadLocalAttentionV3 = RA.MultiheadLocalAttentionV2
+
+from configs.default import DefaultEngineConfig  # noqa: E402
+from networks.engines import build_engine as ref_build_engine  # noqa: E402
+from networks.models import build_vos_model as ref_build_model  # noqa: E402
+
+# name: (model, H, W, out_h, out_w, frames, objs, gap, weight flavour)
+VIDEO_CASES = {
+    "aott_256": ("aott", 256, 256, 256, 256, 3, 1, 9999, "calibrated"),          # BASELINE configs[0]
+    "aott_raw_257": ("aott", 257, 257, 240, 250, 4, 3, 2, "raw"),
+    "r50_aotl_small": ("r50_aotl", 161, 241, 150, 230, 7, 10, 2, "calibrated"),
+    "r50_deaotl_small": ("r50_deaotl", 161, 241, 150, 230, 7, 10, 2, "calibrated"),
+    "deaott_small": ("deaott", 129, 177, 129, 177, 5, 4, 2, "calibrated"),
+}
+
+
+def run_reference_video(model_name, H, W, oh, ow, T, objs, gap, flavour, seed=0):
+    torch.manual_seed(0)
+    sd = OW.build_state_dict(model_name, seed=seed, flavour=flavour)
+    rcfg = DefaultEngineConfig("golden", model_name)
+    ref_model = ref_build_model(rcfg.MODEL_VOS, rcfg).eval()
+    ref_model.load_state_dict(sd, strict=True)
+    engine = ref_build_engine(rcfg.MODEL_ENGINE, phase="eval", aot_model=ref_model, gpu_id=-1,
+                              long_term_mem_gap=gap, short_term_mem_skip=1)
+    engine.eval()
+    frames, mask = O.synthetic_video(T, H, W, objs, seed=1234 + seed)
+    with torch.no_grad():
+        logits_lo, labels = O.run_video(engine, frames, mask, objs, (oh, ow))
+    return sd, frames, mask, logits_lo, labels
+
+
+def video_case(name, out_dir):
+    model_name, H, W, oh, ow, T, objs, gap, flavour = VIDEO_CASES[name]
+    sd, frames, mask, ref_lo, ref_labels = run_reference_video(model_name, H, W, oh, ow, T, objs, gap, flavour)
+    # pin the oracle (teacher-forced with the reference's own labels)
+    ocfg = O.OracleConfig(model_name)
+    oe = O.OracleEngine(sd, ocfg, long_term_mem_gap=gap)
+    with torch.no_grad():
+        o_lo, o_labels = O.run_video(oe, frames, mask, objs, (oh, ow), forced_masks=ref_labels)
+    max_d = max((a - b).abs().max().item() for a, b in zip(ref_lo, o_lo))
+    mism = sum((a != b).sum().item() for a, b in zip(ref_labels, o_labels))
+    used = sorted(set(int(v) for l in ref_labels for v in l.unique().tolist()))
+    print(f"[{name}] oracle vs reference: max|dlogit|={max_d:.3e} label mismatches={mism} "
+          f"|logit|max={max(a[:, :objs + 1].abs().max().item() for a in ref_lo):.2f} labels used={used}")
+    torch.save({
+        "model": model_name, "H": H, "W": W, "out_size": (oh, ow), "frames": T, "objs": objs, "gap": gap,
+        "flavour": flavour, "seed": 0, "weights_checksum": OW.checksum(sd),
+        "ref_logits_lo": [t.to(torch.float32) for t in ref_lo],
+        "ref_labels": [t.to(torch.uint8) for t in ref_labels],
+        "oracle_pin_max_dlogit": max_d, "oracle_pin_label_mismatch": mism,
+    }, os.path.join(out_dir, f"video_{name}.pt"))
+
+
+def op_cases(out_dir):
+    """Per-op vectors straight from the reference's attention modules (K1, K2, K1', K2')."""
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    with torch.no_grad():
+        # K1  MultiheadAttention(use_linear=False)  attention.py:64-121
+        m = RA.MultiheadAttention(256, 8, use_linear=False).eval()
+        Q = torch.randn(70, 1, 256, generator=g) * 2
+        K = torch.randn(333, 1, 256, generator=g)
+        V = torch.randn(333, 1, 256, generator=g)
+        out["k1"] = {"sd": {k: v.clone() for k, v in m.state_dict().items()}, "Q": Q, "K": K, "V": V,
+                     "out": m(Q, K, V)[0]}
+        # K3  MultiheadAttention(use_linear=True) (self-attention)
+        m = RA.MultiheadAttention(256, 8, use_linear=True).eval()
+        X = torch.randn(90, 1, 256, generator=g)
+        out["k3"] = {"sd": {k: v.clone() for k, v in m.state_dict().items()}, "X": X, "out": m(X, X, X)[0]}
+        # K2  MultiheadLocalAttentionV2 unfold branch  attention.py:308-376
+        m = RA.MultiheadLocalAttentionV2(256, 8, use_linear=False, enable_corr=False).eval()
+        m.relative_emb_v.data = torch.randn(8, 32, 225, generator=g) * 0.2
+        m.relative_emb_k.weight.data = torch.randn(1800, 32, 1, 1, generator=g) * 0.1
+        h, w = 9, 20
+        q = torch.randn(1, 256, h, w, generator=g)
+        k = torch.randn(1, 256, h, w, generator=g)
+        v = torch.randn(1, 256, h, w, generator=g)
+        o, attn = m(q, k, v)
+        out["k2"] = {"sd": {kk: vv.clone() for kk, vv in m.state_dict().items()}, "q": q, "k": k, "v": v,
+                     "out": o, "attn": attn}
+        # K1' GatedPropagation(use_linear=False)  attention.py:636-712
+        m = RA.GatedPropagation(d_qk=64, d_vu=64, num_head=1, use_linear=False, d_att=32).eval()  # small dims: fixture size
+        N, Tk, hh, ww = 6 * 7, 150, 6, 7
+        Q = torch.randn(N, 1, 32, generator=g) * 2
+        K = torch.randn(Tk, 1, 32, generator=g)
+        V = torch.randn(Tk, 1, 128, generator=g)
+        U = torch.randn(N, 1, 128, generator=g)
+        out["k1p"] = {"sd": {kk: vv.clone() for kk, vv in m.state_dict().items()}, "Q": Q, "K": K, "V": V, "U": U,
+                      "size_2d": (hh, ww), "out": m(Q, K, V, U, (hh, ww))[0]}
+        # K2' LocalGatedPropagation(use_linear=False, enable_corr=False)  attention.py:789-861
+        m = RA.LocalGatedPropagation(d_qk=64, d_vu=64, num_head=1, use_linear=False, enable_corr=False,
+                                     d_att=32, max_dis=7).eval()
+        m.relative_emb_k.weight.data = torch.randn(225, 32, 1, 1, generator=g) * 0.1
+        q = torch.randn(1, 32, hh, ww, generator=g)
+        k = torch.randn(1, 32, hh, ww, generator=g)
+        v = torch.randn(1, 128, hh, ww, generator=g)
+        u = torch.randn(N, 1, 128, generator=g)
+        out["k2p"] = {"sd": {kk: vv.clone() for kk, vv in m.state_dict().items()}, "q": q, "k": k, "v": v, "u": u,
+                      "size_2d": (hh, ww), "out": m(q, k, v, u, (hh, ww))[0]}
+        # sine position embedding  position.py:49-74
+        from networks.layers.position import PositionEmbeddingSine
+        pe = PositionEmbeddingSine(128, normalize=True)
+        out["pos"] = {"h": 11, "w": 16, "out": pe(torch.zeros(1, 1, 11, 16))}
+    # oracle pin on the op vectors
+    W = {"p." + k: v for k, v in out["k1"]["sd"].items()}
+    o = O._lin(O.multihead_attention(out["k1"]["Q"], out["k1"]["K"], out["k1"]["V"], 8), W, "p.projection")
+    print("[ops] k1 oracle pin", (o - out["k1"]["out"]).abs().max().item())
+    c = out["k2"]
+    core = O.local_attention(c["q"], c["k"], c["v"], c["sd"]["relative_emb_k.weight"], c["sd"]["relative_emb_k.bias"],
+                             c["sd"]["relative_emb_v"], 8)
+    o = F.linear(core, c["sd"]["projection.weight"], c["sd"]["projection.bias"])
+    print("[ops] k2 oracle pin", (o - c["out"]).abs().max().item())
+    c = out["k1p"]
+    o, _ = O.gated_propagation({"p." + k: v for k, v in c["sd"].items()}, "p.", c["Q"], c["K"], c["V"], c["U"],
+                               c["size_2d"], False)
+    print("[ops] k1' oracle pin", (o - c["out"]).abs().max().item())
+    c = out["k2p"]
+    o, _ = O.local_gated_propagation({"p." + k: v for k, v in c["sd"].items()}, "p.", c["q"], c["k"], c["v"], c["u"],
+                                     c["size_2d"])
+    print("[ops] k2' oracle pin", (o - c["out"]).abs().max().item())
+    print("[ops] pos oracle pin", (O.pos_emb_sine(11, 16) - out["pos"]["out"]).abs().max().item())
+    torch.save(out, os.path.join(out_dir, "ops_attention.pt"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(REPO, "tests", "golden"))
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    os.makedirs(a.out, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    if a.only in (None, "ops"):
+        op_cases(a.out)
+    for name in VIDEO_CASES:
+        if a.only in (None, name):
+            video_case(name, a.out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,70 @@
+"""Deterministic weight sets for parity tests (TEST INFRASTRUCTURE ONLY, see aot_oracle.py).
+
+No checkpoints or datasets are available offline, so parity uses seeded random
+weights in two flavours:
+
+* ``raw``        -- the product model's own seeded init (same distributions as the reference).
+* ``calibrated`` -- SURVEY Appendix E recipe: encoder_projector rescaled to ~unit-std tokens,
+  ID bank x100, ``linear_Q`` scaled so long-term attention is sharp (entropy well below
+  log Tk), plus randomised FrozenBN statistics so BN folding is actually exercised.  With raw
+  weights the logits are insensitive to attention errors; with these they are not.
+
+Every step is element-wise RNG / fixed constants (no LAPACK, no measured statistics), so the
+same seed gives bit-identical weights on every machine; ``checksum`` lets tests assert that.
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Dict
+
+import torch
+
+# fixed calibration constants (measured once in the build container through the oracle and
+# frozen here so weights do not depend on the machine): projector-output std under raw init
+_PROJ_STD = {"resnet50": 9.0, "mobilenetv2": 0.016}
+
+
+def build_state_dict(model_name: str, seed: int = 0, flavour: str = "calibrated",
+                     q_scale: float = 4.0, id_scale: float = 100.0) -> Dict[str, torch.Tensor]:
+    from aot_benchmark_b200 import EngineConfig, build_vos_model
+
+    cfg = EngineConfig("golden", model_name)
+    torch.manual_seed(seed)
+    model = build_vos_model(cfg.MODEL_VOS, cfg)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    if flavour == "raw":
+        return sd
+    g = torch.Generator().manual_seed(seed + 7919)
+    for k in list(sd.keys()):
+        if k.endswith("running_var"):
+            n = sd[k].numel()
+            # keep the composite BN scale weight/sqrt(var+eps) in [0.8, 1.25]: activations stay O(1)
+            sd[k] = 0.7 + 0.6 * torch.rand(n, generator=g)
+            base = k[: -len("running_var")]
+            sd[base + "running_mean"] = 0.1 * torch.randn(n, generator=g)
+            sd[base + "weight"] = 0.9 + 0.2 * torch.rand(n, generator=g)
+            sd[base + "bias"] = 0.05 * torch.randn(n, generator=g)
+    s = 1.0 / _PROJ_STD[cfg.MODEL_ENCODER]
+    sd["encoder_projector.weight"] = sd["encoder_projector.weight"] * s
+    sd["encoder_projector.bias"] = sd["encoder_projector.bias"] * s
+    sd["patch_wise_id_bank.weight"] = sd["patch_wise_id_bank.weight"] * id_scale
+    for i in range(cfg.MODEL_LSTT_NUM):
+        p = f"LSTT.layers.{i}."
+        if cfg.MODEL_VOS == "aot":
+            sd[p + "linear_Q.weight"] = sd[p + "linear_Q.weight"] * q_scale
+            sd[p + "linear_Q.bias"] = sd[p + "linear_Q.bias"] * q_scale
+            # zero-initialised in the reference (attention.py:281-285) but xavier'd by the block's
+            # _init_weight (transformer.py:369-372): keep it non-zero so the emb_v path is tested
+        else:
+            d_att = cfg.MODEL_ENCODER_EMBEDDING_DIM // 2
+            sd[p + "linear_QV.weight"][:d_att] *= q_scale
+            sd[p + "linear_QV.bias"][:d_att] *= q_scale
+    return sd
+
+
+def checksum(sd: Dict[str, torch.Tensor]) -> str:
+    h = hashlib.sha256()
+    for k in sorted(sd.keys()):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()[:16]

@@ -1,0 +1,122 @@
+"""CPU: the oracle restatement vs the golden vectors produced by the REAL reference
+(oracle/gen_golden.py).  This is the pin SURVEY 8(c) asks for."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import aot_oracle as O
+from oracle import weights as OW
+
+VIDEO = ["aott_256", "aott_raw_257", "r50_aotl_small", "r50_deaotl_small", "deaott_small"]
+
+
+@pytest.fixture(scope="module")
+def ops(golden_dir):
+    return torch.load(os.path.join(golden_dir, "ops_attention.pt"))
+
+
+def test_k1_long_term_attention(ops):
+    c = ops["k1"]
+    W = {"p." + k: v for k, v in c["sd"].items()}
+    o = O._lin(O.multihead_attention(c["Q"], c["K"], c["V"], 8), W, "p.projection")
+    assert (o - c["out"]).abs().max().item() < 1e-5
+
+
+def test_k3_self_attention(ops):
+    c = ops["k3"]
+    W = {"p." + k: v for k, v in c["sd"].items()}
+    X = c["X"]
+    core = O.multihead_attention(O._lin(X, W, "p.linear_Q"), O._lin(X, W, "p.linear_K"), O._lin(X, W, "p.linear_V"), 8)
+    assert (O._lin(core, W, "p.projection") - c["out"]).abs().max().item() < 1e-5
+
+
+def test_k2_local_attention(ops):
+    c = ops["k2"]
+    s = O.local_window_scores(c["q"], c["k"], c["sd"]["relative_emb_k.weight"], c["sd"]["relative_emb_k.bias"], 8)
+    p = torch.softmax(s, dim=2)
+    h, w = c["q"].shape[-2:]
+    assert (p.reshape(1, 8, 225, h * w) - c["attn"]).abs().max().item() < 1e-6
+    core = O.local_window_aggregate(p, c["v"], 8, c["sd"]["relative_emb_v"])
+    o = F.linear(core, c["sd"]["projection.weight"], c["sd"]["projection.bias"])
+    assert (o - c["out"]).abs().max().item() < 1e-5
+
+
+def test_k1p_gated_propagation(ops):
+    c = ops["k1p"]
+    o, _ = O.gated_propagation({"p." + k: v for k, v in c["sd"].items()}, "p.", c["Q"], c["K"], c["V"], c["U"],
+                               c["size_2d"], False)
+    assert (o - c["out"]).abs().max().item() < 1e-5
+
+
+def test_k2p_local_gated_propagation(ops):
+    c = ops["k2p"]
+    o, _ = O.local_gated_propagation({"p." + k: v for k, v in c["sd"].items()}, "p.", c["q"], c["k"], c["v"],
+                                     c["u"], c["size_2d"])
+    assert (o - c["out"]).abs().max().item() < 1e-5
+
+
+def test_sine_position_embedding(ops):
+    c = ops["pos"]
+    assert (O.pos_emb_sine(c["h"], c["w"]) - c["out"]).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("name", VIDEO)
+def test_video_vs_reference_golden(name, golden_dir):
+    """End-to-end: reference engine outputs (stored) vs oracle engine, teacher-forced."""
+    g = torch.load(os.path.join(golden_dir, f"video_{name}.pt"))
+    sd = OW.build_state_dict(g["model"], seed=g["seed"], flavour=g["flavour"])
+    assert OW.checksum(sd) == g["weights_checksum"], "seeded weights are not reproducible on this machine"
+    frames, mask = O.synthetic_video(g["frames"], g["H"], g["W"], g["objs"], seed=1234 + g["seed"])
+    eng = O.OracleEngine(sd, O.OracleConfig(g["model"]), long_term_mem_gap=g["gap"])
+    forced = [l.float() for l in g["ref_labels"]]
+    with torch.no_grad():
+        lo, labels = O.run_video(eng, frames, mask, g["objs"], tuple(g["out_size"]), forced_masks=forced)
+    n = g["objs"] + 1
+    for a, b in zip(lo, g["ref_logits_lo"]):
+        assert (a[:, :n] - b[:, :n]).abs().max().item() < 1e-4
+    mism = sum((a.to(torch.uint8) != b).sum().item() for a, b in zip(labels, g["ref_labels"]))
+    total = sum(b.numel() for b in g["ref_labels"])
+    assert mism <= 1e-4 * total  # fp32 summation-order ties only
+
+
+def test_float64_oracle_close_to_float32():
+    """The fp64 truth used to size tolerances must agree with the fp32 restatement."""
+    sd = OW.build_state_dict("aott", seed=1)
+    frames, mask = O.synthetic_video(2, 65, 81, 2, seed=5)
+    outs = []
+    for dt in (torch.float32, torch.float64):
+        e = O.OracleEngine(sd, O.OracleConfig("aott"), dtype=dt)
+        with torch.no_grad():
+            e.add_reference_frame(frames[0], mask, [2], 0)
+            e.match_propogate_one_frame(frames[1])
+            outs.append(e.decode_current_logits((65, 81))[:, :3].double())
+    assert (outs[0] - outs[1]).abs().max().item() < 1e-4
+
+
+@pytest.mark.reference
+def test_state_dict_contract_against_reference():
+    """Our parameter trees expose exactly the reference's state_dict keys/shapes."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, "/root/reference"); sys.path.insert(0, "%s")
+import networks.layers.transformer as T, networks.layers.attention as A
+T.MultiheadLocalAttentionV3 = A.MultiheadLocalAttentionV2
+from configs.default import DefaultEngineConfig
+from networks.models import build_vos_model as ref_build
+from aot_benchmark_b200 import build_vos_model, EngineConfig
+for m in ["aott", "r50_aotl", "deaott", "r50_deaotl"]:
+    rc = DefaultEngineConfig("x", m); mc = EngineConfig("x", m)
+    a = {k: tuple(v.shape) for k, v in ref_build(rc.MODEL_VOS, rc).state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in build_vos_model(mc.MODEL_VOS, mc).state_dict().items()}
+    assert a == b, m
+    for k, v in mc.__dict__.items():
+        if k not in ("EXP_NAME", "MODEL_NAME"):
+            assert getattr(rc, k) == v, (m, k)
+print("OK")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
