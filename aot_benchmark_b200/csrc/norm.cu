@@ -1,0 +1,165 @@
+// LayerNorm over channels and GroupNorm over (pixels x channels-in-group), NHWC fp32.
+//
+// Reference sites: nn.LayerNorm(256) norm1/norm2/norm3, decoder_norms, id_norm*
+// (transformer.py:274,293,297,85-93,530,537,565-566; deaot.py:39,53); with_pos_embed
+// (transformer.py:305-310,322: q = k = LN(x) + pos -> emitted as a second output here);
+// GroupNorm(32,1024)+GELU of the FFN (basic.py:18,30-32), GroupNorm(8,C)+ReLU of ConvGN
+// (basic.py:75-85, fpn.py:41-56), GroupNorm1D(512, groups=2) (basic.py:6-12, transformer.py:197-200).
+// eps = 1e-5 everywhere (PyTorch default).
+//
+// GroupNorm statistics are reduced deterministically (fixed partial layout, double precision
+// partials) so replicated ranks stay bit-identical.
+#include "common.cuh"
+
+namespace aotb {
+
+// one warp per row; C % 4 == 0; C <= 4096
+__global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, const float* __restrict__ add, int ldadd,
+                                 float* __restrict__ out, int ldo, float* __restrict__ out2, int ldo2, int rows,
+                                 int C, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float* xr = x + (size_t)warp * ldx;
+    float s = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(xr + c);
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+    s = warp_sum(s);
+    const float mean = s / (float)C;
+    float q = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(xr + c);
+        float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+        q += (a * a + b * b) + (cc * cc + d * d);
+    }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(xr + c);
+        float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float4 o;
+        o.x = (v.x - mean) * rstd * g.x + b.x;
+        o.y = (v.y - mean) * rstd * g.y + b.y;
+        o.z = (v.z - mean) * rstd * g.z + b.z;
+        o.w = (v.w - mean) * rstd * g.w + b.w;
+        *reinterpret_cast<float4*>(out + (size_t)warp * ldo + c) = o;
+        if (out2) {
+            float4 p = __ldg(reinterpret_cast<const float4*>(add + (size_t)warp * ldadd + c));
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            *reinterpret_cast<float4*>(out2 + (size_t)warp * ldo2 + c) = o;
+        }
+    }
+}
+
+// ---- GroupNorm, stage 1: partial (sum, sumsq) per (b, g, chunk) in double
+// x [B][P][ldx] (P pixels), group g covers channels [g*Cg, (g+1)*Cg)
+constexpr int GN_CHUNKS = 64;
+
+__global__ void groupnorm_stats_kernel(const float* __restrict__ x, int ldx, int P, int G, int Cg,
+                                       double* __restrict__ partial) {
+    const int chunk = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+    const int per = (P + GN_CHUNKS - 1) / GN_CHUNKS;
+    const int p0 = chunk * per, p1 = min(P, p0 + per);
+    const float* xb = x + (size_t)b * P * ldx + (size_t)g * Cg;
+    const int Cg4 = Cg >> 2;
+    float s = 0.f, q = 0.f;
+    const int n = (p1 > p0 ? (p1 - p0) : 0) * Cg4;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int p = p0 + i / Cg4, c = (i % Cg4) * 4;
+        float4 v = *reinterpret_cast<const float4*>(xb + (size_t)p * ldx + c);
+        s += (v.x + v.y) + (v.z + v.w);
+        q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    __shared__ double sh[2][8];
+    double ds = (double)warp_sum(s), dq = (double)warp_sum(q);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][wid] = ds; sh[1][wid] = dq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, c = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; c += sh[1][w]; }
+        double* o = partial + (((size_t)b * G + g) * GN_CHUNKS + chunk) * 2;
+        o[0] = a; o[1] = c;
+    }
+}
+
+// ---- stage 2: normalise + affine + activation
+__global__ void groupnorm_apply_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const double* __restrict__ partial,
+                                       float* __restrict__ out, int ldo, int P, int C, int G, int Cg, int act,
+                                       float eps) {
+    extern __shared__ float stat[];  // [G][2] mean, rstd for this batch element
+    const int b = blockIdx.y;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const double* pp = partial + ((size_t)b * G + g) * GN_CHUNKS * 2;
+        double s = 0, q = 0;
+        for (int c = 0; c < GN_CHUNKS; ++c) { s += pp[2 * c]; q += pp[2 * c + 1]; }
+        const double n = (double)P * Cg;
+        const double mean = s / n;
+        double var = q / n - mean * mean;
+        if (var < 0) var = 0;
+        stat[2 * g] = (float)mean;
+        stat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const int C4 = C >> 2;
+    const size_t total = (size_t)P * C4;
+    const float* xb = x + (size_t)b * P * ldx;
+    float* ob = out + (size_t)b * P * ldo;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int p = i / C4, c = (i - (size_t)p * C4) * 4;
+        const int g = c / Cg;
+        const float mean = stat[2 * g], rstd = stat[2 * g + 1];
+        float4 v = *reinterpret_cast<const float4*>(xb + (size_t)p * ldx + c);
+        float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float4 o;
+        o.x = apply_act((v.x - mean) * rstd * ga.x + be.x, act);
+        o.y = apply_act((v.y - mean) * rstd * ga.y + be.y, act);
+        o.z = apply_act((v.z - mean) * rstd * ga.z + be.z, act);
+        o.w = apply_act((v.w - mean) * rstd * ga.w + be.w, act);
+        *reinterpret_cast<float4*>(ob + (size_t)p * ldo + c) = o;
+    }
+}
+
+}  // namespace aotb
+
+using namespace aotb;
+
+extern "C" int aotb_layernorm_f32(const float* x, int ldx, const float* gamma, const float* beta, const float* add,
+                                  int ldadd, float* out, int ldo, float* out2, int ldo2, int rows, int C,
+                                  void* stream) {
+    AOTB_REQUIRE(x && gamma && beta && out && rows > 0, "aotb_layernorm_f32: bad args");
+    AOTB_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "aotb_layernorm_f32: C/ld must be %%4");
+    AOTB_REQUIRE(!out2 || (add && ldadd % 4 == 0 && ldo2 % 4 == 0), "aotb_layernorm_f32: out2 needs add");
+    const int warps_per_block = 8;
+    layernorm_kernel<<<cdiv(rows, warps_per_block), warps_per_block * 32, 0, (cudaStream_t)stream>>>(
+        x, ldx, gamma, beta, add, ldadd, out, ldo, out2, ldo2, rows, C, 1e-5f);
+    return check_launch("aotb_layernorm_f32");
+}
+
+extern "C" size_t aotb_groupnorm_workspace_bytes(int B, int G) {
+    return (size_t)B * G * GN_CHUNKS * 2 * sizeof(double);
+}
+
+extern "C" int aotb_groupnorm_nhwc_f32(const float* x, int ldx, const float* gamma, const float* beta, float* out,
+                                       int ldo, int B, int P, int C, int G, int act, void* workspace,
+                                       void* stream) {
+    AOTB_REQUIRE(x && gamma && beta && out && workspace, "aotb_groupnorm_nhwc_f32: null pointer");
+    AOTB_REQUIRE(G > 0 && C % G == 0 && (C / G) % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && G <= 1024,
+                 "aotb_groupnorm_nhwc_f32: unsupported channel/group configuration");
+    const int Cg = C / G;
+    cudaStream_t st = (cudaStream_t)stream;
+    groupnorm_stats_kernel<<<dim3(GN_CHUNKS, G, B), 256, 0, st>>>(x, ldx, P, G, Cg, (double*)workspace);
+    const size_t total = (size_t)P * (C / 4);
+    int gx = (int)((total + 255) / 256);
+    if (gx > 148 * 8) gx = 148 * 8;
+    groupnorm_apply_kernel<<<dim3(gx, B), 256, 2 * G * sizeof(float), st>>>(x, ldx, gamma, beta,
+                                                                             (const double*)workspace, out, ldo, P, C,
+                                                                             G, Cg, act, 1e-5f);
+    return check_launch("aotb_groupnorm_nhwc_f32", 2);
+}

@@ -1,0 +1,812 @@
+"""Drop-in eval engines: the reference's protocol, executed by the sm_100a kernels.
+
+Mirrors networks/engines/aot_engine.py (AOTEngine :13-482, AOTInferEngine :485-635) and
+networks/engines/deaot_engine.py (DeAOTEngine :9-56, DeAOTInferEngine :59-94): same class and
+method names, arguments, state attributes and error behaviour, so networks/managers/evaluator.py
+and tools/demo.py drive it unedited.  Differences are internal:
+
+* activations live in NHWC / token-major fp32 buffers allocated once per video;
+* the long-term memory is a pre-allocated append buffer (bank) instead of torch.cat'ed tensors
+  (new frames are appended, not prepended -- attention is permutation invariant over keys);
+* every FLOP of the per-frame path runs in libaotb200.so; there is no eager fallback and the
+  engines refuse CPU tensors.
+
+Training (AOTEngine.forward, aot_engine.py:33-108) is a "next" row of SURVEY 8(f) and raises.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .plan import get_plan
+
+A_NONE, A_RELU, A_GELU, A_SILU, A_RELU6 = ops.ACT_NONE, ops.ACT_RELU, ops.ACT_GELU, ops.ACT_SILU, ops.ACT_RELU6
+
+# bench.py hook: when set to a list, every long-term attention launch appends
+# (start_event, end_event, algorithmic_flops) so the roofline is measured live, per launch.
+LT_PROBE = None
+LT_KERNEL_NAME = "attn_f32_kernel<32,32> (fp32 SIMT flash attention)"
+
+
+def _pos_emb_sine(h, w, npf=128):
+    """networks/layers/position.py:49-74 (normalize=True, scale=2*pi, T=1e4), as a host-computed
+    constant table [h*w, 2*npf] (computed once per video, aot_engine.py:225-228)."""
+    y = torch.arange(h, dtype=torch.float32).view(h, 1).expand(h, w)
+    x = torch.arange(w, dtype=torch.float32).view(1, w).expand(h, w)
+    eps = 1e-6
+    y = y / (y[-1:, :] + eps) * (2 * math.pi)
+    x = x / (x[:, -1:] + eps) * (2 * math.pi)
+    dim_t = torch.arange(npf, dtype=torch.float32)
+    dim_t = 10000 ** (2 * (dim_t // 2) / npf)
+    px = x[:, :, None] / dim_t
+    py = y[:, :, None] / dim_t
+    px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=3).flatten(2)
+    py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), dim=3).flatten(2)
+    return torch.cat((py, px), dim=2).reshape(h * w, 2 * npf).contiguous()
+
+
+class EncEmbs(list):
+    """``curr_enc_embs``: list of NCHW feature views [4x, 8x, 16x, 16x-projected] like the reference
+    (aot.py:81-84) plus the NHWC tensors the kernels use (``.nhwc``)."""
+    nhwc = None
+
+
+# =====================================================================================
+# image encoder (shared by all sub-engines of an infer engine)
+# =====================================================================================
+class _Encoder:
+    def __init__(self, plan, H, W):
+        self.plan = plan
+        self.H, self.W = H, W
+        dev = plan.device
+        self.bufs = {}
+        self.dev = dev
+
+    def _buf(self, key, shape):
+        b = self.bufs.get(key)
+        if b is None or tuple(b.shape) != tuple(shape):
+            b = torch.empty(shape, dtype=torch.float32, device=self.dev)
+            self.bufs[key] = b
+        return b
+
+    @staticmethod
+    def _osz(n, k, s, p, d=1):
+        return (n + 2 * p - d * (k - 1) - 1) // s + 1
+
+    def __call__(self, img, st):
+        P = self.plan
+        if img.dim() != 4 or img.shape[0] != 1 or img.shape[1] != 3:
+            raise ValueError("expected an image tensor [1,3,H,W]")
+        H, W = img.shape[2], img.shape[3]
+        x = self._buf("in", (1, H, W, 3))
+        ops.nchw_to_nhwc(img.float(), x, stream=st)
+        if P.encoder_name == "resnet50":
+            feats = self._resnet(x, st)
+        else:
+            feats = self._mobilenet(x, st)
+        f16 = feats[-1]
+        proj = self._buf("proj", (1, f16.shape[1], f16.shape[2], P.C))
+        ops.conv2d(f16, P.proj.w, P.proj.b, proj, stream=st)
+        nhwc = [feats[0], feats[1], feats[2], proj]
+        out = EncEmbs(t.permute(0, 3, 1, 2) for t in nhwc)
+        out.nhwc = nhwc
+        return out
+
+    def _resnet(self, x, st):
+        e = self.plan.enc
+        H, W = x.shape[1], x.shape[2]
+        h1, w1 = self._osz(H, 7, 2, 3), self._osz(W, 7, 2, 3)
+        c1 = self._buf("stem", (1, h1, w1, 64))
+        ops.conv2d(x, e.stem.w, e.stem.b, c1, KH=7, KW=7, stride=2, pad=3, act=A_RELU, stream=st)
+        h, w = self._osz(h1, 3, 2, 1), self._osz(w1, 3, 2, 1)
+        cur = self._buf("pool", (1, h, w, 64))
+        ops.maxpool3x3s2(c1, cur, stream=st)
+        feats = []
+        for si, blocks in enumerate(e.stages):
+            for bi, b in enumerate(blocks):
+                ho, wo = self._osz(h, 3, b.stride, 1), self._osz(w, 3, b.stride, 1)
+                t1 = self._buf(f"s{si}b{bi}t1", (1, h, w, b.c1.cout))
+                ops.conv2d(cur, b.c1.w, b.c1.b, t1, act=A_RELU, stream=st)
+                t2 = self._buf(f"s{si}b{bi}t2", (1, ho, wo, b.c2.cout))
+                ops.conv2d(t1, b.c2.w, b.c2.b, t2, KH=3, KW=3, stride=b.stride, pad=1, act=A_RELU, stream=st)
+                if b.down is not None:
+                    res = self._buf(f"s{si}ds", (1, ho, wo, b.down.cout))
+                    ops.conv2d(cur, b.down.w, b.down.b, res, stride=b.stride, stream=st)
+                else:
+                    res = cur
+                out = self._buf(f"s{si}o{bi % 2}", (1, ho, wo, b.c3.cout))
+                ops.conv2d(t2, b.c3.w, b.c3.b, out, res=res, act=A_RELU, stream=st)
+                cur, h, w = out, ho, wo
+            feats.append(cur)
+        return feats
+
+    def _mobilenet(self, x, st):
+        e = self.plan.enc
+        H, W = x.shape[1], x.shape[2]
+        h, w = self._osz(H, 3, 2, 1), self._osz(W, 3, 2, 1)
+        cur = self._buf("stem", (1, h, w, 32))
+        ops.conv2d(x, e.stem.w, e.stem.b, cur, KH=3, KW=3, stride=2, pad=1, act=A_RELU6, stream=st)
+        feats = []
+        for i, b in enumerate(e.blocks):
+            y = cur
+            if b.expand is not None:
+                t = self._buf(f"b{i}e", (1, h, w, b.expand.cout))
+                ops.conv2d(y, b.expand.w, b.expand.b, t, act=A_RELU6, stream=st)
+                y = t
+            pad = b.dil  # (3-1)//2*dil, mobilenetv2.py:41-42
+            ho, wo = self._osz(h, 3, b.stride, pad, b.dil), self._osz(w, 3, b.stride, pad, b.dil)
+            t = self._buf(f"b{i}d", (1, ho, wo, b.dw.cout))
+            ops.dwconv(y, b.dw.w, b.dw.b, t, K=3, stride=b.stride, pad=pad, dil=b.dil, act=A_RELU6, stream=st)
+            o = self._buf(f"b{i}o", (1, ho, wo, b.pw.cout))
+            ops.conv2d(t, b.pw.w, b.pw.b, o, res=cur if b.res else None, stream=st)
+            cur, h, w = o, ho, wo
+            if b.tap:
+                feats.append(cur)
+        last = self._buf("last", (1, h, w, e.last.cout))
+        ops.conv2d(cur, e.last.w, e.last.b, last, act=A_RELU6, stream=st)
+        feats.append(last)
+        return feats
+
+
+# =====================================================================================
+# single engine (<= max_obj_num objects)
+# =====================================================================================
+class AOTEngine(nn.Module):
+    def __init__(self, aot_model, gpu_id=0, long_term_mem_gap=9999, short_term_mem_skip=1):
+        super().__init__()
+        self.cfg = aot_model.cfg
+        self.align_corners = aot_model.cfg.MODEL_ALIGN_CORNERS
+        self.AOT = aot_model
+        self.max_obj_num = aot_model.max_obj_num
+        self.gpu_id = gpu_id
+        self.long_term_mem_gap = long_term_mem_gap
+        self.short_term_mem_skip = short_term_mem_skip
+        self.losses = None
+        self._enc = None
+        self._ws = None
+        self._P = None
+        self.restart_engine()
+
+    # ------------------------------------------------------------------ protocol
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("training step (BASELINE config 5) is a 'next' row (SURVEY 8f); the B200 engine "
+                                  "implements the eval protocol")
+
+    def restart_engine(self, batch_size=1, enable_id_shuffle=False):
+        if batch_size != 1 or enable_id_shuffle:
+            raise NotImplementedError("batch_size > 1 / id shuffle are training-only (SURVEY 8f)")
+        self.batch_size = 1
+        self.frame_step = 0
+        self.last_mem_step = -1
+        self.enable_id_shuffle = False
+        self.freeze_id = False
+        self.obj_nums = None
+        self.pos_emb = None
+        self.enc_size_2d = None
+        self.enc_hw = None
+        self.input_size_2d = None
+        self.bank_len = 0
+        self.enable_offline_enc = False
+        self.curr_enc_embs = None
+        self.curr_id_embs = None
+        self.pred_id_logits = None
+        self._have_lstt = False
+
+    def update_size(self, input_size, enc_size):
+        self.input_size_2d = tuple(int(s) for s in input_size)
+        self.enc_size_2d = tuple(int(s) for s in enc_size)
+        self.enc_hw = self.enc_size_2d[0] * self.enc_size_2d[1]
+
+    # ------------------------------------------------------------------ buffers
+    def _plan(self):
+        # resolved once per reference frame (get_plan walks every parameter to detect reloads)
+        if self._P is None:
+            self._P = get_plan(self.AOT)
+        return self._P
+
+    def _alloc(self):
+        P = self._plan()
+        dev = P.device
+        N = self.enc_hw
+        C = P.C
+        L = P.L
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        ws = type("WS", (), {})()
+        ws.N = N
+        ws.gn_ws = ops.groupnorm_workspace(1, 32, dev)
+        ws.id_emb = f(N, C)
+        if not P.deaot:
+            ws.x = f(N, C)
+            ws.ln = f(N, C)
+            ws.ln_pos = f(N, C)
+            ws.qk = f(N, 2 * C)
+            ws.v = f(N, C)
+            ws.core = f(N, 2 * C)
+            ws.tmp = f(N, C)
+            ws.ff = f(N, 4 * C)
+            ws.ff2 = f(N, 4 * C)
+            ws.cat = f(N, (L + 1) * C)
+            self.curr_Q = [f(N, C) for _ in range(L)]
+            self.curr_V = [f(N, C) for _ in range(L)]
+            self.st_K = [f(N, C) for _ in range(L)]
+            self.st_V = [f(N, C) for _ in range(L)]
+            self._kdim, self._vdim = C, C
+        else:
+            d = C // 2
+            ws.xz = f(N, 2 * C)
+            ws.ln = f(N, C)
+            ws.qv = f(N, d + 2 * C)
+            ws.catU = f(N, 4 * C)
+            ws.idin = f(N, 2 * C)
+            ws.core = f(N, 4 * C)
+            ws.gated = f(N, 4 * C)
+            ws.dw = f(N, 8 * C)
+            ws.c = f(N, 2 * C)
+            ws.sa_qk = f(N, d)
+            ws.sa_v = f(N, 4 * C)
+            ws.sa_u = f(N, 4 * C)
+            ws.cat = f(N, 2 * C)
+            self.curr_Q = [f(N, d) for _ in range(L)]
+            self.curr_V = [f(N, 2 * C) for _ in range(L)]
+            self.curr_IDV = [None] + [f(N, C) for _ in range(L - 1)]
+            self.st_K = [f(N, d) for _ in range(L)]
+            self.st_V = [f(N, 4 * C) for _ in range(L)]   # cat[V | ID_V] (transformer.py:625-626)
+            self._kdim, self._vdim = d, 4 * C
+        cap = 4 * N
+        self.bank_cap = cap
+        self.bank_K = [f(cap, self._kdim) for _ in range(L)]
+        self.bank_V = [f(cap, self._vdim) for _ in range(L)]
+        self.bank_len = 0
+        self._st_ring = []
+        self._ws = ws
+        self._dec_bufs = {}
+
+    def _bank_reserve(self, rows):
+        if self.bank_len + rows <= self.bank_cap:
+            return
+        new_cap = max(2 * self.bank_cap, self.bank_len + rows)
+        for lst in (self.bank_K, self.bank_V):
+            for i, old in enumerate(lst):
+                nb = torch.empty((new_cap, old.shape[1]), dtype=torch.float32, device=old.device)
+                nb[: self.bank_len].copy_(old[: self.bank_len])
+                lst[i] = nb
+        self.bank_cap = new_cap
+
+    # ------------------------------------------------------------------ reference-shaped views
+    @property
+    def long_term_memories(self):
+        if self.bank_len == 0:
+            return None
+        P = self._plan()
+        n = self.bank_len
+        out = []
+        for li in range(P.L):
+            K = self.bank_K[li][:n].unsqueeze(1)
+            V = self.bank_V[li][:n]
+            if P.deaot:
+                c2 = 2 * P.C
+                out.append([K, V[:, :c2].unsqueeze(1), None, V[:, c2:].unsqueeze(1)])
+            else:
+                out.append([K, V.unsqueeze(1)])
+        return out
+
+    @property
+    def short_term_memories(self):
+        if not self._have_lstt:
+            return None
+        P = self._plan()
+        h, w = self.enc_size_2d
+        to2d = lambda t: t.view(h, w, 1, -1).permute(2, 3, 0, 1)
+        out = []
+        for li in range(P.L):
+            if P.deaot:
+                c2 = 2 * P.C
+                out.append([to2d(self.st_K[li]), to2d(self.st_V[li][:, :c2]), None, to2d(self.st_V[li][:, c2:])])
+            else:
+                out.append([to2d(self.st_K[li]), to2d(self.st_V[li])])
+        return out
+
+    # ------------------------------------------------------------------ steps
+    def _encode(self, img, st):
+        if self._enc is None:
+            self._enc = _Encoder(self._plan(), img.shape[2], img.shape[3])
+        self._enc.plan = self._plan()
+        return self._enc(img, st)
+
+    def _check_img(self, img):
+        if not img.is_cuda:
+            raise RuntimeError("aot_benchmark_b200 engines run on CUDA tensors only (there is no CPU path)")
+
+    def assign_identity_from_mask(self, mask, st):
+        """one_hot_mask + get_id_emb (aot_engine.py:168-179) fused as a gather (K4)."""
+        P = self._plan()
+        ws = self._ws
+        if mask.dim() == 4 and mask.shape[1] != 1:
+            # probability / one-hot input [1, 11, H, W]: dense conv through the same weight table
+            x = torch.empty((1, mask.shape[2], mask.shape[3], mask.shape[1]), dtype=torch.float32, device=mask.device)
+            ops.nchw_to_nhwc(mask.float().contiguous(), x, stream=st)
+            ops.conv2d(x, P.id_wt, P.id_b, ws.id_emb.view(1, *self.enc_size_2d, P.C), KH=P.id_k, KW=P.id_k,
+                       stride=P.id_stride, pad=P.id_pad, stream=st)
+            if P.deaot:
+                ops.layernorm(ws.id_emb, P.id_norm[0], P.id_norm[1], ws.id_emb, stream=st)
+            return ws.id_emb
+        m2 = mask.reshape(mask.shape[-2], mask.shape[-1]).float().contiguous()
+        ops.id_embed(m2, P.id_wt, P.id_b, ws.id_emb, P.C, P.nid, P.id_k, P.id_stride, P.id_pad,
+                     ln_gamma=P.id_norm[0] if P.deaot else None, ln_beta=P.id_norm[1] if P.deaot else None, stream=st)
+        return ws.id_emb
+
+    def add_reference_frame(self, img=None, mask=None, frame_step=-1, obj_nums=None, img_embs=None):
+        if self.obj_nums is None and obj_nums is None:
+            print('No objects for reference frame!')
+            exit()
+        elif obj_nums is not None:
+            self.obj_nums = obj_nums
+        if frame_step == -1:
+            frame_step = self.frame_step
+        if img_embs is None and img is None:
+            print('No image for reference frame!')
+            exit()
+        if mask is None:
+            print('No mask for reference frame!')
+            exit()
+        st = torch.cuda.current_stream().cuda_stream
+        self._P = get_plan(self.AOT)   # picks up load_state_dict / .to() done since the last video
+        if img_embs is None:
+            self._check_img(img)
+            img_embs = self._encode(img, st)
+        if self.input_size_2d is None:
+            f16 = img_embs.nhwc[-1]
+            in_size = img.shape[2:] if img is not None else (f16.shape[1] * 16, f16.shape[2] * 16)
+            self.update_size(in_size, (f16.shape[1], f16.shape[2]))
+            self._alloc()
+        self.curr_enc_embs = img_embs
+        if self.pos_emb is None:
+            self.pos_emb = _pos_emb_sine(*self.enc_size_2d, npf=self._plan().C // 2).to(self._plan().device)
+        id_emb = self.assign_identity_from_mask(mask, st)
+        self.curr_id_embs = id_emb
+        self._lstt_forward(img_embs, id_emb, st)
+        # lstt_long_memories of a reference frame = its own fused K/V (transformer.py:337-341)
+        self._append_short_to_bank(st)
+        self.last_mem_step = self.frame_step
+        self._have_lstt = True
+
+    def match_propogate_one_frame(self, img=None, img_embs=None):
+        self.frame_step += 1
+        st = torch.cuda.current_stream().cuda_stream
+        if img_embs is None:
+            self._check_img(img)
+            img_embs = self._encode(img, st)
+        self.curr_enc_embs = img_embs
+        self._lstt_forward(img_embs, None, st)
+
+    def update_short_term_memory(self, curr_mask, curr_id_emb=None, skip_long_term_update=False):
+        st = torch.cuda.current_stream().cuda_stream
+        id_emb = self.assign_identity_from_mask(curr_mask, st) if curr_id_emb is None else curr_id_emb
+        self._fuse_memories(id_emb, st)
+        if self.frame_step - self.last_mem_step >= self.long_term_mem_gap:
+            if not skip_long_term_update:
+                self._append_short_to_bank(st)
+            self.last_mem_step = self.frame_step
+
+    def _append_short_to_bank(self, st):
+        N = self.enc_hw
+        self._bank_reserve(N)
+        K_src, V_src = self._latest_kv()
+        for li in range(self._plan().L):
+            ops.bank_append(K_src[li], self.bank_K[li], self.bank_len, stream=st)
+            ops.bank_append(V_src[li], self.bank_V[li], self.bank_len, stream=st)
+        self.bank_len += N
+
+    def _latest_kv(self):
+        return self._new_K, self._new_V
+
+    # ------------------------------------------------------------------ LSTT (AOT)
+    def _lstt_forward(self, embs, id_emb, st):
+        P = self._plan()
+        ws = self._ws
+        N, C, H = self.enc_hw, P.C, P.H
+        h, w = self.enc_size_2d
+        d = C // H
+        proj = embs.nhwc[-1].view(N, C)
+        ops.eltwise(ops.EW_COPY, proj, None, ws.x, stream=st)
+        ops.eltwise(ops.EW_COPY, proj, None, ws.cat[:, :C], stream=st)
+        x = ws.x
+        is_ref = id_emb is not None
+        if is_ref:
+            stK, stV = self._next_short_slot()
+        else:
+            stK, stV = self.st_K, self.st_V
+        for li in range(P.L):
+            Lw = P.layers[li]
+            # 1) self-attention (transformer.py:321-326)
+            ops.layernorm(x, Lw.norm1[0], Lw.norm1[1], ws.ln, add=self.pos_emb, out2=ws.ln_pos, stream=st)
+            ops.linear(ws.ln_pos, Lw.sa_qk_w, Lw.sa_qk_b, ws.qk, stream=st)
+            ops.linear(ws.ln, Lw.sa_v_w, Lw.sa_v_b, ws.v, stream=st)
+            ops.attention(ws.qk[:, :C], ws.qk[:, C:], ws.v, ws.core[:, :C], H, d, d, Tk=N, stream=st)
+            ops.linear(ws.core[:, :C], Lw.sa_proj_w, Lw.sa_proj_b, x, res=x, stream=st)
+            # 2) long + short term (transformer.py:329-352)
+            cQ, cV = self.curr_Q[li], self.curr_V[li]
+            ops.layernorm(x, Lw.norm2[0], Lw.norm2[1], cV, stream=st)
+            ops.linear(cV, Lw.linQ_w, Lw.linQ_b, cQ, stream=st)
+            if is_ref:
+                ops.eltwise(ops.EW_ADD, cV, id_emb, ws.tmp, stream=st)
+                ops.linear(ws.tmp, Lw.linV_w, Lw.linV_b, stV[li], stream=st)      # fuse_key_value_id :364-367
+                ops.eltwise(ops.EW_COPY, cQ, None, stK[li], stream=st)
+                gK, gV, Tk = stK[li], stV[li], N
+            else:
+                gK, gV, Tk = self.bank_K[li], self.bank_V[li], self.bank_len
+            self._long_term_attention(li, cQ, gK, gV, Tk, ws.core[:, :C], st)
+            ops.local_attention(cQ, stK[li], stV[li], Lw.relk_w, Lw.relk_b, Lw.relv, ws.core[:, C:], h, w, H, d, d,
+                                stream=st)
+            ops.linear(ws.core, Lw.lst_proj_w, Lw.lst_proj_b, x, res=x, stream=st)
+            # 3) feed-forward (transformer.py:354-359, basic.py:27-35)
+            ops.layernorm(x, Lw.norm3[0], Lw.norm3[1], ws.ln, stream=st)
+            ops.linear(ws.ln, Lw.lin1_w, Lw.lin1_b, ws.ff, stream=st)
+            ops.groupnorm(ws.ff.view(1, N, 4 * C), Lw.gn[0], Lw.gn[1], ws.ff.view(1, N, 4 * C), 32, A_GELU, ws.gn_ws,
+                          stream=st)
+            ops.dwconv(ws.ff.view(1, h, w, 4 * C), Lw.dw_w, None, ws.ff2.view(1, h, w, 4 * C), K=5, pad=2, stream=st)
+            ops.linear(ws.ff2, Lw.lin2_w, Lw.lin2_b, x, res=x, stream=st)
+            # decoder norms (transformer.py:124-135) written straight into the decoder input
+            ops.layernorm(x, Lw.dec_norm[0], Lw.dec_norm[1], ws.cat[:, (li + 1) * C:(li + 2) * C], stream=st)
+        if is_ref:
+            self._commit_short_slot(stK, stV)
+        self._have_lstt = True
+
+    def _long_term_attention(self, li, Q, K, V, Tk, out, st):
+        P = self._plan()
+        d = P.C // P.H
+        probe = LT_PROBE
+        if probe is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        ops.attention(Q, K, V, out, P.H, d, d, Tk=Tk, stream=st)
+        if probe is not None:
+            e1.record()
+            probe.append((e0, e1, 4.0 * Q.shape[0] * Tk * P.C))
+
+    # short-term memory slots (TEST_SHORT_TERM_MEM_SKIP ring, aot_engine.py:329-332)
+    def _next_short_slot(self):
+        if self.short_term_mem_skip <= 1:
+            return self.st_K, self.st_V
+        K = [torch.empty_like(t) for t in self.st_K]
+        V = [torch.empty_like(t) for t in self.st_V]
+        return K, V
+
+    def _commit_short_slot(self, K, V, reset=True):
+        self._new_K, self._new_V = K, V
+        if self.short_term_mem_skip <= 1:
+            return
+        if reset:
+            self._st_ring = [(K, V)]
+        else:
+            self._st_ring.append((K, V))
+            self._st_ring = self._st_ring[-self.short_term_mem_skip:]
+        self.st_K, self.st_V = self._st_ring[0]
+
+    def _fuse_memories(self, id_emb, st):
+        """update_short_term_memory core (aot_engine.py:315-332): K = curr_K, V = linear_V(curr_V + id)."""
+        P = self._plan()
+        ws = self._ws
+        K, V = self._next_short_slot()
+        for li in range(P.L):
+            Lw = P.layers[li]
+            ops.eltwise(ops.EW_ADD, self.curr_V[li], id_emb, ws.tmp, stream=st)
+            ops.linear(ws.tmp, Lw.linV_w, Lw.linV_b, V[li], stream=st)
+            ops.eltwise(ops.EW_COPY, self.curr_Q[li], None, K[li], stream=st)
+        self._commit_short_slot(K, V, reset=False)
+
+    # ------------------------------------------------------------------ decoder (fpn.py:34-58)
+    def _dbuf(self, key, shape):
+        b = self._dec_bufs.get(key)
+        if b is None or tuple(b.shape) != tuple(shape):
+            b = torch.empty(shape, dtype=torch.float32, device=self._plan().device)
+            self._dec_bufs[key] = b
+        return b
+
+    def _decode(self, st):
+        P = self._plan()
+        D = P.dec
+        ws = self._ws
+        ac = P.align_corners
+        x4, x8, x16, _ = self.curr_enc_embs.nhwc
+        h, w = self.enc_size_2d
+        C = P.C
+        gws = ws.gn_ws
+
+        def conv_gn(x, blk, key, k, pad, res=None):
+            o = self._dbuf(key, (1, x.shape[1], x.shape[2], blk.cout))
+            ops.conv2d(x, blk.w, blk.b, o, KH=k, KW=k, pad=pad, stream=st)
+            ov = o.view(1, -1, blk.cout)
+            ops.groupnorm(ov, blk.gn[0], blk.gn[1], ov, 8, A_RELU, gws, stream=st)
+            return o
+
+        cat = ws.cat.view(1, h, w, -1)
+        x = conv_gn(cat, D.conv_in, "in", 1, 0)
+        a = self._dbuf("a16", (1, h, w, D.adapter_16x.cout))
+        ops.conv2d(x16, D.adapter_16x.w, D.adapter_16x.b, a, res=x, stream=st)
+        x = conv_gn(a, D.conv_16x, "c16", 3, 1)
+        up = self._dbuf("up8", (1, x8.shape[1], x8.shape[2], x.shape[3]))
+        ops.bilinear(x, up, ac, stream=st)
+        a = self._dbuf("a8", (1, x8.shape[1], x8.shape[2], D.adapter_8x.cout))
+        ops.conv2d(x8, D.adapter_8x.w, D.adapter_8x.b, a, res=up, stream=st)
+        x = conv_gn(a, D.conv_8x, "c8", 3, 1)
+        up = self._dbuf("up4", (1, x4.shape[1], x4.shape[2], x.shape[3]))
+        ops.bilinear(x, up, ac, stream=st)
+        a = self._dbuf("a4", (1, x4.shape[1], x4.shape[2], D.adapter_4x.cout))
+        ops.conv2d(x4, D.adapter_4x.w, D.adapter_4x.b, a, res=up, stream=st)
+        x = conv_gn(a, D.conv_4x, "c4", 3, 1)
+        lg = self._dbuf("logit", (1, x.shape[1], x.shape[2], D.conv_out.cout))
+        ops.conv2d(x, D.conv_out.w, D.conv_out.b, lg, stream=st)
+        return lg
+
+    def decode_current_logits(self, output_size=None):
+        st = torch.cuda.current_stream().cuda_stream
+        P = self._plan()
+        lg = self._decode(st)
+        h4, w4, NC = lg.shape[1], lg.shape[2], lg.shape[3]
+        lo = torch.empty((1, NC, h4, w4), dtype=torch.float32, device=lg.device)
+        out = None
+        if output_size is not None:
+            oh, ow = int(output_size[0]), int(output_size[1])
+            out = torch.empty((1, NC, oh, ow), dtype=torch.float32, device=lg.device)
+        ops.logits_postproc(lg, lo, out, int(self.obj_nums[0]), P.align_corners, stream=st)
+        self.pred_id_logits = lo
+        return lo if out is None else out
+
+    def predict_current_mask(self, output_size=None, return_prob=False):
+        """aot_engine.py:382-396 (argmax of the upsampled logits; fused K9 kernel)."""
+        if output_size is None:
+            output_size = self.input_size_2d
+        st = torch.cuda.current_stream().cuda_stream
+        oh, ow = int(output_size[0]), int(output_size[1])
+        label = torch.empty((1, oh, ow), dtype=torch.float32, device=self.pred_id_logits.device)
+        ops.logits_argmax(self.pred_id_logits, label, self._plan().align_corners, stream=st)
+        if return_prob:
+            raise NotImplementedError("return_prob is used by the training path only (SURVEY 8f)")
+        return label.long()
+
+
+class DeAOTEngine(AOTEngine):
+    """networks/engines/deaot_engine.py:9-56 -- GatedPropagationModule stack (transformer.py:501-665)."""
+
+    def __init__(self, aot_model, gpu_id=0, long_term_mem_gap=9999, short_term_mem_skip=1,
+                 layer_loss_scaling_ratio=2.):
+        super().__init__(aot_model, gpu_id, long_term_mem_gap, short_term_mem_skip)
+        self.layer_loss_scaling_ratio = layer_loss_scaling_ratio
+
+    def _gated_tail(self, core, U, dw_w, out_slice, h, w, st):
+        """(attn @ V) * U -> depthwise 5x5 (attention.py:707-709 / :855-857); projection is fused later."""
+        ws = self._ws
+        N = core.shape[0]
+        C4 = core.shape[1]
+        ops.eltwise(ops.EW_MUL, core, U, ws.gated, stream=st)
+        ops.dwconv(ws.gated.view(1, h, w, C4), dw_w, None, out_slice.unflatten(0, (1, h, w)), K=5, pad=2, stream=st)
+
+    def _lstt_forward(self, embs, id_emb, st):
+        P = self._plan()
+        ws = self._ws
+        N, C = self.enc_hw, P.C
+        h, w = self.enc_size_2d
+        d = C // 2
+        C2, C4 = 2 * C, 4 * C
+        proj = embs.nhwc[-1].view(N, C)
+        x, z = ws.xz[:, :C], ws.xz[:, C:]
+        ops.eltwise(ops.EW_COPY, proj, None, x, stream=st)
+        ops.eltwise(ops.EW_FILL, None, None, z, scalar=0.0, stream=st)        # tgt_id = 0 (transformer.py:603)
+        is_ref = id_emb is not None
+        if is_ref:
+            stK, stV = self._next_short_slot()
+        else:
+            stK, stV = self.st_K, self.st_V
+        for li in range(P.L):
+            Lw = P.layers[li]
+            cQ, cV = self.curr_Q[li], self.curr_V[li]
+            ops.layernorm(x, Lw.norm1[0], Lw.norm1[1], ws.ln, stream=st)
+            ops.linear(ws.ln, Lw.qv_w, Lw.qv_b, ws.qv, stream=st)
+            ops.eltwise(ops.EW_COPY, ws.qv[:, :d], None, cQ, stream=st)
+            ops.eltwise(ops.EW_SILU, ws.qv[:, d:], None, cV, stream=st)          # curr_V = silu(.) :599
+            ops.linear(ws.ln, Lw.u_w, Lw.u_b, ws.catU[:, :C2], act=A_SILU, stream=st)
+            if li == 0:
+                ops.eltwise(ops.EW_FILL, None, None, ws.catU[:, C2:], scalar=1.0, stream=st)   # :604-605
+                cIDV = None
+            else:
+                cIDV = self.curr_IDV[li]
+                ops.layernorm(z, Lw.id_norm1[0], Lw.id_norm1[1], cIDV, stream=st)
+                ops.linear(cIDV, Lw.idu_w, Lw.idu_b, ws.catU[:, C2:], act=A_SILU, stream=st)    # :610-611
+            if is_ref:
+                ops.eltwise(ops.EW_COPY, cQ, None, stK[li], stream=st)
+                ops.eltwise(ops.EW_COPY, cV, None, stV[li][:, :C2], stream=st)
+                self._fuse_id(li, cIDV, id_emb, stV[li][:, C2:], st)
+                gK, gV, Tk = stK[li], stV[li], N
+            else:
+                gK, gV, Tk = self.bank_K[li], self.bank_V[li], self.bank_len
+            ops.attention(cQ, gK, gV, ws.core, 1, d, C4, Tk=Tk, stream=st)
+            self._gated_tail(ws.core, ws.catU, Lw.lt_dw, ws.dw[:, :C4], h, w, st)
+            ops.local_attention(cQ, stK[li], stV[li], Lw.relk_w, Lw.relk_b, None, ws.core, h, w, 1, d, C4, stream=st)
+            self._gated_tail(ws.core, ws.catU, Lw.st_dw, ws.dw[:, C4:], h, w, st)
+            # [tgt | tgt_id] += proj_lt(.) + proj_st(.)   (transformer.py:633-641) as one K = 8C GEMM
+            ops.linear(ws.dw, Lw.lst_proj_w, Lw.lst_proj_b, ws.xz, res=ws.xz, stream=st)
+            # gated self-attention on both streams (transformer.py:644-653, attention.py:648-669)
+            ops.layernorm(x, Lw.norm2[0], Lw.norm2[1], ws.c[:, :C], stream=st)
+            ops.layernorm(z, Lw.id_norm2[0], Lw.id_norm2[1], ws.c[:, C:], stream=st)
+            ops.linear(ws.c, Lw.sa_qk_w, Lw.sa_qk_b, ws.sa_qk, stream=st)
+            ops.linear(ws.c[:, :C], Lw.sa_v1[0], Lw.sa_v1[1], ws.sa_v[:, :C2], act=A_SILU, stream=st)
+            ops.linear(ws.c[:, C:], Lw.sa_v2[0], Lw.sa_v2[1], ws.sa_v[:, C2:], act=A_SILU, stream=st)
+            ops.linear(ws.c[:, :C], Lw.sa_u1[0], Lw.sa_u1[1], ws.sa_u[:, :C2], act=A_SILU, stream=st)
+            ops.linear(ws.c[:, C:], Lw.sa_u2[0], Lw.sa_u2[1], ws.sa_u[:, C2:], act=A_SILU, stream=st)
+            ops.attention(ws.sa_qk, ws.sa_qk, ws.sa_v, ws.core, 1, d, C4, Tk=N, stream=st)
+            self._gated_tail(ws.core, ws.sa_u, Lw.sa_dw, ws.dw[:, :C4], h, w, st)
+            ops.linear(ws.dw[:, :C4], Lw.sa_proj_w, Lw.sa_proj_b, ws.xz, res=ws.xz, stream=st)
+        # final GroupNorm1D(2C, groups=2) (transformer.py:197-200,241) -> decoder input
+        ops.groupnorm(ws.xz.view(1, N, C2), P.final_gn[0], P.final_gn[1], ws.cat.view(1, N, C2), 2, A_NONE, ws.gn_ws,
+                      stream=st)
+        if is_ref:
+            self._commit_short_slot(stK, stV)
+        self._have_lstt = True
+
+    def _fuse_id(self, li, cIDV, id_emb, out, st):
+        """GatedPropagationModule.fuse_key_value_id (transformer.py:659-665)."""
+        Lw = self._plan().layers[li]
+        ws = self._ws
+        C = self._plan().C
+        if cIDV is None:
+            ops.linear(id_emb, Lw.idv_w, Lw.idv_b, out, act=A_SILU, stream=st)
+        else:
+            ops.eltwise(ops.EW_COPY, cIDV, None, ws.idin[:, :C], stream=st)
+            ops.eltwise(ops.EW_COPY, id_emb, None, ws.idin[:, C:], stream=st)
+            ops.linear(ws.idin, Lw.idv_w, Lw.idv_b, out, act=A_SILU, stream=st)
+
+    def _fuse_memories(self, id_emb, st):
+        """deaot_engine.py:20-45: K, V unchanged; ID_V = fuse_key_value_id(None, curr_ID_V, id_emb)."""
+        P = self._plan()
+        C2 = 2 * P.C
+        K, V = self._next_short_slot()
+        for li in range(P.L):
+            ops.eltwise(ops.EW_COPY, self.curr_Q[li], None, K[li], stream=st)
+            ops.eltwise(ops.EW_COPY, self.curr_V[li], None, V[li][:, :C2], stream=st)
+            self._fuse_id(li, self.curr_IDV[li], id_emb, V[li][:, C2:], st)
+        self._commit_short_slot(K, V, reset=False)
+
+
+# =====================================================================================
+# multi-object facade (aot_engine.py:485-635)
+# =====================================================================================
+class AOTInferEngine(nn.Module):
+    _engine_cls = AOTEngine
+
+    def __init__(self, aot_model, gpu_id=0, long_term_mem_gap=9999, short_term_mem_skip=1, max_aot_obj_num=None):
+        super().__init__()
+        self.cfg = aot_model.cfg
+        self.AOT = aot_model
+        if max_aot_obj_num is None or max_aot_obj_num > aot_model.max_obj_num:
+            self.max_aot_obj_num = aot_model.max_obj_num
+        else:
+            self.max_aot_obj_num = max_aot_obj_num
+        self.gpu_id = gpu_id
+        self.long_term_mem_gap = long_term_mem_gap
+        self.short_term_mem_skip = short_term_mem_skip
+        self.aot_engines = []
+        self.restart_engine()
+
+    def restart_engine(self):
+        # keep the engines (and their device buffers) across videos; just reset their state
+        self._pool = getattr(self, "_pool", []) + list(self.aot_engines)
+        self.aot_engines = []
+        self.obj_nums = None
+
+    def separate_mask(self, mask, obj_nums):
+        # aot_engine.py:515-545
+        if mask is None:
+            return [None] * len(self.aot_engines)
+        if len(self.aot_engines) == 1:
+            return [mask], [obj_nums]
+        separated_obj_nums = [self.max_aot_obj_num for _ in range(len(self.aot_engines))]
+        if obj_nums % self.max_aot_obj_num > 0:
+            separated_obj_nums[-1] = obj_nums % self.max_aot_obj_num
+        if len(mask.size()) == 3 or mask.size()[0] == 1:
+            separated_masks = []
+            for idx in range(len(self.aot_engines)):
+                start_id = idx * self.max_aot_obj_num + 1
+                end_id = (idx + 1) * self.max_aot_obj_num
+                fg_mask = ((mask >= start_id) & (mask <= end_id)).float()
+                separated_masks.append((fg_mask * mask - start_id + 1) * fg_mask)
+            return separated_masks, separated_obj_nums
+        prob = mask
+        separated_probs = []
+        for idx in range(len(self.aot_engines)):
+            start_id = idx * self.max_aot_obj_num + 1
+            end_id = (idx + 1) * self.max_aot_obj_num
+            fg_prob = prob[start_id:(end_id + 1)]
+            bg_prob = 1. - torch.sum(fg_prob, dim=1, keepdim=True)
+            separated_probs.append(torch.cat([bg_prob, fg_prob], dim=1))
+        return separated_probs, separated_obj_nums
+
+    def soft_logit_aggregation(self, all_logits):
+        # aot_engine.py:565-582 (identity for <= 10 objects; the >10-object merge is a "next" row and
+        # still uses element-wise tensor ops on the few merged logit maps)
+        if len(all_logits) == 1:
+            return all_logits[0]
+        fg_probs, bg_probs = [], []
+        for logit in all_logits:
+            prob = torch.softmax(logit, dim=1)
+            bg_probs.append(prob[:, 0:1])
+            fg_probs.append(prob[:, 1:1 + self.max_aot_obj_num])
+        bg_prob = torch.prod(torch.cat(bg_probs, dim=1), dim=1, keepdim=True)
+        merged_prob = torch.cat([bg_prob] + fg_probs, dim=1).clamp(1e-5, 1 - 1e-5)
+        return torch.logit(merged_prob)
+
+    def add_reference_frame(self, img, mask, obj_nums, frame_step=-1):
+        if isinstance(obj_nums, list):
+            obj_nums = obj_nums[0]
+        self.obj_nums = obj_nums
+        aot_num = max(np.ceil(obj_nums / self.max_aot_obj_num), 1)
+        while aot_num > len(self.aot_engines):
+            if self._pool:
+                new_engine = self._pool.pop(0)
+                new_engine.restart_engine()
+            else:
+                new_engine = self._engine_cls(self.AOT, self.gpu_id, self.long_term_mem_gap, self.short_term_mem_skip)
+            new_engine.eval()
+            self.aot_engines.append(new_engine)
+        separated_masks, separated_obj_nums = self.separate_mask(mask, obj_nums)
+        img_embs = None
+        for aot_engine, separated_mask, separated_obj_num in zip(self.aot_engines, separated_masks,
+                                                                 separated_obj_nums):
+            aot_engine.add_reference_frame(img, separated_mask, obj_nums=[separated_obj_num], frame_step=frame_step,
+                                           img_embs=img_embs)
+            if img_embs is None:
+                img_embs = aot_engine.curr_enc_embs
+        self.update_size()
+
+    def match_propogate_one_frame(self, img=None):
+        img_embs = None
+        for aot_engine in self.aot_engines:
+            aot_engine.match_propogate_one_frame(img, img_embs=img_embs)
+            if img_embs is None:
+                img_embs = aot_engine.curr_enc_embs
+
+    def decode_current_logits(self, output_size=None):
+        all_logits = [e.decode_current_logits(output_size) for e in self.aot_engines]
+        return self.soft_logit_aggregation(all_logits)
+
+    def update_memory(self, curr_mask, skip_long_term_update=False):
+        separated_masks, _ = self.separate_mask(curr_mask, self.obj_nums)
+        for aot_engine, separated_mask in zip(self.aot_engines, separated_masks):
+            aot_engine.update_short_term_memory(separated_mask, skip_long_term_update=skip_long_term_update)
+
+    # BASELINE.json's north_star names this method; the reference's real name is update_memory
+    update_short_long_term_memory = update_memory
+
+    def update_size(self):
+        self.input_size_2d = self.aot_engines[0].input_size_2d
+        self.enc_size_2d = self.aot_engines[0].enc_size_2d
+        self.enc_hw = self.aot_engines[0].enc_hw
+
+    @property
+    def pred_id_logits(self):
+        return self.aot_engines[0].pred_id_logits if self.aot_engines else None
+
+
+class DeAOTInferEngine(AOTInferEngine):
+    _engine_cls = DeAOTEngine
+
+
+def build_engine(name, phase='train', **kwargs):
+    """networks/engines/__init__.py:5-21."""
+    if name == 'aotengine':
+        if phase == 'train':
+            return AOTEngine(**kwargs)
+        elif phase == 'eval':
+            return AOTInferEngine(**kwargs)
+        raise NotImplementedError
+    elif name == 'deaotengine':
+        if phase == 'train':
+            return DeAOTEngine(**kwargs)
+        elif phase == 'eval':
+            return DeAOTInferEngine(**kwargs)
+        raise NotImplementedError
+    raise NotImplementedError

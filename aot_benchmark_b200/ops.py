@@ -1,0 +1,208 @@
+"""Thin tensor-level wrappers over the C ABI (include/aotb200.h).
+
+PyTorch is used here only for device memory (tensors) and streams.  Every function launches
+hand-written sm_100a kernels from libaotb200.so on ``stream`` (a raw cudaStream_t int, default:
+torch's current stream) and raises ``AotbError`` on failure -- there is no eager fallback.
+
+Layout conventions: activations are NHWC ``[B,H,W,C]`` or token matrices ``[rows, C]`` whose last
+stride is 1; channel-sliced views are fine (the row stride is passed as ``ld``).
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import AotbError, check, lib
+
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU, ACT_RELU6 = 0, 1, 2, 3, 4
+EW_COPY, EW_ADD, EW_MUL, EW_SILU, EW_SILU_MUL, EW_FILL = 0, 1, 2, 3, 4, 5
+
+
+def _st(stream):
+    return torch.cuda.current_stream().cuda_stream if stream is None else stream
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise AotbError(f"aot_benchmark_b200 kernels need float32 CUDA tensors, got {t.dtype} on {t.device}")
+        if t.dim() >= 1 and t.stride(-1) != 1:
+            raise AotbError("innermost stride must be 1")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _nhwc_ld(x):
+    B, H, W, C = x.shape
+    ld = x.stride(2)
+    if x.stride(1) != W * ld or (B > 1 and x.stride(0) != H * W * ld):
+        raise AotbError("NHWC tensor must be dense over pixels")
+    return ld
+
+
+def conv2d(x, w, bias, out, res=None, KH=1, KW=1, stride=1, pad=0, dil=1, act=ACT_NONE, stream=None):
+    """x [B,H,W,Cin], w [KH*KW*Cin, Cout], out [B,Ho,Wo,Cout] (+res like out)."""
+    _chk(x, w, bias, out, res)
+    B, H, W, Cin = x.shape
+    Cout = w.shape[1]
+    check(lib().aotb_conv2d_nhwc_f32(_p(x), _p(w), _p(bias), _p(res), _p(out), B, H, W, Cin, _nhwc_ld(x), Cout,
+                                     _nhwc_ld(out), _nhwc_ld(res) if res is not None else 0, KH, KW, stride, pad,
+                                     dil, act, _st(stream)), "aotb_conv2d_nhwc_f32")
+    return out
+
+
+def linear(x, wt, bias, out, res=None, act=ACT_NONE, stream=None):
+    """x [M,K], wt [K,N], out [M,N] (+res [M,N]); res may alias out (in-place accumulate)."""
+    _chk(x, wt, bias, out, res)
+    M, K = x.shape
+    N = wt.shape[1]
+    check(lib().aotb_linear_f32(_p(x), _p(wt), _p(bias), _p(res), _p(out), M, K, x.stride(0), N, out.stride(0),
+                                res.stride(0) if res is not None else 0, act, _st(stream)), "aotb_linear_f32")
+    return out
+
+
+def nchw_to_nhwc(x, out, stream=None):
+    _chk(x, out)
+    B, C, H, W = x.shape
+    check(lib().aotb_nchw_to_nhwc_f32(_p(x.contiguous()), _p(out), B, C, H * W, _st(stream)), "aotb_nchw_to_nhwc_f32")
+    return out
+
+
+def nhwc_to_nchw(x, out, stream=None):
+    _chk(x, out)
+    B, H, W, C = x.shape
+    check(lib().aotb_nhwc_to_nchw_f32(_p(x), _p(out), B, C, H * W, _st(stream)), "aotb_nhwc_to_nchw_f32")
+    return out
+
+
+def maxpool3x3s2(x, out, stream=None):
+    _chk(x, out)
+    B, H, W, C = x.shape
+    check(lib().aotb_maxpool3x3s2_nhwc_f32(_p(x), _p(out), B, H, W, C, _st(stream)), "aotb_maxpool3x3s2_nhwc_f32")
+    return out
+
+
+def dwconv(x, w, bias, out, K=5, stride=1, pad=2, dil=1, act=ACT_NONE, stream=None):
+    """x [B,H,W,C], w [K*K, C]."""
+    _chk(x, w, bias, out)
+    B, H, W, C = x.shape
+    check(lib().aotb_dwconv_nhwc_f32(_p(x), _p(w), _p(bias), _p(out), B, H, W, C, _nhwc_ld(x), _nhwc_ld(out), K, K,
+                                     stride, pad, dil, act, _st(stream)), "aotb_dwconv_nhwc_f32")
+    return out
+
+
+def bilinear(x, out, align_corners, stream=None):
+    _chk(x, out)
+    B, H, W, C = x.shape
+    check(lib().aotb_bilinear_nhwc_f32(_p(x), _p(out), B, H, W, C, out.shape[1], out.shape[2],
+                                       1 if align_corners else 0, _st(stream)), "aotb_bilinear_nhwc_f32")
+    return out
+
+
+def eltwise(op, a, b, out, scalar=0.0, stream=None):
+    """2-D strided element-wise op on [rows, cols] views."""
+    _chk(a, b, out)
+    rows, cols = out.shape
+    check(lib().aotb_eltwise_f32(op, _p(a), a.stride(0) if a is not None else 0, _p(b),
+                                 b.stride(0) if b is not None else 0, _p(out), out.stride(0), rows, cols,
+                                 float(scalar), _st(stream)), "aotb_eltwise_f32")
+    return out
+
+
+def layernorm(x, gamma, beta, out, add=None, out2=None, stream=None):
+    _chk(x, gamma, beta, out, add, out2)
+    rows, C = x.shape
+    check(lib().aotb_layernorm_f32(_p(x), x.stride(0), _p(gamma), _p(beta), _p(add),
+                                   add.stride(0) if add is not None else 0, _p(out), out.stride(0), _p(out2),
+                                   out2.stride(0) if out2 is not None else 0, rows, C, _st(stream)),
+          "aotb_layernorm_f32")
+    return out
+
+
+def groupnorm_workspace(B, G, device):
+    n = lib().aotb_groupnorm_workspace_bytes(B, G)
+    return torch.empty(n // 8, dtype=torch.float64, device=device)
+
+
+def groupnorm(x, gamma, beta, out, G, act, workspace, stream=None):
+    """x/out [B, P, C] (any NHWC flattened over pixels)."""
+    _chk(x, gamma, beta, out)
+    B, P, C = x.shape
+    check(lib().aotb_groupnorm_nhwc_f32(_p(x), x.stride(1), _p(gamma), _p(beta), _p(out), out.stride(1), B, P, C, G,
+                                        act, workspace.data_ptr(), _st(stream)), "aotb_groupnorm_nhwc_f32")
+    return out
+
+
+def attention(Q, K, V, O, H, d_qk, d_v, Tk=None, Tk_dev=None, Mout=None, Lout=None, stream=None):
+    """Q [N, H*d_qk], K [>=Tk, H*d_qk], V [>=Tk, H*d_v], O [N, H*d_v]."""
+    _chk(Q, K, V, O, Mout, Lout)
+    N = Q.shape[0]
+    tk = K.shape[0] if Tk is None else int(Tk)
+    check(lib().aotb_attention_f32(_p(Q), Q.stride(0), _p(K), K.stride(0), _p(V), V.stride(0), _p(O), O.stride(0),
+                                   N, tk, Tk_dev.data_ptr() if Tk_dev is not None else None, H, d_qk, d_v,
+                                   _p(Mout), _p(Lout), _st(stream)), "aotb_attention_f32")
+    return O
+
+
+def attn_merge(Opart, Mpart, Lpart, O, H, d_v, stream=None):
+    _chk(Opart, Mpart, Lpart, O)
+    R, N = Opart.shape[0], Opart.shape[1]
+    check(lib().aotb_attn_merge_f32(_p(Opart), _p(Mpart), _p(Lpart), _p(O), R, N, H, d_v, O.stride(0), _st(stream)),
+          "aotb_attn_merge_f32")
+    return O
+
+
+def local_attention(q, k, v, relk_w, relk_b, relv, out, h, w, H, d_att, d_v, stream=None):
+    """q,k [hw, H*d_att], v [hw, H*d_v], out [hw, H*d_v]."""
+    _chk(q, k, v, relk_w, relk_b, relv, out)
+    check(lib().aotb_local_attention_f32(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(relk_w),
+                                         _p(relk_b), _p(relv), _p(out), out.stride(0), h, w, H, d_att, d_v,
+                                         _st(stream)), "aotb_local_attention_f32")
+    return out
+
+
+def id_embed(mask, wt, bias, out, C, nid, ksize, stride, pad, ln_gamma=None, ln_beta=None, stream=None):
+    """mask [Hm, Wm] float ids -> out [ho*wo, C]."""
+    _chk(mask, wt, bias, out, ln_gamma, ln_beta)
+    Hm, Wm = mask.shape
+    check(lib().aotb_id_embed_f32(_p(mask), Hm, Wm, _p(wt), _p(bias), _p(ln_gamma), _p(ln_beta), _p(out),
+                                  out.stride(0), C, nid, ksize, stride, pad, _st(stream)), "aotb_id_embed_f32")
+    return out
+
+
+def logits_postproc(logits_nhwc, lowres_nchw, out_nchw, obj_num, align_corners, stream=None):
+    _chk(logits_nhwc, lowres_nchw, out_nchw)
+    h, w, NC = logits_nhwc.shape[-3:]
+    Ho, Wo = (out_nchw.shape[-2], out_nchw.shape[-1]) if out_nchw is not None else (0, 0)
+    check(lib().aotb_logits_postproc_f32(_p(logits_nhwc), _p(lowres_nchw), _p(out_nchw), h, w, NC, obj_num, Ho, Wo,
+                                         1 if align_corners else 0, _st(stream)), "aotb_logits_postproc_f32")
+    return out_nchw
+
+
+def logits_argmax(lowres_nchw, label, align_corners, stream=None):
+    _chk(lowres_nchw, label)
+    NC, h, w = lowres_nchw.shape[-3:]
+    Ho, Wo = label.shape[-2:]
+    check(lib().aotb_logits_argmax_f32(_p(lowres_nchw), _p(label), h, w, NC, Ho, Wo, 1 if align_corners else 0,
+                                       _st(stream)), "aotb_logits_argmax_f32")
+    return label
+
+
+def nearest_resize(x, out, stream=None):
+    _chk(x, out)
+    H, W = x.shape[-2:]
+    Ho, Wo = out.shape[-2:]
+    check(lib().aotb_nearest_resize_f32(_p(x), _p(out), H, W, Ho, Wo, _st(stream)), "aotb_nearest_resize_f32")
+    return out
+
+
+def bank_append(src, bank, offset, offset_dev=None, stream=None):
+    _chk(src, bank)
+    rows, cols = src.shape
+    check(lib().aotb_bank_append_f32(_p(src), src.stride(0), _p(bank), bank.stride(0), rows, cols, int(offset),
+                                     offset_dev.data_ptr() if offset_dev is not None else None, _st(stream)),
+          "aotb_bank_append_f32")
+    return bank

@@ -1,0 +1,226 @@
+"""Packed, device-resident copies of a model's parameters in the layouts the kernels read.
+
+* convolutions   [Cout,Cin,KH,KW] -> [KH*KW*Cin, Cout] with FrozenBatchNorm2d folded in
+  (networks/layers/normalization.py:30-43: y = (x-mean)*w/sqrt(var+eps)+b, folded in float64);
+* depthwise convs [C,1,K,K]        -> [K*K, C];
+* linears        [out,in]          -> [in, out]; sibling projections that share an input or an
+  output are concatenated so one GEMM replaces two (self-attention Q|K, and the long-term +
+  short-term output projections whose results the reference adds, transformer.py:349-352);
+* ID bank        [C,11,K,K]        -> [(ky*K+kx)*11 + id, C]  (gather table == dense-conv layout).
+
+The plan is cached on the model and rebuilt when any parameter's version counter or device
+changes (``load_state_dict`` / ``.to()`` after a plan was built).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace as NS
+
+import torch
+
+from .model import mobilenetv2_plan
+
+
+def _signature(model):
+    items = list(model.named_parameters()) + list(model.named_buffers())
+    return tuple((n, t._version, t.data_ptr(), str(t.device)) for n, t in items)
+
+
+def get_plan(model):
+    sig = _signature(model)
+    cached = getattr(model, "_aotb_plan", None)
+    if cached is not None and cached[0] == sig:
+        return cached[1]
+    plan = Plan(model)
+    model._aotb_plan = (sig, plan)
+    return plan
+
+
+class Plan:
+    def __init__(self, model):
+        cfg = model.cfg
+        self.cfg = cfg
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("aot_benchmark_b200 runs on CUDA devices only (no CPU path): move the model to "
+                               "a GPU before building an engine")
+        self.device = dev
+        sd = {k: v.detach() for k, v in model.state_dict().items()}
+        self.sd = sd
+        self.deaot = cfg.MODEL_VOS == "deaot"
+        self.L = cfg.MODEL_LSTT_NUM
+        self.C = cfg.MODEL_ENCODER_EMBEDDING_DIM
+        self.H = cfg.MODEL_ATT_HEADS
+        self.align_corners = bool(cfg.MODEL_ALIGN_CORNERS)
+        self.nid = cfg.MODEL_MAX_OBJ_NUM + 1
+        self._encoder(cfg.MODEL_ENCODER)
+        w = sd["encoder_projector.weight"]
+        self.proj = NS(w=self._conv_w(w), b=self._f(sd["encoder_projector.bias"]))
+        self.layers = [self._gpm_layer(i) if self.deaot else self._lstt_layer(i) for i in range(self.L)]
+        self._decoder()
+        self._idbank()
+
+    # ------------------------------------------------------------------ helpers
+    def _f(self, t):
+        return t.to(self.device, torch.float32).contiguous()
+
+    def _conv_w(self, w, scale=None):
+        # [Cout,Cin,KH,KW] -> [KH*KW*Cin, Cout]
+        w = w.double()
+        if scale is not None:
+            w = w * scale.view(-1, 1, 1, 1)
+        co, ci, kh, kw = w.shape
+        return self._f(w.permute(2, 3, 1, 0).reshape(kh * kw * ci, co).float())
+
+    def _dw_w(self, w, scale=None):
+        # [C,1,K,K] -> [K*K, C]
+        w = w.double()
+        if scale is not None:
+            w = w * scale.view(-1, 1, 1, 1)
+        c, _, kh, kw = w.shape
+        return self._f(w.permute(2, 3, 1, 0).reshape(kh * kw, c).float())
+
+    def _bn(self, name):
+        sd = self.sd
+        eps = 1e-5
+        scale = sd[name + ".weight"].double() / torch.sqrt(sd[name + ".running_var"].double() + eps)
+        shift = sd[name + ".bias"].double() - sd[name + ".running_mean"].double() * scale
+        return scale, shift
+
+    def _conv_bn(self, conv, bn, depthwise=False):
+        scale, shift = self._bn(bn)
+        w = self.sd[conv + ".weight"]
+        ns = NS(b=self._f(shift.float()), k=w.shape[2], cin=w.shape[1], cout=w.shape[0])
+        ns.w = self._dw_w(w, scale) if depthwise else self._conv_w(w, scale)
+        return ns
+
+    def _lin(self, name):
+        return self._f(self.sd[name + ".weight"].t()), self._f(self.sd[name + ".bias"])
+
+    def _norm(self, name):
+        return self._f(self.sd[name + ".weight"]), self._f(self.sd[name + ".bias"])
+
+    # ------------------------------------------------------------------ encoders
+    def _encoder(self, name):
+        self.encoder_name = name
+        p = "encoder."
+        if name == "resnet50":
+            e = NS(stem=self._conv_bn(p + "conv1", p + "bn1"), stages=[])
+            for li, (nblk, stride) in enumerate(((3, 1), (4, 2), (6, 2)), start=1):
+                blocks = []
+                for bi in range(nblk):
+                    q = f"{p}layer{li}.{bi}."
+                    b = NS(c1=self._conv_bn(q + "conv1", q + "bn1"), c2=self._conv_bn(q + "conv2", q + "bn2"),
+                           c3=self._conv_bn(q + "conv3", q + "bn3"), stride=stride if bi == 0 else 1, down=None)
+                    if (q + "downsample.0.weight") in self.sd:
+                        b.down = self._conv_bn(q + "downsample.0", q + "downsample.1")
+                    blocks.append(b)
+                e.stages.append(blocks)
+            self.enc = e
+        elif name == "mobilenetv2":
+            e = NS(stem=self._conv_bn(p + "features.0.0", p + "features.0.1"), blocks=[])
+            for idx, (inp, oup, stride, dil, t) in enumerate(mobilenetv2_plan(16), start=1):
+                q = f"{p}features.{idx}.conv."
+                b = NS(stride=stride, dil=dil, res=(stride == 1 and inp == oup), expand=None, tap=idx in (3, 6, 13))
+                j = 0
+                if t != 1:
+                    b.expand = self._conv_bn(q + "0.0", q + "0.1")
+                    j = 1
+                b.dw = self._conv_bn(q + f"{j}.0", q + f"{j}.1", depthwise=True)
+                b.pw = self._conv_bn(q + f"{j + 1}", q + f"{j + 2}")
+                e.blocks.append(b)
+            e.last = self._conv_bn(p + "features.18.0", p + "features.18.1")
+            self.enc = e
+        else:
+            raise NotImplementedError(f"encoder '{name}' has no sm_100a path")
+
+    # ------------------------------------------------------------------ AOT block
+    def _lstt_layer(self, i):
+        p = f"LSTT.layers.{i}."
+        sd = self.sd
+        n = NS()
+        n.norm1 = self._norm(p + "norm1")
+        wq, bq = self._lin(p + "self_attn.linear_Q")
+        wk, bk = self._lin(p + "self_attn.linear_K")
+        n.sa_qk_w = torch.cat([wq, wk], dim=1).contiguous()
+        n.sa_qk_b = torch.cat([bq, bk]).contiguous()
+        n.sa_v_w, n.sa_v_b = self._lin(p + "self_attn.linear_V")
+        n.sa_proj_w, n.sa_proj_b = self._lin(p + "self_attn.projection")
+        n.norm2 = self._norm(p + "norm2")
+        n.linQ_w, n.linQ_b = self._lin(p + "linear_Q")
+        n.linV_w, n.linV_b = self._lin(p + "linear_V")
+        wl, bl = self._lin(p + "long_term_attn.projection")
+        ws, bs = self._lin(p + "short_term_attn.projection")
+        n.lst_proj_w = torch.cat([wl, ws], dim=0).contiguous()       # [2C, C]: x += [lt|st] @ W
+        n.lst_proj_b = (bl.double() + bs.double()).float().contiguous()
+        rk = sd[p + "short_term_attn.relative_emb_k.weight"]
+        n.relk_w = self._f(rk.reshape(rk.shape[0], rk.shape[1]))       # [H*225, d]
+        n.relk_b = self._f(sd[p + "short_term_attn.relative_emb_k.bias"])
+        n.relv = self._f(sd[p + "short_term_attn.relative_emb_v"])     # [H, d, 225]
+        n.norm3 = self._norm(p + "norm3")
+        n.lin1_w, n.lin1_b = self._lin(p + "linear1")
+        n.gn = self._norm(p + "activation.gn")
+        n.dw_w = self._dw_w(sd[p + "activation.conv.weight"])
+        n.lin2_w, n.lin2_b = self._lin(p + "linear2")
+        if i < self.L:
+            n.dec_norm = self._norm(f"LSTT.decoder_norms.{i}")
+        return n
+
+    # ------------------------------------------------------------------ DeAOT block
+    def _gpm_layer(self, i):
+        p = f"LSTT.layers.{i}."
+        sd = self.sd
+        n = NS()
+        n.norm1 = self._norm(p + "norm1")
+        n.qv_w, n.qv_b = self._lin(p + "linear_QV")           # [C, d_att + 2C]
+        n.u_w, n.u_b = self._lin(p + "linear_U")              # [C, 2C]
+        n.idv_w, n.idv_b = self._lin(p + "linear_ID_V")       # layer 0: [C, 2C]; else [2C, 2C]
+        if i > 0:
+            n.id_norm1 = self._norm(p + "id_norm1")
+            n.idu_w, n.idu_b = self._lin(p + "linear_ID_U")
+        wl, bl = self._lin(p + "long_term_attn.projection")   # [4C, 2C]
+        ws, bs = self._lin(p + "short_term_attn.projection")
+        n.lst_proj_w = torch.cat([wl, ws], dim=0).contiguous()  # [8C, 2C]
+        n.lst_proj_b = (bl.double() + bs.double()).float().contiguous()
+        n.lt_dw = self._dw_w(sd[p + "long_term_attn.dw_conv.conv.weight"])
+        n.st_dw = self._dw_w(sd[p + "short_term_attn.dw_conv.conv.weight"])
+        rk = sd[p + "short_term_attn.relative_emb_k.weight"]
+        n.relk_w = self._f(rk.reshape(rk.shape[0], rk.shape[1]))   # [225, d_att]
+        n.relk_b = self._f(sd[p + "short_term_attn.relative_emb_k.bias"])
+        n.norm2 = self._norm(p + "norm2")
+        n.id_norm2 = self._norm(p + "id_norm2")
+        q = p + "self_attn."
+        n.sa_qk_w, n.sa_qk_b = self._lin(q + "linear_QK")
+        n.sa_v1 = self._lin(q + "linear_V1")
+        n.sa_v2 = self._lin(q + "linear_V2")
+        n.sa_u1 = self._lin(q + "linear_U1")
+        n.sa_u2 = self._lin(q + "linear_U2")
+        n.sa_dw = self._dw_w(sd[q + "dw_conv.conv.weight"])
+        n.sa_proj_w, n.sa_proj_b = self._lin(q + "projection")
+        return n
+
+    # ------------------------------------------------------------------ decoder / id bank
+    def _decoder(self):
+        sd = self.sd
+        p = "decoder."
+        d = NS()
+
+        def cg(name):
+            return NS(w=self._conv_w(sd[p + name + ".conv.weight"]), b=self._f(sd[p + name + ".conv.bias"]),
+                      gn=self._norm(p + name + ".gn"), cout=sd[p + name + ".conv.weight"].shape[0])
+
+        d.conv_in, d.conv_16x, d.conv_8x, d.conv_4x = cg("conv_in"), cg("conv_16x"), cg("conv_8x"), cg("conv_4x")
+        for a in ("adapter_16x", "adapter_8x", "adapter_4x", "conv_out"):
+            setattr(d, a, NS(w=self._conv_w(sd[p + a + ".weight"]), b=self._f(sd[p + a + ".bias"]),
+                             cout=sd[p + a + ".weight"].shape[0]))
+        self.dec = d
+        if self.deaot:
+            self.final_gn = self._norm("LSTT.decoder_norms.0.gn")
+            self.id_norm = self._norm("id_norm")
+
+    def _idbank(self):
+        w = self.sd["patch_wise_id_bank.weight"]           # [C, 11, K, K]
+        self.id_k = w.shape[2]
+        self.id_stride = 16
+        self.id_pad = 8 if self.align_corners else 0       # aot.py:50-63
+        self.id_wt = self._conv_w(w)                        # [(ky*K+kx)*11 + id, C]
+        self.id_b = self._f(self.sd["patch_wise_id_bank.bias"])

@@ -1,0 +1,114 @@
+/* libaotb200.so -- C ABI of the B200-native AOT/DeAOT mask-propagation hot path.
+ *
+ * The reference (yoxu515/aot-benchmark @601c138) is pure Python/PyTorch and has no FFI of its
+ * own; this is the boundary the drop-in Python engines bind with ctypes, and the one
+ * a reference maintainer would bind (INTEGRATION.md shows the stub).  Each entry point replaces
+ * the reference code cited beside it (paths relative to the reference root).
+ *
+ * Conventions: every pointer is a caller-owned DEVICE pointer (fp32 unless noted) obtained from
+ * torch tensors via data_ptr(); no allocation, no host sync, no exceptions; `stream` is a
+ * cudaStream_t (launch is capturable in a CUDA graph); returns 0 or a negative error code,
+ * message via aotb_last_error_string().  Activations are NHWC / [rows][ld] row-major; an `ld*`
+ * argument is the row (pixel) stride in elements so kernels can address channel slices.
+ * Activation codes: 0 none, 1 ReLU, 2 GELU(erf), 3 SiLU, 4 ReLU6.
+ */
+#ifndef AOTB200_H
+#define AOTB200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int aotb_version(void);
+const char* aotb_arch(void);
+const char* aotb_last_error_string(void);
+/* kernels launched by this library in this process so far (bench.py reports the delta). */
+unsigned long long aotb_launch_count(void);
+
+/* nn.Conv2d (+ folded FrozenBatchNorm2d, + residual, + activation) as im2col-free implicit GEMM.
+ * networks/encoders/resnet.py:34-54,140-157; networks/layers/normalization.py:30-43;
+ * networks/models/aot.py:19-21,83; networks/decoders/fpn.py:34-58.
+ * in [B][H][W][ldin], w [KH*KW*Cin][Cout], out [B][Ho][Wo][ldout], res like out with ldres. */
+int aotb_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, const float* res, float* out,
+                         int B, int H, int W, int Cin, int ldin, int Cout, int ldout, int ldres,
+                         int KH, int KW, int stride, int pad, int dil, int act, void* stream);
+
+/* nn.Linear on tokens: out[M][N] = act(in[M][K] @ wt[K][N] + bias + res).
+ * networks/layers/transformer.py:321-367,582-665; networks/layers/attention.py:76-79,119,710,858. */
+int aotb_linear_f32(const float* in, const float* wt, const float* bias, const float* res, float* out,
+                    int M, int K, int ldin, int N, int ldout, int ldres, int act, void* stream);
+
+/* Layout changes at the API edge (callers hand NCHW images, read NCHW features). */
+int aotb_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int HW, void* stream);
+int aotb_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int HW, void* stream);
+
+/* nn.MaxPool2d(3, 2, 1): networks/encoders/resnet.py:79,146. */
+int aotb_maxpool3x3s2_nhwc_f32(const float* in, float* out, int B, int H, int W, int C, void* stream);
+
+/* Depthwise conv, w [KH*KW][C]: networks/layers/basic.py:15-57 (5x5 of the FFN / gated propagation),
+ * networks/encoders/mobilenetv2.py:93-101 (3x3 + folded BN + ReLU6). */
+int aotb_dwconv_nhwc_f32(const float* in, const float* w, const float* bias, float* out, int B, int H, int W,
+                         int C, int ldin, int ldout, int KH, int KW, int stride, int pad, int dil, int act,
+                         void* stream);
+
+/* F.interpolate(mode="bilinear", align_corners=...): networks/decoders/fpn.py:45-54. */
+int aotb_bilinear_nhwc_f32(const float* in, float* out, int B, int H, int W, int C, int Ho, int Wo,
+                           int align_corners, void* stream);
+
+/* Strided element-wise: op 0 copy, 1 a+b, 2 a*b, 3 silu(a), 4 silu(a)*b, 5 fill(scalar).
+ * networks/layers/attention.py:585-586,707,855; networks/layers/transformer.py:602-611,625-626. */
+int aotb_eltwise_f32(int op, const float* a, int lda, const float* b, int ldb, float* out, int ldo,
+                     int rows, int cols, float scalar, void* stream);
+
+/* nn.LayerNorm(C) per row; if out2 != NULL also out2 = LN(x) + add (with_pos_embed,
+ * networks/layers/transformer.py:305-310,321-322). */
+int aotb_layernorm_f32(const float* x, int ldx, const float* gamma, const float* beta, const float* add,
+                       int ldadd, float* out, int ldo, float* out2, int ldo2, int rows, int C, void* stream);
+
+/* nn.GroupNorm(G, C) over [B][P pixels][C] + activation: networks/layers/basic.py:6-12,18,30-32,75-85. */
+size_t aotb_groupnorm_workspace_bytes(int B, int G);
+int aotb_groupnorm_nhwc_f32(const float* x, int ldx, const float* gamma, const float* beta, float* out, int ldo,
+                            int B, int P, int C, int G, int act, void* workspace, void* stream);
+
+/* softmax((Q/T) K^T) V per head, scores never materialised (fp32 reference-precision path).
+ * networks/layers/attention.py:82-117 (MultiheadAttention) and :672-704 (GatedPropagation).
+ * Tk_dev (optional) is a device int holding the live key count.  With Mout/Lout the kernel writes
+ * the un-normalised split-KV partial (row max, row sum, O) for aotb_attn_merge_f32. */
+int aotb_attention_f32(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, float* O,
+                       int ldo, int N, int Tk, const int* Tk_dev, int H, int d_qk, int d_v, float* Mout,
+                       float* Lout, void* stream);
+int aotb_attn_merge_f32(const float* Opart, const float* Mpart, const float* Lpart, float* O, int R, int N,
+                        int H, int d_v, int ldo, void* stream);
+
+/* 15x15 local-window attention with relative_emb_k / relative_emb_v:
+ * networks/layers/attention.py:308-428 (MultiheadLocalAttentionV2) and :789-914 (LocalGatedPropagation);
+ * replaces the third-party spatial_correlation_sampler call sites :341,:828. */
+int aotb_local_attention_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                             const float* relk_w, const float* relk_b, const float* relv, float* out, int ldo,
+                             int h, int w, int H, int d_att, int d_v, void* stream);
+
+/* one_hot_mask + patch_wise_id_bank conv as a gather-sum (+ LayerNorm for DeAOT):
+ * utils/image.py:69-74; networks/models/aot.py:50-63,76-79; networks/models/deaot.py:51-55.
+ * mask [Hm][Wm] float ids; wt [(ky*KS+kx)*nid + id][C]. */
+int aotb_id_embed_f32(const float* mask, int Hm, int Wm, const float* wt, const float* bias,
+                      const float* ln_gamma, const float* ln_beta, float* out, int ldo, int C, int nid,
+                      int ksize, int stride, int pad, void* stream);
+
+/* networks/engines/aot_engine.py:367-378: mask ids > obj_num with -1e10, bilinear upsample to NCHW. */
+int aotb_logits_postproc_f32(const float* logits_nhwc, float* lowres_nchw, float* out_nchw, int h, int w,
+                             int NC, int obj_num, int Ho, int Wo, int align_corners, void* stream);
+/* fused upsample + argmax (networks/managers/evaluator.py:339-361 for one engine, no TTA). */
+int aotb_logits_argmax_f32(const float* lowres_nchw, float* label, int h, int w, int NC, int Ho, int Wo,
+                           int align_corners, void* stream);
+/* F.interpolate(mode="nearest") of a label map: networks/managers/evaluator.py:418-421. */
+int aotb_nearest_resize_f32(const float* in, float* out, int H, int W, int Ho, int Wo, void* stream);
+
+/* Long-term memory append in place (replaces torch.cat, networks/engines/aot_engine.py:291-305). */
+int aotb_bank_append_f32(const float* src, int lds, float* bank, int ldb, int rows, int cols, int offset,
+                         const int* offset_dev, void* stream);
+int aotb_counter_add(int* counter, int delta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AOTB200_H */

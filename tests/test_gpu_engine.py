@@ -1,0 +1,124 @@
+"""GPU: the drop-in engines (CUDA, through the C ABI) against the committed reference goldens
+and against the CPU oracle on the same seeded inputs."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _build_cuda_engine(model_name, sd, gap):
+    from aot_benchmark_b200 import EngineConfig, build_engine, build_vos_model
+    cfg = EngineConfig("t", model_name)
+    model = build_vos_model(cfg.MODEL_VOS, cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=0, long_term_mem_gap=gap,
+                       short_term_mem_skip=cfg.TEST_SHORT_TERM_MEM_SKIP)
+    eng.eval()
+    return eng
+
+
+def _tie_band_ok(cuda_lo, ref_lo, cuda_labels, ref_labels, out_size, n, align=True):
+    """Every mismatching pixel must lie in the reference's tie band."""
+    bad = 0
+    for a, b, la, lb in zip(cuda_lo, ref_lo, cuda_labels, ref_labels):
+        mm = la.cpu().to(torch.uint8) != lb.cpu().to(torch.uint8)
+        if mm.any():
+            up = F.interpolate(b[:, :n].float(), size=out_size, mode="bilinear", align_corners=align)
+            top2 = up.topk(2, dim=1).values
+            margin = (top2[:, 0] - top2[:, 1]).unsqueeze(1)
+            dmax = (a.cpu()[:, :n] - b[:, :n]).abs().max().item()
+            bad += int((mm & (margin > 4 * dmax + 1e-5)).sum().item())
+    return bad
+
+
+@pytest.mark.parametrize("name", ["aott_256", "aott_raw_257", "r50_aotl_small", "r50_deaotl_small", "deaott_small"])
+def test_engine_vs_reference_golden(name, golden_dir):
+    from oracle import aot_oracle as O
+    from oracle import weights as OW
+    g = torch.load(os.path.join(golden_dir, f"video_{name}.pt"))
+    sd = OW.build_state_dict(g["model"], seed=g["seed"], flavour=g["flavour"])
+    assert OW.checksum(sd) == g["weights_checksum"], "seeded weights are not reproducible on this machine"
+    frames, mask = O.synthetic_video(g["frames"], g["H"], g["W"], g["objs"], seed=1234 + g["seed"])
+    eng = _build_cuda_engine(g["model"], sd, g["gap"])
+    forced = [l.float() for l in g["ref_labels"]]
+    with torch.no_grad():
+        lo, labels = O.run_video(eng, [f.cuda() for f in frames], mask.cuda(), g["objs"], tuple(g["out_size"]),
+                                 forced_masks=forced)
+    n = g["objs"] + 1
+    dmax = max((a.cpu()[:, :n] - b[:, :n]).abs().max().item() for a, b in zip(lo, g["ref_logits_lo"]))
+    assert dmax < 1e-3, f"max |dlogit| vs reference = {dmax}"   # north-star tolerance (fp32 logits)
+    assert _tie_band_ok(lo, g["ref_logits_lo"], labels, g["ref_labels"], tuple(g["out_size"]), n) == 0
+    total = sum(b.numel() for b in g["ref_labels"])
+    mism = sum((a.cpu().to(torch.uint8) != b).sum().item() for a, b in zip(labels, g["ref_labels"]))
+    assert mism <= 2e-4 * total
+
+
+@pytest.mark.parametrize("model_name,H,W,objs", [("r50_aotl", 241, 321, 10), ("r50_deaotl", 241, 321, 7)])
+def test_engine_vs_oracle_memory_growth(model_name, H, W, objs):
+    """Mid-size clip with the long-term bank growing every 2nd frame: logits + bank contents."""
+    from oracle import aot_oracle as O
+    from oracle import weights as OW
+    sd = OW.build_state_dict(model_name, seed=3)
+    frames, mask = O.synthetic_video(6, H, W, objs, seed=99)
+    oe = O.OracleEngine(sd, O.OracleConfig(model_name), long_term_mem_gap=2)
+    with torch.no_grad():
+        o_lo, o_labels = O.run_video(oe, frames, mask, objs, (H - 1, W - 1))
+    eng = _build_cuda_engine(model_name, sd, 2)
+    with torch.no_grad():
+        c_lo, c_labels = O.run_video(eng, [f.cuda() for f in frames], mask.cuda(), objs, (H - 1, W - 1),
+                                     forced_masks=o_labels)
+    n = objs + 1
+    dmax = max((a.cpu()[:, :n] - b[:, :n]).abs().max().item() for a, b in zip(c_lo, o_lo))
+    assert dmax < 1e-3, dmax
+    # bank: same rows as the oracle's (prepended) memory, as a set of frames
+    e0 = eng.aot_engines[0]
+    o_mem = oe.long_term_memories
+    c_mem = e0.long_term_memories
+    N = e0.enc_hw
+    assert c_mem[0][0].shape[0] == o_mem[0][0].shape[0]
+    nfr = c_mem[0][0].shape[0] // N
+    for li in range(len(o_mem)):
+        for slot in (0, 1, 3) if model_name.endswith("deaotl") else (0, 1):
+            a = c_mem[li][slot].cpu().view(nfr, N, -1)
+            b = o_mem[li][slot].view(nfr, N, -1).flip(0)     # oracle prepends, the bank appends
+            assert (a - b).abs().max().item() < 1e-3 * max(1.0, b.abs().max().item())
+
+
+def test_multi_object_engines_share_encoding():
+    """> 10 objects: ceil(n/10) sub-engines, merged logits [1, 1+10*k, H, W] (aot_engine.py:584-623)."""
+    from oracle import aot_oracle as O
+    from oracle import weights as OW
+    sd = OW.build_state_dict("aott", seed=2)
+    frames, mask = O.synthetic_video(3, 129, 161, 14, seed=5)
+    eng = _build_cuda_engine("aott", sd, 9999)
+    with torch.no_grad():
+        eng.restart_engine()
+        eng.add_reference_frame(frames[0].cuda(), mask.cuda(), obj_nums=[14], frame_step=0)
+        assert len(eng.aot_engines) == 2
+        eng.match_propogate_one_frame(frames[1].cuda())
+        lg = eng.decode_current_logits((129, 161))
+        assert lg.shape == (1, 21, 129, 161) and torch.isfinite(lg).all()
+        lab = lg.argmax(1, keepdim=True).float()
+        eng.update_memory(lab)
+        # sub-engine 1 must equal a single oracle engine fed the separated mask (ids 11..14 -> 1..4)
+        sep = ((mask >= 11) & (mask <= 20)).float()
+        sep = (sep * mask - 11 + 1) * sep
+        oe = O.OracleEngine(sd, O.OracleConfig("aott"))
+        oe.add_reference_frame(frames[0], sep, [4], 0)
+        oe.match_propogate_one_frame(frames[1])
+        ol = oe.decode_current_logits(None)
+        cl = eng.aot_engines[1].pred_id_logits.cpu()
+        assert (cl[:, :5] - ol[:, :5]).abs().max().item() < 1e-3
+
+
+def test_engine_refuses_cpu():
+    from aot_benchmark_b200 import EngineConfig, build_engine, build_vos_model
+    cfg = EngineConfig("t", "aott")
+    model = build_vos_model(cfg.MODEL_VOS, cfg).cuda().eval()
+    eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=0)
+    with pytest.raises(RuntimeError):
+        eng.add_reference_frame(torch.zeros(1, 3, 65, 65), torch.zeros(1, 1, 65, 65), obj_nums=[1], frame_step=0)
