@@ -1,0 +1,396 @@
+// Long-term attention (K1) on the 5th-gen tensor cores: fused Q K^T -> softmax -> P V, AOT head shape
+// (H heads x d = 32), scores never leave the SM.
+//
+// Reference computation: MultiheadAttention.forward(use_linear=False), networks/layers/attention.py:82-117,
+// called at networks/layers/transformer.py:346 (long-term) and :324 (self-attention, Tk = N).
+//
+// Design (one CTA = 256 queries x 1 head x one KV split, 1 CTA / SM, 320 threads):
+//   warp 8      TMA producer: Q tiles once, then a 3-stage ring of K/V tiles (128 keys) via
+//               cp.async.bulk.tensor + mbarrier complete_tx
+//   warp 9      tcgen05.mma issuer (one elected thread): S_i = Q_i K_j^T into TMEM, later O_i += P_i V_j
+//   warps 0-3   softmax warpgroup 0 (query rows   0..127): one thread = one row; tcgen05.ld S -> row max /
+//   warps 4-7   softmax warpgroup 1 (query rows 128..255)  ex2 / row sum in registers -> P back into TMEM
+//               (aliasing S) as the A operand of the PV MMA; the two groups ping-pong so MUFU and the
+//               tensor pipe overlap (issue order PV_0, S_0', PV_1, S_1').
+//   TMEM        S_0 | S_1 (128 fp32 columns each, P aliases them) | O_0 | O_1 (64 columns each)
+//
+// Precision ("fp16x2"): every fp32 operand x is carried as hi = fp16(x), lo = fp16(x - hi); rows of the
+// packed operands are [hi(32) | lo(32)] halfs = 128 bytes (the same bytes as fp32, one TMA swizzle atom).
+//   exact mode  S = Qh Kh + Ql Kh + Qh Kl   (6 MMAs of 128x128x16),  O' = (Ph + Pl) [Vh | Vl]  (16 MMAs 128x64x16)
+//   fast mode   S = Qh Kh                   (2 MMAs),               O' =  Ph       [Vh | Vl]  ( 8 MMAs)
+// and O = O'[:, :32] + O'[:, 32:].  With d = 32 the kernel is MUFU(ex2)-bound (128 tensor FLOPs per
+// exponential), so the extra MMAs of the exact mode ride in otherwise idle tensor-pipe slots.
+// fp32 accumulation everywhere; Q is pre-divided by T (true division, attention.py:82) when packed.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace aotb {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, STAGES = 3, NTHREADS = 320;
+constexpr int TILE_BYTES = BN * 128;  // 128 rows x 128 B
+constexpr float LOG2E = 1.4426950408889634f;
+
+int make_tmap_rows64(CUtensorMap* out, const void* base, int rows, int heads) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+            set_error("cuTensorMapEncodeTiled entry point unavailable");
+            return AOTB_ERR_CUDA;
+        }
+        fn = (PFN_encodeTiled)p;
+    }
+    cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)heads};
+    cuuint64_t strides[2] = {128, (cuuint64_t)rows * 128};  // bytes, dims 1..2
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return AOTB_ERR_CUDA;
+    }
+    return AOTB_OK;
+}
+
+struct LtArgs {
+    int N, Tk;
+    const int* Tk_dev;
+    int H;
+    float* O;
+    int ldo;
+    float* Opart;
+    float* Mpart;
+    float* Lpart;
+    int splits;
+    int exact;
+    float* dbg;  // optional: CTA (0,0,0) dumps S_0(tile 0) [128][128] then O'_0 [128][64]
+};
+
+struct __align__(8) Barriers {
+    uint64_t q_full;
+    uint64_t kv_full[STAGES];
+    uint64_t kv_free[STAGES];
+    uint64_t s_full[2];
+    uint64_t p_full[2];
+    uint64_t o_final[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const LtArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;                                  // 2 tiles
+    uint8_t* sK = sQ + 2 * TILE_BYTES;                   // STAGES tiles
+    uint8_t* sV = sK + STAGES * TILE_BYTES;              // STAGES tiles
+    Barriers* B = reinterpret_cast<Barriers*>(sV + STAGES * TILE_BYTES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * (2 * BM), h = blockIdx.y, z = blockIdx.z;
+    const int Tk = a.Tk_dev ? *a.Tk_dev : a.Tk;
+    const int tiles_total = (Tk + BN - 1) / BN;
+    const int per = (tiles_total + a.splits - 1) / a.splits;
+    const int tb = z * per;
+    int T = tiles_total - tb;
+    T = T < 0 ? 0 : (T > per ? per : T);
+
+    if (tid == 0) {
+        mbar_init(&B->q_full, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&B->kv_full[s], 1); mbar_init(&B->kv_free[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&B->s_full[i], 1); mbar_init(&B->p_full[i], BM); mbar_init(&B->o_final[i], 1); }
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc<512>(&B->tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = B->tmem_base;
+
+    if (warp == 8) {
+        // ======================= TMA producer =======================
+        if (elect_one() && T > 0) {
+            tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+            mbar_arrive_expect_tx(&B->q_full, 2 * TILE_BYTES);
+            tma_load_3d(sQ, &tmQ, &B->q_full, 0, q0, h);
+            tma_load_3d(sQ + TILE_BYTES, &tmQ, &B->q_full, 0, q0 + BM, h);
+            for (int j = 0; j < T; ++j) {
+                const int s = j % STAGES;
+                if (j >= STAGES) mbar_wait(&B->kv_free[s], ((j / STAGES) - 1) & 1);
+                mbar_arrive_expect_tx(&B->kv_full[s], 2 * TILE_BYTES);
+                tma_load_3d(sK + s * TILE_BYTES, &tmK, &B->kv_full[s], 0, (tb + j) * BN, h);
+                tma_load_3d(sV + s * TILE_BYTES, &tmV, &B->kv_full[s], 0, (tb + j) * BN, h);
+            }
+        }
+    } else if (warp == 9) {
+        // ======================= MMA issuer =======================
+        if (elect_one() && T > 0) {
+            constexpr uint32_t IDESC_S = idesc_f16(128, 128, 0, 0);
+            constexpr uint32_t IDESC_O = idesc_f16(128, 64, 0, 1);
+            const uint32_t qaddr = smem_u32(sQ), kaddr = smem_u32(sK), vaddr = smem_u32(sV);
+            auto issue_S = [&](int i, int s) {
+                const uint32_t qa = qaddr + i * TILE_BYTES, ka = kaddr + s * TILE_BYTES;
+                const uint32_t d = tmem + i * 128;
+                // k-slices of 16 halfs = 32 B inside the 128 B row: 0,1 = hi ; 2,3 = lo
+                mma_ss(d, smem_desc_sw128(qa + 0), smem_desc_sw128(ka + 0), IDESC_S, 0);
+                mma_ss(d, smem_desc_sw128(qa + 32), smem_desc_sw128(ka + 32), IDESC_S, 1);
+                if (a.exact) {
+                    mma_ss(d, smem_desc_sw128(qa + 64), smem_desc_sw128(ka + 0), IDESC_S, 1);
+                    mma_ss(d, smem_desc_sw128(qa + 96), smem_desc_sw128(ka + 32), IDESC_S, 1);
+                    mma_ss(d, smem_desc_sw128(qa + 0), smem_desc_sw128(ka + 64), IDESC_S, 1);
+                    mma_ss(d, smem_desc_sw128(qa + 32), smem_desc_sw128(ka + 96), IDESC_S, 1);
+                }
+            };
+            auto issue_PV = [&](int i, int s, uint32_t acc) {
+                const uint32_t va = vaddr + s * TILE_BYTES;
+                const uint32_t d = tmem + 256 + i * 64;
+                const uint32_t p = tmem + i * 128;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    mma_ts(d, p + 8 * kk, smem_desc_sw128(va + kk * 2048), IDESC_O, (kk > 0) ? 1u : acc);
+                }
+                if (a.exact) {
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        mma_ts(d, p + 64 + 8 * kk, smem_desc_sw128(va + kk * 2048), IDESC_O, 1);
+                }
+            };
+            mbar_wait(&B->q_full, 0);
+            mbar_wait(&B->kv_full[0], 0);
+            tc_fence_after();
+            issue_S(0, 0); mma_commit(&B->s_full[0]);
+            issue_S(1, 0); mma_commit(&B->s_full[1]);
+            for (int j = 0; j < T; ++j) {
+                const int s = j % STAGES;
+                for (int i = 0; i < 2; ++i) {
+                    mbar_wait(&B->p_full[i], j & 1);
+                    tc_fence_after();
+                    issue_PV(i, s, j > 0 ? 1u : 0u);
+                    if (i == 1) mma_commit(&B->kv_free[s]);
+                    if (j + 1 < T) {
+                        const int s2 = (j + 1) % STAGES;
+                        if (i == 0) { mbar_wait(&B->kv_full[s2], ((j + 1) / STAGES) & 1); tc_fence_after(); }
+                        issue_S(i, s2);
+                        mma_commit(&B->s_full[i]);
+                    } else {
+                        mma_commit(&B->o_final[i]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ======================= softmax warpgroups =======================
+        const int wg = warp >> 2, wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const uint32_t tS = tmem + lane_addr + wg * 128;
+        const uint32_t tO = tmem + lane_addr + 256 + wg * 64;
+        const int q = q0 + wg * BM + row;
+        const bool dump = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && wg == 0;
+        float m_used = -INFINITY, l = 0.f;
+
+        for (int j = 0; j < T; ++j) {
+            mbar_wait(&B->s_full[wg], j & 1);
+            tc_fence_after();
+            uint32_t sr[128];
+            tmem_ld32(tS + 0, sr);
+            tmem_ld32(tS + 32, sr + 32);
+            tmem_ld32(tS + 64, sr + 64);
+            tmem_ld32(tS + 96, sr + 96);
+            tmem_wait_ld();
+            if (dump && j == 0) {
+#pragma unroll
+                for (int k = 0; k < 128; ++k) a.dbg[row * 128 + k] = __uint_as_float(sr[k]);
+            }
+            const int key0 = (tb + j) * BN;
+            float mt = -INFINITY;
+            if (key0 + BN > Tk) {
+#pragma unroll
+                for (int k = 0; k < 128; ++k) {
+                    if (key0 + k >= Tk) sr[k] = __float_as_uint(-INFINITY);
+                    mt = fmaxf(mt, __uint_as_float(sr[k]));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 128; ++k) mt = fmaxf(mt, __uint_as_float(sr[k]));
+            }
+            const float m_new = fmaxf(m_used, mt);
+            const bool grow = (m_new > m_used) && (j > 0);
+            if (__any_sync(0xffffffffu, grow)) {
+                // rescale the running output / sum of this warp's rows (O_i is quiescent here: every MMA issued
+                // before S_i(j) has completed, PV_i(j) is not issued until we arrive on p_full)
+                const float f = grow ? ex2((m_used - m_new) * LOG2E) : 1.f;
+                uint32_t orr[32];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    tmem_ld32(tO + 32 * c, orr);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) orr[k] = __float_as_uint(__uint_as_float(orr[k]) * f);
+                    tmem_st32(tO + 32 * c, orr);
+                }
+                l *= f;
+            }
+            m_used = m_new;
+            const float neg = m_used * LOG2E;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t ph[16], pl[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const float p0 = ex2(fmaf(__uint_as_float(sr[32 * c + 2 * t]), LOG2E, -neg));
+                    const float p1 = ex2(fmaf(__uint_as_float(sr[32 * c + 2 * t + 1]), LOG2E, -neg));
+                    l += p0 + p1;
+                    const __half2 hi = __floats2half2_rn(p0, p1);
+                    const __half2 lo = __floats2half2_rn(p0 - __low2float(hi), p1 - __high2float(hi));
+                    ph[t] = *reinterpret_cast<const uint32_t*>(&hi);
+                    pl[t] = *reinterpret_cast<const uint32_t*>(&lo);
+                }
+                tmem_st16(tS + 16 * c, ph);         // P_hi: columns [0, 64) of the S region
+                tmem_st16(tS + 64 + 16 * c, pl);    // P_lo: columns [64, 128)
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&B->p_full[wg]);
+        }
+
+        // ---- epilogue
+        float o[32];
+        if (T > 0) {
+            mbar_wait(&B->o_final[wg], 0);
+            tc_fence_after();
+            uint32_t o0[32], o1[32];
+            tmem_ld32(tO, o0);
+            tmem_ld32(tO + 32, o1);
+            tmem_wait_ld();
+            if (dump) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    a.dbg[128 * 128 + row * 64 + k] = __uint_as_float(o0[k]);
+                    a.dbg[128 * 128 + row * 64 + 32 + k] = __uint_as_float(o1[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(o0[k]) + __uint_as_float(o1[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = 0.f;
+        }
+        if (q < a.N) {
+            if (a.splits == 1) {
+                const float inv = 1.f / l;
+                float* dst = a.O + (size_t)q * a.ldo + h * 32;
+#pragma unroll
+                for (int k = 0; k < 32; k += 4)
+                    *reinterpret_cast<float4*>(dst + k) = make_float4(o[k] * inv, o[k + 1] * inv, o[k + 2] * inv, o[k + 3] * inv);
+            } else {
+                float* dst = a.Opart + ((size_t)z * a.N + q) * (a.H * 32) + h * 32;
+#pragma unroll
+                for (int k = 0; k < 32; k += 4)
+                    *reinterpret_cast<float4*>(dst + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+                a.Mpart[((size_t)z * a.H + h) * a.N + q] = m_used;
+                a.Lpart[((size_t)z * a.H + h) * a.N + q] = l;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------ operand packing
+// src fp32 [rows][ld] (head h at columns h*32) -> dst halfs [H][cap][64] at row offset: [hi(32) | lo(32)]
+__global__ void pack_rows64_kernel(const float* __restrict__ src, int ld, __half* __restrict__ dst, int cap, int rows,
+                                   int H, int row_off, const int* __restrict__ row_off_dev, float div) {
+    const int off = row_off_dev ? *row_off_dev : row_off;
+    const size_t total = (size_t)rows * H * 8;  // 4 channels per thread
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = i % 8;
+        const int hh = (i / 8) % H;
+        const int r = i / (8 * (size_t)H);
+        float4 v = *reinterpret_cast<const float4*>(src + (size_t)r * ld + hh * 32 + c4 * 4);
+        if (div != 1.f) { v.x = v.x / div; v.y = v.y / div; v.z = v.z / div; v.w = v.w / div; }
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        const __half2 l0 = __floats2half2_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+        const __half2 l1 = __floats2half2_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+        __half* d = dst + ((size_t)hh * cap + off + r) * 64 + c4 * 4;
+        *reinterpret_cast<__half2*>(d) = h0;
+        *reinterpret_cast<__half2*>(d + 2) = h1;
+        *reinterpret_cast<__half2*>(d + 32) = l0;
+        *reinterpret_cast<__half2*>(d + 34) = l1;
+    }
+}
+
+}  // namespace tc
+}  // namespace aotb
+
+using namespace aotb;
+
+// Pack fp32 rows into the split-fp16 operand layout of the tensor-core attention kernel.
+// src [rows][ld] fp32, dst [H][cap][64] fp16; written at rows [row_off, row_off+rows) (device counter optional);
+// values are divided by `div` first (T for Q -- attention.py:82 -- 1 for K/V).
+extern "C" int aotb_tc_pack_rows_f16x2(const float* src, int ld, void* dst, int cap, int rows, int H, int row_off,
+                                       const int* row_off_dev, float div, void* stream) {
+    AOTB_REQUIRE(src && dst && rows > 0 && H > 0 && ld % 4 == 0 && cap > 0, "aotb_tc_pack_rows_f16x2: bad args");
+    AOTB_REQUIRE(row_off_dev || row_off + rows <= cap, "aotb_tc_pack_rows_f16x2: rows exceed capacity");
+    const size_t total = (size_t)rows * H * 8;
+    int g = (int)((total + 255) / 256);
+    if (g > 148 * 8) g = 148 * 8;
+    tc::pack_rows64_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(src, ld, (__half*)dst, cap, rows, H, row_off,
+                                                                row_off_dev, div);
+    return check_launch("aotb_tc_pack_rows_f16x2");
+}
+
+extern "C" size_t aotb_lt_attn_tc_smem_bytes(void) {
+    return (size_t)(2 + 2 * tc::STAGES) * tc::TILE_BYTES + sizeof(tc::Barriers) + 1024;
+}
+
+// Qp [H][Nq_cap][64], Kp/Vp [H][kv_cap][64] packed fp16x2 operands (zero-filled beyond the live rows);
+// O [N][ldo] fp32 (head h at columns h*32).  splits > 1 writes un-normalised partials
+// (Opart [splits][N][H*32], Mpart/Lpart [splits][H][N]) for aotb_attn_merge_f32.
+extern "C" int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp, const void* Vp, int kv_cap, int N,
+                                     int Tk, const int* Tk_dev, int H, float* O, int ldo, float* Opart, float* Mpart,
+                                     float* Lpart, int splits, int exact, float* dbg, void* stream) {
+    AOTB_REQUIRE(Qp && Kp && Vp && N > 0 && H > 0 && (Tk > 0 || Tk_dev) && splits >= 1,
+                 "aotb_lt_attn_tc_f16x2: bad args");
+    AOTB_REQUIRE(Nq_cap >= ((N + 255) / 256) * 256, "aotb_lt_attn_tc_f16x2: Q buffer must be padded to 256 rows");
+    AOTB_REQUIRE(splits == 1 ? (O != nullptr && ldo % 4 == 0) : (Opart && Mpart && Lpart),
+                 "aotb_lt_attn_tc_f16x2: output buffers");
+    AOTB_REQUIRE(((uintptr_t)Qp | (uintptr_t)Kp | (uintptr_t)Vp) % 128 == 0, "aotb_lt_attn_tc_f16x2: alignment");
+    CUtensorMap tq, tk, tv;
+    int rc;
+    if ((rc = tc::make_tmap_rows64(&tq, Qp, Nq_cap, H)) != AOTB_OK) return rc;
+    if ((rc = tc::make_tmap_rows64(&tk, Kp, kv_cap, H)) != AOTB_OK) return rc;
+    if ((rc = tc::make_tmap_rows64(&tv, Vp, kv_cap, H)) != AOTB_OK) return rc;
+    const size_t smem = aotb_lt_attn_tc_smem_bytes();
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::lt_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("aotb_lt_attn_tc_f16x2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return AOTB_ERR_CUDA;
+        }
+        configured = true;
+    }
+    tc::LtArgs a;
+    a.N = N; a.Tk = Tk; a.Tk_dev = Tk_dev; a.H = H; a.O = O; a.ldo = ldo;
+    a.Opart = Opart; a.Mpart = Mpart; a.Lpart = Lpart; a.splits = splits; a.exact = exact; a.dbg = dbg;
+    dim3 grid(cdiv(N, 2 * tc::BM), H, splits);
+    tc::lt_attn_tc_kernel<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(tq, tk, tv, a);
+    return check_launch("aotb_lt_attn_tc_f16x2");
+}

@@ -206,3 +206,36 @@ def bank_append(src, bank, offset, offset_dev=None, stream=None):
                                      offset_dev.data_ptr() if offset_dev is not None else None, _st(stream)),
           "aotb_bank_append_f32")
     return bank
+
+
+# ------------------------------------------------------------------ tensor-core long-term attention
+def tc_pack_rows(src, dst, row_off=0, div=1.0, row_off_dev=None, stream=None):
+    """src fp32 [rows, H*32] -> dst fp16 [H, cap, 64] rows [row_off, row_off+rows) as [hi(32) | lo(32)]."""
+    _chk(src)
+    if dst.dtype != torch.float16 or not dst.is_cuda or not dst.is_contiguous():
+        raise AotbError("packed operand buffer must be a contiguous fp16 CUDA tensor [H, cap, 64]")
+    H, cap, _ = dst.shape
+    rows = src.shape[0]
+    check(lib().aotb_tc_pack_rows_f16x2(_p(src), src.stride(0), dst.data_ptr(), cap, rows, H, int(row_off),
+                                        row_off_dev.data_ptr() if row_off_dev is not None else None, float(div),
+                                        _st(stream)), "aotb_tc_pack_rows_f16x2")
+    return dst
+
+
+def lt_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True, part=None, dbg=None, stream=None):
+    """Qp [H, Nq_cap, 64], Kp/Vp [H, kv_cap, 64] packed fp16x2; O [N, H*32] fp32.
+    With splits > 1, `part` = (Opart [S,N,H*32], Mpart [S,H,N], Lpart [S,H,N]) and O receives the merge."""
+    H, nq_cap, _ = Qp.shape
+    kv_cap = Kp.shape[1]
+    if splits > 1:
+        Op, Mp, Lp = part
+    else:
+        Op = Mp = Lp = None
+    check(lib().aotb_lt_attn_tc_f16x2(Qp.data_ptr(), nq_cap, Kp.data_ptr(), Vp.data_ptr(), kv_cap, N, int(Tk),
+                                      Tk_dev.data_ptr() if Tk_dev is not None else None, H,
+                                      _p(O) if splits == 1 else None, O.stride(0) if O is not None else 0,
+                                      _p(Op), _p(Mp), _p(Lp), splits, 1 if exact else 0, _p(dbg), _st(stream)),
+          "aotb_lt_attn_tc_f16x2")
+    if splits > 1:
+        attn_merge(Op, Mp, Lp, O, H, 32, stream=stream)
+    return O

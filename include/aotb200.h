@@ -103,6 +103,22 @@ int aotb_logits_argmax_f32(const float* lowres_nchw, float* label, int h, int w,
 /* F.interpolate(mode="nearest") of a label map: networks/managers/evaluator.py:418-421. */
 int aotb_nearest_resize_f32(const float* in, float* out, int H, int W, int Ho, int Wo, void* stream);
 
+/* Tensor-core long-term attention (tcgen05 + TMEM + TMA), AOT head shape H x 32, split-fp16 ("fp16x2")
+ * operands: every fp32 value x is stored as hi = fp16(x), lo = fp16(x - hi) in rows [hi(32) | lo(32)].
+ * networks/layers/attention.py:82-117 called from networks/layers/transformer.py:346 (and :324, Tk = N).
+ *   aotb_tc_pack_rows_f16x2: fp32 [rows][ld] -> packed [H][cap][64] at a row offset, values / div first
+ *                            (div = T for Q, attention.py:82; 1 for K and V).  Buffers must be zero-filled
+ *                            beyond the live rows.
+ *   aotb_lt_attn_tc_f16x2  : exact = 1 -> S = QhKh + QlKh + QhKl, O = (Ph + Pl)[Vh|Vl] (fp32-faithful);
+ *                            exact = 0 -> S = QhKh, O = Ph[Vh|Vl].  splits > 1 writes split-KV partials
+ *                            for aotb_attn_merge_f32.  dbg (optional) receives S and O' of CTA 0. */
+int aotb_tc_pack_rows_f16x2(const float* src, int ld, void* dst, int cap, int rows, int H, int row_off,
+                            const int* row_off_dev, float div, void* stream);
+size_t aotb_lt_attn_tc_smem_bytes(void);
+int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp, const void* Vp, int kv_cap, int N, int Tk,
+                          const int* Tk_dev, int H, float* O, int ldo, float* Opart, float* Mpart, float* Lpart,
+                          int splits, int exact, float* dbg, void* stream);
+
 /* Long-term memory append in place (replaces torch.cat, networks/engines/aot_engine.py:291-305). */
 int aotb_bank_append_f32(const float* src, int lds, float* bank, int ldb, int rows, int cols, int offset,
                          const int* offset_dev, void* stream);

@@ -1,0 +1,104 @@
+"""GPU: the tcgen05 long-term attention kernel (lt_attn_tc.cu) vs the fp64 oracle and vs the fp32 SIMT
+kernel, in exact (fp16x2 split) and fast modes, with KV splits and a device-resident key count."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+H, D = 8, 32
+
+
+def _pack(x, cap, div=1.0):
+    from aot_benchmark_b200 import ops
+    dst = torch.zeros(H, cap, 64, dtype=torch.float16, device=x.device)
+    ops.tc_pack_rows(x, dst, 0, div)
+    return dst
+
+
+def _ref(Q, K, V):
+    from oracle import aot_oracle as O
+    return O.multihead_attention(Q.double().cpu().unsqueeze(1), K.double().cpu().unsqueeze(1),
+                                 V.double().cpu().unsqueeze(1), H)[:, 0]
+
+
+def test_pack_rows_layout():
+    d = torch.device("cuda:0")
+    x = torch.randn(50, 256, device=d) * 3
+    p = _pack(x, 64, div=math.sqrt(32.0))
+    xs = (x / math.sqrt(32.0)).view(50, H, D).permute(1, 0, 2)
+    hi = xs.half()
+    lo = (xs - hi.float()).half()
+    assert torch.equal(p[:, :50, :32], hi) and torch.equal(p[:, :50, 32:], lo)
+    assert p[:, 50:].abs().max().item() == 0
+    assert ((hi.float() + lo.float()) - xs).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("N,Tk,qs,exact,tol", [
+    (128, 128, 1.0, True, 3e-5),
+    (300, 700, 1.0, True, 3e-5),
+    (1674, 5022, 4.0, True, 3e-5),
+    (300, 700, 1.0, False, 5e-3),
+    (1674, 3348, 2.0, False, 2e-2),
+])
+def test_lt_attention_tc(N, Tk, qs, exact, tol):
+    from aot_benchmark_b200 import ops
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(N + Tk)
+    Q = (torch.randn(N, 256, generator=g) * qs).to(d)
+    K = torch.randn(Tk, 256, generator=g).to(d)
+    V = torch.randn(Tk, 256, generator=g).to(d)
+    ref = _ref(Q, K, V)
+    ncap = ((N + 255) // 256) * 256
+    kcap = ((Tk + 127) // 128) * 128 + 128
+    Qp, Kp, Vp = _pack(Q, ncap, math.sqrt(32.0)), _pack(K, kcap), _pack(V, kcap)
+    O = torch.full((N, 256), float("nan"), device=d)
+    dbg = torch.zeros(128 * 128 + 128 * 64, device=d)
+    ops.lt_attention_tc(Qp, Kp, Vp, N, Tk, O=O, exact=exact, dbg=dbg)
+    torch.cuda.synchronize()
+    err = (O.cpu().double() - ref).abs().max().item()
+    if not (err < tol):
+        # diagnostics: raw scores of tile (q 0..127, keys 0..127, head 0) and the un-normalised output
+        S = dbg[:128 * 128].view(128, 128).cpu().double()
+        nq, nk = min(N, 128), min(Tk, 128)
+        Sref = (Q[:nq, :32].double().cpu() / math.sqrt(32.0)) @ K[:nk, :32].double().cpu().t()
+        print("S err", (S[:nq, :nk] - Sref).abs().max().item(), "S ref max", Sref.abs().max().item())
+        print("S[0,:8]", S[0, :8].tolist(), "ref", Sref[0, :8].tolist())
+        Od = dbg[128 * 128:].view(128, 64).cpu()
+        print("O' row0", Od[0, :8].tolist(), Od[0, 32:40].tolist())
+    assert err < tol, f"max |dO| = {err}"
+
+
+def test_lt_attention_tc_matches_simt_and_splits():
+    from aot_benchmark_b200 import ops
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    N, Tk = 1674, 1674 * 4 + 77
+    Q = (torch.randn(N, 256, generator=g) * 3).to(d)
+    K = torch.randn(Tk, 256, generator=g).to(d)
+    V = torch.randn(Tk, 256, generator=g).to(d)
+    simt = torch.empty(N, 256, device=d)
+    ops.attention(Q, K, V, simt, H, D, D)
+    ncap, kcap = 1792, ((Tk + 127) // 128) * 128 + 256
+    Qp, Kp, Vp = _pack(Q, ncap, math.sqrt(32.0)), _pack(K, kcap), _pack(V, kcap)
+    O1 = torch.empty(N, 256, device=d)
+    ops.lt_attention_tc(Qp, Kp, Vp, N, Tk, O=O1, exact=True)
+    assert (O1 - simt).abs().max().item() < 3e-5
+    for splits in (2, 5):
+        part = (torch.empty(splits, N, 256, device=d), torch.empty(splits, H, N, device=d),
+                torch.empty(splits, H, N, device=d))
+        O2 = torch.empty(N, 256, device=d)
+        ops.lt_attention_tc(Qp, Kp, Vp, N, Tk, O=O2, splits=splits, exact=True, part=part)
+        assert (O2 - simt).abs().max().item() < 3e-5
+    tk_dev = torch.tensor([Tk], dtype=torch.int32, device=d)
+    O3 = torch.empty(N, 256, device=d)
+    ops.lt_attention_tc(Qp, Kp, Vp, N, 1, O=O3, Tk_dev=tk_dev, exact=True)
+    assert torch.equal(O3, O1)
+    # more splits than tiles: empty splits must contribute nothing
+    part = (torch.empty(8, 200, 256, device=d), torch.empty(8, H, 200, device=d), torch.empty(8, H, 200, device=d))
+    O4 = torch.empty(200, 256, device=d)
+    ops.lt_attention_tc(Qp, Kp, Vp, 200, 300, O=O4, splits=8, exact=True, part=part)
+    ref = torch.empty(200, 256, device=d)
+    ops.attention(Q[:200], K[:300], V[:300], ref, H, D, D)
+    assert (O4 - ref).abs().max().item() < 3e-5
