@@ -29,7 +29,31 @@ A_NONE, A_RELU, A_GELU, A_SILU, A_RELU6 = ops.ACT_NONE, ops.ACT_RELU, ops.ACT_GE
 # bench.py hook: when set to a list, every long-term attention launch appends
 # (start_event, end_event, algorithmic_flops) so the roofline is measured live, per launch.
 LT_PROBE = None
-LT_KERNEL_NAME = "attn_f32_kernel<32,32> (fp32 SIMT flash attention)"
+# long-term attention implementation for the AOT head shape (8 x 32):
+#   "tc_exact" tcgen05 kernel, split-fp16 operands, fp32-faithful   (lt_attn_tc.cu)
+#   "tc_fast"  tcgen05 kernel, single fp16 pass for Q K^T and P
+#   "simt"     fp32 CUDA-core flash kernel                          (attention_simt.cu)
+import os as _os
+LT_IMPL = _os.environ.get("AOTB_LT_IMPL", "simt")
+_LT_NAMES = {"simt": "attn_f32_kernel<32,32> (fp32 SIMT flash attention)",
+             "tc_exact": "lt_attn_tc_kernel (tcgen05 fp16x2 exact: 6+16 MMAs/tile)",
+             "tc_fast": "lt_attn_tc_kernel (tcgen05 fp16 fast: 2+8 MMAs/tile)"}
+LT_KERNEL_NAME = _LT_NAMES.get(LT_IMPL, LT_IMPL)
+
+
+def lt_splits(n_queries, heads, tk, sms=148):
+    """KV-split count for the tensor-core kernel: fill whole waves of `sms` CTAs (one CTA = 256 queries x
+    1 head x 1 split) while keeping >= 2 key tiles per split."""
+    base = ((n_queries + 255) // 256) * heads
+    tiles = (tk + 127) // 128
+    effs = []
+    for s in range(1, 17):
+        if s > 1 and tiles < 2 * s:
+            break
+        ctas = base * s
+        effs.append((s, ctas / (((ctas + sms - 1) // sms) * sms)))
+    top = max(e for _, e in effs)
+    return next(s for s, e in effs if e >= top - 0.05)     # fewest splits within 5 % of the best wave fill
 
 
 def _pos_emb_sine(h, w, npf=128):
@@ -261,6 +285,13 @@ class AOTEngine(nn.Module):
         self.bank_K = [f(cap, self._kdim) for _ in range(L)]
         self.bank_V = [f(cap, self._vdim) for _ in range(L)]
         self.bank_len = 0
+        self._tc = LT_IMPL.startswith("tc") and (not P.deaot) and (C // P.H == 32)
+        if self._tc:
+            hz = lambda *s: torch.zeros(s, dtype=torch.float16, device=dev)
+            ws.Qp = hz(P.H, ((N + 255) // 256) * 256, 64)
+            self.bank_Kp = [hz(P.H, cap, 64) for _ in range(L)]     # split-fp16 copies read by TMA
+            self.bank_Vp = [hz(P.H, cap, 64) for _ in range(L)]
+            ws.part = {}
         self._st_ring = []
         self._ws = ws
         self._dec_bufs = {}
@@ -274,6 +305,12 @@ class AOTEngine(nn.Module):
                 nb = torch.empty((new_cap, old.shape[1]), dtype=torch.float32, device=old.device)
                 nb[: self.bank_len].copy_(old[: self.bank_len])
                 lst[i] = nb
+        if self._tc:
+            for lst in (self.bank_Kp, self.bank_Vp):
+                for i, old in enumerate(lst):
+                    nb = torch.zeros((old.shape[0], new_cap, 64), dtype=torch.float16, device=old.device)
+                    nb[:, : self.bank_len].copy_(old[:, : self.bank_len])
+                    lst[i] = nb
         self.bank_cap = new_cap
 
     # ------------------------------------------------------------------ reference-shaped views
@@ -399,6 +436,9 @@ class AOTEngine(nn.Module):
         for li in range(self._plan().L):
             ops.bank_append(K_src[li], self.bank_K[li], self.bank_len, stream=st)
             ops.bank_append(V_src[li], self.bank_V[li], self.bank_len, stream=st)
+            if self._tc:
+                ops.tc_pack_rows(K_src[li], self.bank_Kp[li], self.bank_len, stream=st)
+                ops.tc_pack_rows(V_src[li], self.bank_Vp[li], self.bank_len, stream=st)
         self.bank_len += N
 
     def _latest_kv(self):
@@ -460,10 +500,27 @@ class AOTEngine(nn.Module):
         P = self._plan()
         d = P.C // P.H
         probe = LT_PROBE
+        use_tc = self._tc and (K is self.bank_K[li])
+        if use_tc:
+            ws = self._ws
+            N = Q.shape[0]
+            splits = lt_splits(N, P.H, Tk)
+            part = None
+            if splits > 1:
+                part = ws.part.get(splits)
+                if part is None:
+                    fz = lambda *s: torch.empty(s, dtype=torch.float32, device=Q.device)
+                    part = (fz(splits, N, P.C), fz(splits, P.H, N), fz(splits, P.H, N))
+                    ws.part[splits] = part
+            ops.tc_pack_rows(Q, ws.Qp, 0, div=math.sqrt(d), stream=st)      # Q / T (attention.py:82)
         if probe is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        ops.attention(Q, K, V, out, P.H, d, d, Tk=Tk, stream=st)
+        if use_tc:
+            ops.lt_attention_tc(ws.Qp, self.bank_Kp[li], self.bank_Vp[li], N, Tk, O=out, splits=splits,
+                                exact=(LT_IMPL == "tc_exact"), part=part, stream=st)
+        else:
+            ops.attention(Q, K, V, out, P.H, d, d, Tk=Tk, stream=st)
         if probe is not None:
             e1.record()
             probe.append((e0, e1, 4.0 * Q.shape[0] * Tk * P.C))

@@ -302,11 +302,41 @@ def local_window_aggregate(p: Tensor, v2d: Tensor, H: int, relv: Optional[Tensor
     return o.permute(3, 4, 0, 1, 2).reshape(h * w, n, cv)
 
 
-def local_attention(q2d, k2d, v2d, relk_w, relk_b, relv, H) -> Tensor:
-    """K2 / K2' before projection: softmax over the 225 window taps."""
+def local_attention_loop(q2d, k2d, v2d, relk_w, relk_b, relv, H) -> Tensor:
+    """K2 / K2' before projection, tap-by-tap form of SURVEY Appendix C (independent cross-check of
+    the unfold form below; slow on many-core hosts)."""
     s = local_window_scores(q2d, k2d, relk_w, relk_b, H)
     p = torch.softmax(s, dim=2)
     return local_window_aggregate(p, v2d, H, relv)
+
+
+def local_attention(q2d, k2d, v2d, relk_w, relk_b, relv, H, chunk: int = 256) -> Tensor:
+    """K2 / K2' before projection, in the reference's own `unfold` formulation
+    (attention.py:318-371 / :805-853): zero-padded F.unfold windows of k and v, scores + relative_emb_k(q)
+    (on UNSCALED q, :327) - 1e8 outside the frame (:355-357), softmax over the 225 taps, then
+    sum_w p * v_window (+ einsum with relative_emb_v, :363-364).  The dense local2global matmul of
+    :366-368 is the same sum.  v is processed in channel chunks to bound memory."""
+    n, c, h, w = q2d.shape
+    d = c // H
+    T = d ** 0.5
+    cv = v2d.shape[1]
+    dv = cv // H
+    P = WINDOW * WINDOW
+    rel = F.conv2d(q2d, relk_w, relk_b, groups=H).view(n, H, P, h * w)
+    ku = F.unfold(k2d, WINDOW, padding=MAX_DIS).view(n, H, d, P, h * w)
+    s = torch.einsum("nhdp,nhdwp->nhwp", (q2d / T).view(n, H, d, h * w), ku) + rel
+    inside = F.unfold(torch.ones(1, 1, h, w, dtype=q2d.dtype), WINDOW, padding=MAX_DIS).view(1, 1, P, h * w)
+    s = s - (1 - inside) * 1e8
+    p = torch.softmax(s, dim=2)
+    o = torch.empty(n, H, dv, h * w, dtype=v2d.dtype)
+    v5 = v2d.view(n, H, dv, h, w)
+    for c0 in range(0, dv, chunk):
+        c1 = min(dv, c0 + chunk)
+        vu = F.unfold(v5[:, :, c0:c1].reshape(n, H * (c1 - c0), h, w), WINDOW, padding=MAX_DIS)
+        o[:, :, c0:c1] = torch.einsum("nhwp,nhdwp->nhdp", p, vu.view(n, H, c1 - c0, P, h * w))
+    if relv is not None:
+        o = o + torch.einsum("nhwp,hcw->nhcp", p, relv)
+    return o.permute(3, 0, 1, 2).reshape(h * w, n, cv)
 
 
 # --------------------------------------------------------------------------------------

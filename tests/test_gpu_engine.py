@@ -122,3 +122,58 @@ def test_engine_refuses_cpu():
     eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=0)
     with pytest.raises(RuntimeError):
         eng.add_reference_frame(torch.zeros(1, 3, 65, 65), torch.zeros(1, 1, 65, 65), obj_nums=[1], frame_step=0)
+
+
+@pytest.mark.parametrize("impl,tol", [("tc_exact", 1e-3), ("tc_fast", 5e-2)])
+def test_engine_tensor_core_long_term_attention(impl, tol, golden_dir):
+    """Same golden clip with the long-term attention on the tcgen05 kernel."""
+    from aot_benchmark_b200 import engine as engine_mod
+    from oracle import aot_oracle as O
+    from oracle import weights as OW
+    g = torch.load(os.path.join(golden_dir, "video_r50_aotl_small.pt"))
+    sd = OW.build_state_dict(g["model"], seed=g["seed"], flavour=g["flavour"])
+    frames, mask = O.synthetic_video(g["frames"], g["H"], g["W"], g["objs"], seed=1234 + g["seed"])
+    old = engine_mod.LT_IMPL
+    engine_mod.LT_IMPL = impl
+    try:
+        eng = _build_cuda_engine(g["model"], sd, g["gap"])
+        forced = [l.float() for l in g["ref_labels"]]
+        with torch.no_grad():
+            lo, labels = O.run_video(eng, [f.cuda() for f in frames], mask.cuda(), g["objs"], tuple(g["out_size"]),
+                                     forced_masks=forced)
+        assert eng.aot_engines[0]._tc
+    finally:
+        engine_mod.LT_IMPL = old
+    n = g["objs"] + 1
+    dmax = max((a.cpu()[:, :n] - b[:, :n]).abs().max().item() for a, b in zip(lo, g["ref_logits_lo"]))
+    print(f"{impl}: max |dlogit| vs reference = {dmax:.3e}")
+    assert dmax < tol, dmax
+    if impl == "tc_exact":
+        assert _tie_band_ok(lo, g["ref_logits_lo"], labels, g["ref_labels"], tuple(g["out_size"]), n) == 0
+
+
+def test_engine_tc_exact_vs_oracle_sharp_attention():
+    """Sharper attention (linear_Q x8) and a bank of several frames: the exact tensor-core mode must stay within
+    the 1e-3 logit gate where a single fp16 pass does not have to."""
+    from aot_benchmark_b200 import engine as engine_mod
+    from oracle import aot_oracle as O
+    from oracle import weights as OW
+    sd = OW.build_state_dict("r50_aotl", seed=5, q_scale=8.0)
+    frames, mask = O.synthetic_video(6, 241, 321, 10, seed=11)
+    oe = O.OracleEngine(sd, O.OracleConfig("r50_aotl"), long_term_mem_gap=1)
+    with torch.no_grad():
+        o_lo, o_labels = O.run_video(oe, frames, mask, 10, (240, 320))
+    res = {}
+    for impl in ("tc_exact", "tc_fast", "simt"):
+        old = engine_mod.LT_IMPL
+        engine_mod.LT_IMPL = impl
+        try:
+            eng = _build_cuda_engine("r50_aotl", sd, 1)
+            with torch.no_grad():
+                c_lo, _ = O.run_video(eng, [f.cuda() for f in frames], mask.cuda(), 10, (240, 320),
+                                      forced_masks=o_labels)
+        finally:
+            engine_mod.LT_IMPL = old
+        res[impl] = max((a.cpu()[:, :11] - b[:, :11]).abs().max().item() for a, b in zip(c_lo, o_lo))
+    print("sharp-attention max |dlogit| vs oracle:", res)
+    assert res["tc_exact"] < 1e-3 and res["simt"] < 1e-3

@@ -43,6 +43,22 @@ def test_k2_local_attention(ops):
     assert (o - c["out"]).abs().max().item() < 1e-5
 
 
+def test_local_attention_two_formulations_agree():
+    """unfold form (used by the engine oracle) vs the tap-by-tap form of SURVEY Appendix C."""
+    g = torch.Generator().manual_seed(3)
+    for (H, d, dv, relv) in ((8, 32, 32, True), (1, 128, 1024, False)):
+        h, w = 10, 17
+        q = torch.randn(1, H * d, h, w, generator=g)
+        k = torch.randn(1, H * d, h, w, generator=g)
+        v = torch.randn(1, H * dv, h, w, generator=g)
+        rkw = torch.randn(H * 225, d, 1, 1, generator=g) * 0.1
+        rkb = torch.randn(H * 225, generator=g) * 0.1
+        rv = torch.randn(H, dv, 225, generator=g) * 0.2 if relv else None
+        a = O.local_attention(q, k, v, rkw, rkb, rv, H)
+        b = O.local_attention_loop(q, k, v, rkw, rkb, rv, H)
+        assert (a - b).abs().max().item() < 1e-5
+
+
 def test_k1p_gated_propagation(ops):
     c = ops["k1p"]
     o, _ = O.gated_propagation({"p." + k: v for k, v in c["sd"].items()}, "p.", c["Q"], c["K"], c["V"], c["U"],
