@@ -1,0 +1,291 @@
+// Implicit-GEMM convolution / linear layer on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), NHWC fp32
+// in / fp32 out, fp32-faithful through the split-fp16 ("fp16x2") scheme of lt_attn_tc.cu.
+//
+//   out[m][n] = act( sum_k A(m,k) * W[k][n] + bias[n] + res[m][n] )      m -> (b, oy, ox), k -> (ky, kx, ci)
+//
+// Same reference sites as conv_igemm.cu (resnet.py:34-54,140-157 with FrozenBatchNorm2d folded,
+// aot.py:19-21,83, fpn.py:34-58, every nn.Linear of transformer.py:321-367,582-665).  Eligibility:
+// Cin % 64 == 0, Cout % 64 == 0, dilation 1 (everything on the R50-AOTL path except the 3-channel stem and
+// the 11-channel conv_out, which stay on conv_igemm.cu).
+//
+// One CTA = 128 output pixels x BN output channels, 192 threads:
+//   warps 0-3  A producers: gather the fp32 activation rows of a 64-wide K chunk straight from NHWC global
+//              memory (im2col is never materialised; padding / stride handled per row), split every value into
+//              hi = fp16(x), lo = fp16(x - hi) and store both 128x64 tiles in the 128B-swizzled K-major layout
+//              the UMMA descriptor expects; afterwards the same warps run the epilogue
+//              (tcgen05.ld -> bias / residual / activation -> fp32 NHWC stores).
+//   warp 4     TMA producer for the pre-split weights (Wh, Wl as [Cout][K] fp16, K-major), 3-stage ring.
+//   warp 5     tcgen05.mma issuer: per 64-wide chunk 4 k-steps x (Ah*Wh + Al*Wh + Ah*Wl) into a 128 x BN fp32
+//              accumulator in TMEM.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace aotb {
+namespace tc {
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+struct ConvTcArgs {
+    const float* in;
+    const float* bias;
+    const float* res;
+    float* out;
+    int B, H, W, Cin, ldin;
+    int Ho, Wo, Cout, ldout, ldres;
+    int KH, KW, stride, pad;
+    int M, nchunks;
+    int act;
+};
+
+struct RowInfo { int pix_base, iy0, ix0, valid; };
+
+template <int BN, int STAGES>
+struct ConvSmem {
+    static constexpr int A_BYTES = 128 * 128;          // one 128 x 64 half tile
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 128 * (int)sizeof(RowInfo) + (3 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const ConvTcArgs a) {
+    using SM = ConvSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    RowInfo* rinfo = reinterpret_cast<RowInfo*>(smem + STAGES * SM::STAGE_BYTES);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(rinfo + 128);
+    uint64_t* b_full = a_full + STAGES;
+    uint64_t* s_free = b_full + STAGES;
+    uint64_t* acc_full = s_free + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&b_full[s], 1); mbar_init(&s_free[s], 1); }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (tid < 128) {
+        const int m = m0 + tid;
+        RowInfo ri;
+        if (m < a.M) {
+            const int HoWo = a.Ho * a.Wo;
+            const int b = m / HoWo, r = m - b * HoWo;
+            const int oy = r / a.Wo, ox = r - oy * a.Wo;
+            ri.pix_base = b * a.H * a.W;
+            ri.iy0 = oy * a.stride - a.pad;
+            ri.ix0 = ox * a.stride - a.pad;
+            ri.valid = 1;
+        } else {
+            ri.pix_base = 0; ri.iy0 = 0; ri.ix0 = 0; ri.valid = 0;
+        }
+        rinfo[tid] = ri;
+    }
+    if (warp == 5) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int cpt = a.Cin >> 6;  // 64-wide chunks per filter tap
+
+    if (warp < 4) {
+        // ======================= A producers =======================
+        const int q = tid & 15, rsub = tid >> 4;
+        for (int kc = 0; kc < a.nchunks; ++kc) {
+            const int s = kc % STAGES;
+            const int tap = kc / cpt, c0 = (kc - tap * cpt) << 6;
+            const int ky = tap / a.KW, kx = tap - ky * a.KW;
+            float4 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const RowInfo ri = rinfo[i * 8 + rsub];
+                const int iy = ri.iy0 + ky, ix = ri.ix0 + kx;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ri.valid && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+                    v[i] = __ldg(reinterpret_cast<const float4*>(
+                        a.in + (size_t)(ri.pix_base + iy * a.W + ix) * a.ldin + c0 + q * 4));
+            }
+            if (kc >= STAGES) mbar_wait(&s_free[s], ((kc / STAGES) - 1) & 1);
+            uint8_t* Ah = smem + s * SM::STAGE_BYTES;
+            uint8_t* Al = Ah + SM::A_BYTES;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int row = i * 8 + rsub;
+                const uint32_t off = row * 128 + (((q >> 1) ^ (row & 7)) << 4) + ((q & 1) << 3);
+                const __half2 h0 = __floats2half2_rn(v[i].x, v[i].y), h1 = __floats2half2_rn(v[i].z, v[i].w);
+                const __half2 l0 = __floats2half2_rn(v[i].x - __low2float(h0), v[i].y - __high2float(h0));
+                const __half2 l1 = __floats2half2_rn(v[i].z - __low2float(h1), v[i].w - __high2float(h1));
+                uint2 ph, pl;
+                ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+                pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+                *reinterpret_cast<uint2*>(Ah + off) = ph;
+                *reinterpret_cast<uint2*>(Al + off) = pl;
+            }
+            fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&a_full[s]);
+        }
+        // ======================= epilogue =======================
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int m = m0 + warp * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(trow + c, r);
+            tmem_wait_ld();
+            if (m < a.M) {
+                float* orow = a.out + (size_t)m * a.ldout + n0 + c;
+                const float* rrow = a.res ? a.res + (size_t)m * a.ldres + n0 + c : nullptr;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = __uint_as_float(r[j]); o.y = __uint_as_float(r[j + 1]);
+                    o.z = __uint_as_float(r[j + 2]); o.w = __uint_as_float(r[j + 3]);
+                    if (a.bias) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c + j));
+                        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                    }
+                    if (rrow) {
+                        const float4 rr = *reinterpret_cast<const float4*>(rrow + j);
+                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                    }
+                    o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act);
+                    o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
+                    *reinterpret_cast<float4*>(orow + j) = o;
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ======================= weight TMA producer =======================
+        if (elect_one()) {
+            tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
+            for (int kc = 0; kc < a.nchunks; ++kc) {
+                const int s = kc % STAGES;
+                if (kc >= STAGES) mbar_wait(&s_free[s], ((kc / STAGES) - 1) & 1);
+                uint8_t* Bh = smem + s * SM::STAGE_BYTES + 2 * SM::A_BYTES;
+                mbar_arrive_expect_tx(&b_full[s], 2 * SM::B_BYTES);
+                tma_load_2d(Bh, &tmWh, &b_full[s], kc * 64, n0);
+                tma_load_2d(Bh + SM::B_BYTES, &tmWl, &b_full[s], kc * 64, n0);
+            }
+        }
+    } else {
+        // ======================= MMA issuer =======================
+        if (elect_one()) {
+            constexpr uint32_t IDESC = idesc_f16(128, BN, 0, 0);
+            for (int kc = 0; kc < a.nchunks; ++kc) {
+                const int s = kc % STAGES;
+                const uint32_t ph = (kc / STAGES) & 1;
+                mbar_wait(&a_full[s], ph);
+                mbar_wait(&b_full[s], ph);
+                tc_fence_after();
+                const uint32_t ah = smem_u32(smem + s * SM::STAGE_BYTES), al = ah + SM::A_BYTES;
+                const uint32_t bh = al + SM::A_BYTES, bl = bh + SM::B_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t dah = smem_desc_sw128(ah + ks * 32), dal = smem_desc_sw128(al + ks * 32);
+                    const uint64_t dbh = smem_desc_sw128(bh + ks * 32), dbl = smem_desc_sw128(bl + ks * 32);
+                    mma_ss(tmem, dah, dbh, IDESC, (kc | ks) ? 1u : 0u);
+                    mma_ss(tmem, dal, dbh, IDESC, 1u);
+                    mma_ss(tmem, dah, dbl, IDESC, 1u);
+                }
+                mma_commit(&s_free[s]);
+            }
+            mma_commit(acc_full);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc<BN>(tmem);
+}
+
+static int make_tmap_weights(CUtensorMap* out, const void* base, int Kpad, int Cout, int BN) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+            set_error("cuTensorMapEncodeTiled entry point unavailable");
+            return AOTB_ERR_CUDA;
+        }
+        fn = (PFN_encodeTiled)p;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
+        return AOTB_ERR_CUDA;
+    }
+    return AOTB_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_conv_tc(const CUtensorMap& th, const CUtensorMap& tl, const ConvTcArgs& a, cudaStream_t st) {
+    constexpr int smem = ConvSmem<BN, STAGES>::TOTAL;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error("aotb_conv2d_nhwc_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return AOTB_ERR_CUDA;
+        }
+        configured = true;
+    }
+    dim3 grid(cdiv(a.M, 128), a.Cout / BN);
+    conv_tc_kernel<BN, STAGES><<<grid, 192, smem, st>>>(th, tl, a);
+    return check_launch("aotb_conv2d_nhwc_tc");
+}
+
+}  // namespace tc
+}  // namespace aotb
+
+using namespace aotb;
+
+// wh / wl: pre-split weights [Cout][K] fp16 (K = KH*KW*Cin, ordered (ky,kx,ci)), from aotb-side packing.
+extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* wl, const float* bias, const float* res,
+                                   float* out, int B, int H, int W, int Cin, int ldin, int Cout, int ldout, int ldres,
+                                   int KH, int KW, int stride, int pad, int act, void* stream) {
+    AOTB_REQUIRE(in && wh && wl && out, "aotb_conv2d_nhwc_tc: null pointer");
+    AOTB_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "aotb_conv2d_nhwc_tc: Cin and Cout must be multiples of 64");
+    AOTB_REQUIRE(ldin % 4 == 0 && ldout % 4 == 0 && (!res || ldres % 4 == 0) && ((uintptr_t)in % 16 == 0) &&
+                     ((uintptr_t)out % 16 == 0) && (!res || (uintptr_t)res % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0),
+                 "aotb_conv2d_nhwc_tc: 16-byte alignment required");
+    tc::ConvTcArgs a;
+    a.in = in; a.bias = bias; a.res = res; a.out = out;
+    a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.ldin = ldin;
+    a.Ho = (H + 2 * pad - KH) / stride + 1;
+    a.Wo = (W + 2 * pad - KW) / stride + 1;
+    AOTB_REQUIRE(a.Ho > 0 && a.Wo > 0, "aotb_conv2d_nhwc_tc: empty output");
+    a.Cout = Cout; a.ldout = ldout; a.ldres = ldres; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad;
+    a.M = B * a.Ho * a.Wo;
+    const int K = KH * KW * Cin;
+    a.nchunks = K / 64;
+    a.act = act;
+    // tile width: widest BN that still gives >= ~1 wave of CTAs, else the narrowest
+    const int mt = cdiv(a.M, 128);
+    int BN = 64;
+    if (Cout % 256 == 0 && mt * (Cout / 256) >= 120) BN = 256;
+    else if (Cout % 128 == 0 && mt * (Cout / 128) >= 120) BN = 128;
+    CUtensorMap th, tl;
+    int rc;
+    if ((rc = tc::make_tmap_weights(&th, wh, K, Cout, BN)) != AOTB_OK) return rc;
+    if ((rc = tc::make_tmap_weights(&tl, wl, K, Cout, BN)) != AOTB_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (BN == 256) return tc::launch_conv_tc<256, 2>(th, tl, a, st);
+    if (BN == 128) return tc::launch_conv_tc<128, 3>(th, tl, a, st);
+    return tc::launch_conv_tc<64, 3>(th, tl, a, st);
+}

@@ -289,6 +289,8 @@ class AOTEngine(nn.Module):
         if self._tc:
             hz = lambda *s: torch.zeros(s, dtype=torch.float16, device=dev)
             ws.Qp = hz(P.H, ((N + 255) // 256) * 256, 64)
+            ws.saKp = hz(P.H, ((N + 127) // 128) * 128, 64)          # self-attention K / V of the current frame
+            ws.saVp = hz(P.H, ((N + 127) // 128) * 128, 64)
             self.bank_Kp = [hz(P.H, cap, 64) for _ in range(L)]     # split-fp16 copies read by TMA
             self.bank_Vp = [hz(P.H, cap, 64) for _ in range(L)]
             ws.part = {}
@@ -466,7 +468,10 @@ class AOTEngine(nn.Module):
             ops.layernorm(x, Lw.norm1[0], Lw.norm1[1], ws.ln, add=self.pos_emb, out2=ws.ln_pos, stream=st)
             ops.linear(ws.ln_pos, Lw.sa_qk_w, Lw.sa_qk_b, ws.qk, stream=st)
             ops.linear(ws.ln, Lw.sa_v_w, Lw.sa_v_b, ws.v, stream=st)
-            ops.attention(ws.qk[:, :C], ws.qk[:, C:], ws.v, ws.core[:, :C], H, d, d, Tk=N, stream=st)
+            if self._tc:
+                self._tc_attention(ws.qk[:, :C], ws.qk[:, C:], ws.v, None, None, N, ws.core[:, :C], st)
+            else:
+                ops.attention(ws.qk[:, :C], ws.qk[:, C:], ws.v, ws.core[:, :C], H, d, d, Tk=N, stream=st)
             ops.linear(ws.core[:, :C], Lw.sa_proj_w, Lw.sa_proj_b, x, res=x, stream=st)
             # 2) long + short term (transformer.py:329-352)
             cQ, cV = self.curr_Q[li], self.curr_V[li]
@@ -502,28 +507,43 @@ class AOTEngine(nn.Module):
         probe = LT_PROBE
         use_tc = self._tc and (K is self.bank_K[li])
         if use_tc:
-            ws = self._ws
-            N = Q.shape[0]
-            splits = lt_splits(N, P.H, Tk)
-            part = None
-            if splits > 1:
-                part = ws.part.get(splits)
-                if part is None:
-                    fz = lambda *s: torch.empty(s, dtype=torch.float32, device=Q.device)
-                    part = (fz(splits, N, P.C), fz(splits, P.H, N), fz(splits, P.H, N))
-                    ws.part[splits] = part
-            ops.tc_pack_rows(Q, ws.Qp, 0, div=math.sqrt(d), stream=st)      # Q / T (attention.py:82)
+            ops.tc_pack_rows(Q, self._ws.Qp, 0, div=math.sqrt(d), stream=st)      # Q / T (attention.py:82)
         if probe is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         if use_tc:
-            ops.lt_attention_tc(ws.Qp, self.bank_Kp[li], self.bank_Vp[li], N, Tk, O=out, splits=splits,
-                                exact=(LT_IMPL == "tc_exact"), part=part, stream=st)
+            self._tc_attention(None, None, None, self.bank_Kp[li], self.bank_Vp[li], Tk, out, st)
+        elif self._tc:
+            self._tc_attention(Q, K, V, None, None, Tk, out, st)     # reference frame: Tk = N, own K/V
         else:
             ops.attention(Q, K, V, out, P.H, d, d, Tk=Tk, stream=st)
         if probe is not None:
             e1.record()
             probe.append((e0, e1, 4.0 * Q.shape[0] * Tk * P.C))
+
+    def _tc_attention(self, Q, K, V, Kp, Vp, Tk, out, st):
+        """softmax(Q K^T / T) V on the tcgen05 kernel.  Q/K/V fp32 [rows, C] are packed into the split-fp16
+        operand buffers first unless already-packed banks (Kp, Vp) are given (then Q was packed by the caller)."""
+        P = self._plan()
+        ws = self._ws
+        d = P.C // P.H
+        N = self.enc_hw
+        if Q is not None:
+            ops.tc_pack_rows(Q, ws.Qp, 0, div=math.sqrt(d), stream=st)
+        if Kp is None:
+            ops.tc_pack_rows(K, ws.saKp, 0, stream=st)
+            ops.tc_pack_rows(V, ws.saVp, 0, stream=st)
+            Kp, Vp = ws.saKp, ws.saVp
+        splits = lt_splits(N, P.H, Tk)
+        part = None
+        if splits > 1:
+            part = ws.part.get(splits)
+            if part is None:
+                fz = lambda *s: torch.empty(s, dtype=torch.float32, device=out.device)
+                part = (fz(splits, N, P.C), fz(splits, P.H, N), fz(splits, P.H, N))
+                ws.part[splits] = part
+        ops.lt_attention_tc(ws.Qp, Kp, Vp, N, Tk, O=out, splits=splits, exact=(LT_IMPL == "tc_exact"), part=part,
+                            stream=st)
 
     # short-term memory slots (TEST_SHORT_TERM_MEM_SKIP ring, aot_engine.py:329-332)
     def _next_short_slot(self):

@@ -9,6 +9,8 @@ stride is 1; channel-sliced views are fine (the row stride is passed as ``ld``).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from ._lib import AotbError, check, lib
@@ -43,8 +45,41 @@ def _nhwc_ld(x):
     return ld
 
 
+# fp32 weight (by data_ptr) -> (wh, wl) split-fp16 [Cout, K] copies for the tensor-core conv (registered by plan.py)
+_TC_WEIGHTS = {}
+CONV_IMPL = os.environ.get("AOTB_CONV_IMPL", "tc")     # "tc" (tcgen05, fp16x2 split) | "simt" (fp32 CUDA cores)
+
+
+def register_tc_weights(w, wh, wl):
+    _TC_WEIGHTS[w.data_ptr()] = (wh, wl, w)     # keep w alive so the pointer key stays unique
+
+
+def split_fp16(w_kn):
+    """fp32 [K, N] -> (hi, lo) fp16 [N, K] with hi + lo ~= w to 2^-22."""
+    wt = w_kn.t().contiguous()
+    hi = wt.half()
+    lo = (wt - hi.float()).half()
+    return hi.contiguous(), lo.contiguous()
+
+
+def conv2d_tc(x, wh, wl, bias, out, res=None, KH=1, KW=1, stride=1, pad=0, act=ACT_NONE, stream=None):
+    """Tensor-core conv: x [B,H,W,Cin] fp32, wh/wl [Cout, KH*KW*Cin] fp16."""
+    _chk(x, bias, out, res)
+    B, H, W, Cin = x.shape
+    Cout = wh.shape[0]
+    check(lib().aotb_conv2d_nhwc_tc(_p(x), wh.data_ptr(), wl.data_ptr(), _p(bias), _p(res), _p(out), B, H, W, Cin,
+                                    _nhwc_ld(x), Cout, _nhwc_ld(out), _nhwc_ld(res) if res is not None else 0, KH, KW,
+                                    stride, pad, act, _st(stream)), "aotb_conv2d_nhwc_tc")
+    return out
+
+
 def conv2d(x, w, bias, out, res=None, KH=1, KW=1, stride=1, pad=0, dil=1, act=ACT_NONE, stream=None):
     """x [B,H,W,Cin], w [KH*KW*Cin, Cout], out [B,Ho,Wo,Cout] (+res like out)."""
+    if CONV_IMPL == "tc" and dil == 1:
+        t = _TC_WEIGHTS.get(w.data_ptr())
+        if t is not None:
+            return conv2d_tc(x, t[0], t[1], bias, out, res=res, KH=KH, KW=KW, stride=stride, pad=pad, act=act,
+                             stream=stream)
     _chk(x, w, bias, out, res)
     B, H, W, Cin = x.shape
     Cout = w.shape[1]
@@ -56,6 +91,16 @@ def conv2d(x, w, bias, out, res=None, KH=1, KW=1, stride=1, pad=0, dil=1, act=AC
 
 def linear(x, wt, bias, out, res=None, act=ACT_NONE, stream=None):
     """x [M,K], wt [K,N], out [M,N] (+res [M,N]); res may alias out (in-place accumulate)."""
+    if CONV_IMPL == "tc":
+        t = _TC_WEIGHTS.get(wt.data_ptr())
+        if t is not None:
+            _chk(x, bias, out, res)
+            M, K = x.shape
+            N = wt.shape[1]
+            check(lib().aotb_conv2d_nhwc_tc(_p(x), t[0].data_ptr(), t[1].data_ptr(), _p(bias), _p(res), _p(out), 1, M, 1,
+                                            K, x.stride(0), N, out.stride(0), res.stride(0) if res is not None else 0,
+                                            1, 1, 1, 0, act, _st(stream)), "aotb_conv2d_nhwc_tc")
+            return out
     _chk(x, wt, bias, out, res)
     M, K = x.shape
     N = wt.shape[1]

@@ -52,12 +52,33 @@ class Plan:
         self.H = cfg.MODEL_ATT_HEADS
         self.align_corners = bool(cfg.MODEL_ALIGN_CORNERS)
         self.nid = cfg.MODEL_MAX_OBJ_NUM + 1
+        self._tc_keys = []
         self._encoder(cfg.MODEL_ENCODER)
         w = sd["encoder_projector.weight"]
-        self.proj = NS(w=self._conv_w(w), b=self._f(sd["encoder_projector.bias"]))
+        self.proj = NS(w=self._reg(self._conv_w(w), w.shape[1]), b=self._f(sd["encoder_projector.bias"]))
         self.layers = [self._gpm_layer(i) if self.deaot else self._lstt_layer(i) for i in range(self.L)]
         self._decoder()
         self._idbank()
+
+    def _reg(self, w, cin=None):
+        """Register split-fp16 [Cout, K] copies of a GEMM-shaped fp32 weight [K, Cout] for the tensor-core conv
+        (eligible when the per-tap channel count and Cout are multiples of 64); ops.conv2d / ops.linear pick them up."""
+        from . import ops
+        K, N = w.shape
+        cin = K if cin is None else cin
+        if cin % 64 == 0 and N % 64 == 0:
+            wh, wl = ops.split_fp16(w)
+            ops.register_tc_weights(w, wh, wl)
+            self._tc_keys.append(w.data_ptr())
+        return w
+
+    def __del__(self):
+        try:
+            from . import ops
+            for k in self._tc_keys:
+                ops._TC_WEIGHTS.pop(k, None)
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ helpers
     def _f(self, t):
@@ -90,11 +111,11 @@ class Plan:
         scale, shift = self._bn(bn)
         w = self.sd[conv + ".weight"]
         ns = NS(b=self._f(shift.float()), k=w.shape[2], cin=w.shape[1], cout=w.shape[0])
-        ns.w = self._dw_w(w, scale) if depthwise else self._conv_w(w, scale)
+        ns.w = self._dw_w(w, scale) if depthwise else self._reg(self._conv_w(w, scale), w.shape[1])
         return ns
 
     def _lin(self, name):
-        return self._f(self.sd[name + ".weight"].t()), self._f(self.sd[name + ".bias"])
+        return self._reg(self._f(self.sd[name + ".weight"].t())), self._f(self.sd[name + ".bias"])
 
     def _norm(self, name):
         return self._f(self.sd[name + ".weight"]), self._f(self.sd[name + ".bias"])
@@ -141,7 +162,7 @@ class Plan:
         n.norm1 = self._norm(p + "norm1")
         wq, bq = self._lin(p + "self_attn.linear_Q")
         wk, bk = self._lin(p + "self_attn.linear_K")
-        n.sa_qk_w = torch.cat([wq, wk], dim=1).contiguous()
+        n.sa_qk_w = self._reg(torch.cat([wq, wk], dim=1).contiguous())
         n.sa_qk_b = torch.cat([bq, bk]).contiguous()
         n.sa_v_w, n.sa_v_b = self._lin(p + "self_attn.linear_V")
         n.sa_proj_w, n.sa_proj_b = self._lin(p + "self_attn.projection")
@@ -150,7 +171,7 @@ class Plan:
         n.linV_w, n.linV_b = self._lin(p + "linear_V")
         wl, bl = self._lin(p + "long_term_attn.projection")
         ws, bs = self._lin(p + "short_term_attn.projection")
-        n.lst_proj_w = torch.cat([wl, ws], dim=0).contiguous()       # [2C, C]: x += [lt|st] @ W
+        n.lst_proj_w = self._reg(torch.cat([wl, ws], dim=0).contiguous())   # [2C, C]: x += [lt|st] @ W
         n.lst_proj_b = (bl.double() + bs.double()).float().contiguous()
         rk = sd[p + "short_term_attn.relative_emb_k.weight"]
         n.relk_w = self._f(rk.reshape(rk.shape[0], rk.shape[1]))       # [H*225, d]
@@ -179,7 +200,7 @@ class Plan:
             n.idu_w, n.idu_b = self._lin(p + "linear_ID_U")
         wl, bl = self._lin(p + "long_term_attn.projection")   # [4C, 2C]
         ws, bs = self._lin(p + "short_term_attn.projection")
-        n.lst_proj_w = torch.cat([wl, ws], dim=0).contiguous()  # [8C, 2C]
+        n.lst_proj_w = self._reg(torch.cat([wl, ws], dim=0).contiguous())  # [8C, 2C]
         n.lst_proj_b = (bl.double() + bs.double()).float().contiguous()
         n.lt_dw = self._dw_w(sd[p + "long_term_attn.dw_conv.conv.weight"])
         n.st_dw = self._dw_w(sd[p + "short_term_attn.dw_conv.conv.weight"])
@@ -205,13 +226,15 @@ class Plan:
         d = NS()
 
         def cg(name):
-            return NS(w=self._conv_w(sd[p + name + ".conv.weight"]), b=self._f(sd[p + name + ".conv.bias"]),
-                      gn=self._norm(p + name + ".gn"), cout=sd[p + name + ".conv.weight"].shape[0])
+            cw = sd[p + name + ".conv.weight"]
+            return NS(w=self._reg(self._conv_w(cw), cw.shape[1]), b=self._f(sd[p + name + ".conv.bias"]),
+                      gn=self._norm(p + name + ".gn"), cout=cw.shape[0])
 
         d.conv_in, d.conv_16x, d.conv_8x, d.conv_4x = cg("conv_in"), cg("conv_16x"), cg("conv_8x"), cg("conv_4x")
         for a in ("adapter_16x", "adapter_8x", "adapter_4x", "conv_out"):
-            setattr(d, a, NS(w=self._conv_w(sd[p + a + ".weight"]), b=self._f(sd[p + a + ".bias"]),
-                             cout=sd[p + a + ".weight"].shape[0]))
+            cw = sd[p + a + ".weight"]
+            setattr(d, a, NS(w=self._reg(self._conv_w(cw), cw.shape[1]), b=self._f(sd[p + a + ".bias"]),
+                             cout=cw.shape[0]))
         self.dec = d
         if self.deaot:
             self.final_gn = self._norm("LSTT.decoder_norms.0.gn")

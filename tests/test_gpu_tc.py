@@ -103,3 +103,73 @@ def test_lt_attention_tc_matches_simt_and_splits():
     ref = torch.empty(200, 256, device=d)
     ops.attention(Q[:200], K[:300], V[:300], ref, H, D, D)
     assert (O4 - ref).abs().max().item() < 1e-4
+
+
+def _pack_w(w):  # [Cout,Cin,KH,KW] -> fp32 [K, Cout] (k = (ky,kx,ci))
+    co, ci, kh, kw = w.shape
+    return w.permute(2, 3, 1, 0).reshape(kh * kw * ci, co).contiguous()
+
+
+@pytest.mark.parametrize("cfg", [
+    # B, H, W, Cin, Cout, K, stride, pad, res, act
+    (1, 37, 53, 64, 64, 1, 1, 0, False, 1),
+    (1, 121, 213, 64, 256, 1, 1, 0, True, 1),      # layer1 conv3 + residual, BN=256/128 path
+    (1, 31, 54, 256, 256, 3, 1, 1, False, 1),      # layer3 3x3
+    (1, 61, 107, 128, 128, 3, 2, 1, False, 1),     # strided 3x3
+    (1, 61, 107, 256, 512, 1, 2, 0, False, 0),     # strided 1x1 downsample
+    (1, 31, 54, 1024, 256, 1, 1, 0, False, 0),     # projector, K = 1024
+    (2, 20, 24, 128, 192, 3, 1, 1, True, 0),       # batch 2, Cout = 192 (BN = 64 only)
+    (1, 1674, 1, 512, 256, 1, 1, 0, True, 0),      # linear with in-place style residual
+])
+def test_conv2d_tc(cfg):
+    from aot_benchmark_b200 import ops
+    import torch.nn.functional as F
+    B, Hh, Ww, Cin, Cout, K, s, p, use_res, act = cfg
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, Cin, Hh, Ww, generator=g) * 2
+    w = torch.randn(Cout, Cin, K, K, generator=g) / math.sqrt(Cin * K * K)
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), s, p)
+    res = torch.randn(ref.shape, generator=g) if use_res else None
+    if use_res:
+        ref = ref + res.double()
+    if act == 1:
+        ref = F.relu(ref)
+    wk = _pack_w(w).to(d)
+    wh, wl = ops.split_fp16(wk)
+    xg = x.permute(0, 2, 3, 1).contiguous().to(d)
+    out = torch.full((B, ref.shape[2], ref.shape[3], Cout), float("nan"), device=d)
+    rg = res.permute(0, 2, 3, 1).contiguous().to(d) if use_res else None
+    ops.conv2d_tc(xg, wh, wl, b.to(d), out, res=rg, KH=K, KW=K, stride=s, pad=p, act=act)
+    torch.cuda.synchronize()
+    err = (out.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err < 2e-6 * max(scale, 1.0) + 2e-6, f"err {err} scale {scale}"
+    # and the fp32 CUDA-core kernel on the same problem agrees
+    out2 = torch.empty_like(out)
+    old = ops.CONV_IMPL
+    ops.CONV_IMPL = "simt"
+    try:
+        ops.conv2d(xg, wk, b.to(d), out2, res=rg, KH=K, KW=K, stride=s, pad=p, act=act)
+    finally:
+        ops.CONV_IMPL = old
+    assert (out - out2).abs().max().item() < 1e-5 * max(scale, 1.0)
+
+
+def test_linear_tc_channel_slices_inplace():
+    from aot_benchmark_b200 import ops
+    import torch.nn.functional as F
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(2)
+    big = torch.randn(300, 1024, generator=g)
+    w = torch.randn(256, 512, generator=g) / 22          # nn.Linear weight [out, in]
+    b = torch.randn(256, generator=g)
+    y = torch.randn(300, 512, generator=g)
+    ref = y[:, 256:].double() + F.linear(big[:, 512:].double(), w.double(), b.double())
+    wk = w.t().contiguous().to(d)
+    ops.register_tc_weights(wk, *ops.split_fp16(wk))
+    yg, bg = y.to(d), big.to(d)
+    ops.linear(bg[:, 512:], wk, b.to(d), yg[:, 256:], res=yg[:, 256:])
+    assert (yg[:, 256:].cpu().double() - ref).abs().max().item() < 1e-5
+    assert torch.equal(yg[:, :256].cpu(), y[:, :256])
