@@ -8,14 +8,14 @@
 // Cin % 64 == 0, Cout % 64 == 0, dilation 1 (everything on the R50-AOTL path except the 3-channel stem and
 // the 11-channel conv_out, which stay on conv_igemm.cu).
 //
-// One CTA = 128 output pixels x BN output channels, 192 threads:
-//   warps 0-3  A producers: gather the fp32 activation rows of a 64-wide K chunk straight from NHWC global
+// One CTA = 128 output pixels x BN output channels, 320 threads:
+//   warps 0-7  A producers (two chunks of loads in flight per thread): gather the fp32 activation rows of a 64-wide K chunk straight from NHWC global
 //              memory (im2col is never materialised; padding / stride handled per row), split every value into
 //              hi = fp16(x), lo = fp16(x - hi) and store both 128x64 tiles in the 128B-swizzled K-major layout
 //              the UMMA descriptor expects; afterwards the same warps run the epilogue
 //              (tcgen05.ld -> bias / residual / activation -> fp32 NHWC stores).
-//   warp 4     TMA producer for the pre-split weights (Wh, Wl as [Cout][K] fp16, K-major), 3-stage ring.
-//   warp 5     tcgen05.mma issuer: per 64-wide chunk 4 k-steps x (Ah*Wh + Al*Wh + Ah*Wl) into a 128 x BN fp32
+//   warp 8     TMA producer for the pre-split weights (Wh, Wl as [Cout][K] fp16, K-major), 3-stage ring.
+//   warp 9     tcgen05.mma issuer: per 64-wide chunk 4 k-steps x (Ah*Wh + Al*Wh + Ah*Wl) into a 128 x BN fp32
 //              accumulator in TMEM.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -53,7 +53,7 @@ struct ConvSmem {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const ConvTcArgs a) {
     using SM = ConvSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
@@ -69,7 +69,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&b_full[s], 1); mbar_init(&s_free[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 256); mbar_init(&b_full[s], 1); mbar_init(&s_free[s], 1); }
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
@@ -89,36 +89,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
         }
         rinfo[tid] = ri;
     }
-    if (warp == 5) tmem_alloc<BN>(tmem_slot);
+    if (warp == 9) tmem_alloc<BN>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const int cpt = a.Cin >> 6;  // 64-wide chunks per filter tap
 
-    if (warp < 4) {
-        // ======================= A producers =======================
-        const int q = tid & 15, rsub = tid >> 4;
-        for (int kc = 0; kc < a.nchunks; ++kc) {
-            const int s = kc % STAGES;
+    if (warp < 8) {
+        // ======================= A producers (8 warps, register double-buffered) =======================
+        const int q = tid & 15, rsub = tid >> 4;      // rsub 0..15
+        auto load_chunk = [&](int kc, float4* v) {
             const int tap = kc / cpt, c0 = (kc - tap * cpt) << 6;
             const int ky = tap / a.KW, kx = tap - ky * a.KW;
-            float4 v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const RowInfo ri = rinfo[i * 8 + rsub];
+            for (int i = 0; i < 8; ++i) {
+                const RowInfo ri = rinfo[i * 16 + rsub];
                 const int iy = ri.iy0 + ky, ix = ri.ix0 + kx;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ri.valid && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
                     v[i] = __ldg(reinterpret_cast<const float4*>(
                         a.in + (size_t)(ri.pix_base + iy * a.W + ix) * a.ldin + c0 + q * 4));
             }
+        };
+        auto store_chunk = [&](int kc, const float4* v) {
+            const int s = kc % STAGES;
             if (kc >= STAGES) mbar_wait(&s_free[s], ((kc / STAGES) - 1) & 1);
             uint8_t* Ah = smem + s * SM::STAGE_BYTES;
             uint8_t* Al = Ah + SM::A_BYTES;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int row = i * 8 + rsub;
+            for (int i = 0; i < 8; ++i) {
+                const int row = i * 16 + rsub;
                 const uint32_t off = row * 128 + (((q >> 1) ^ (row & 7)) << 4) + ((q & 1) << 3);
                 const __half2 h0 = __floats2half2_rn(v[i].x, v[i].y), h1 = __floats2half2_rn(v[i].z, v[i].w);
                 const __half2 l0 = __floats2half2_rn(v[i].x - __low2float(h0), v[i].y - __high2float(h0));
@@ -131,14 +132,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
             }
             fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&a_full[s]);
+        };
+        float4 va[8], vb[8];
+        load_chunk(0, va);
+        for (int kc = 0; kc < a.nchunks; kc += 2) {
+            if (kc + 1 < a.nchunks) load_chunk(kc + 1, vb);     // next chunk's loads in flight while this one is stored
+            store_chunk(kc, va);
+            if (kc + 2 < a.nchunks) load_chunk(kc + 2, va);
+            if (kc + 1 < a.nchunks) store_chunk(kc + 1, vb);
         }
-        // ======================= epilogue =======================
+        // ======================= epilogue (warps 0-3: columns [0, BN/2), warps 4-7: [BN/2, BN)) =======================
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        const int m = m0 + warp * 32 + lane;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const int wq = warp & 3;
+        const int m = m0 + wq * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
+        const int cbeg = (warp >> 2) * (BN / 2);
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = cbeg; c < cbeg + BN / 2; c += 32) {
             uint32_t r[32];
             tmem_ld32(trow + c, r);
             tmem_wait_ld();
@@ -164,7 +175,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ======================= weight TMA producer =======================
         if (elect_one()) {
             tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
@@ -204,7 +215,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc<BN>(tmem);
+    if (warp == 9) tmem_dealloc<BN>(tmem);
 }
 
 static int make_tmap_weights(CUtensorMap* out, const void* base, int Kpad, int Cout, int BN) {
@@ -246,7 +257,7 @@ static int launch_conv_tc(const CUtensorMap& th, const CUtensorMap& tl, const Co
         configured = true;
     }
     dim3 grid(cdiv(a.M, 128), a.Cout / BN);
-    conv_tc_kernel<BN, STAGES><<<grid, 192, smem, st>>>(th, tl, a);
+    conv_tc_kernel<BN, STAGES><<<grid, 320, smem, st>>>(th, tl, a);
     return check_launch("aotb_conv2d_nhwc_tc");
 }
 

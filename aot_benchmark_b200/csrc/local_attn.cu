@@ -180,6 +180,150 @@ static int launch_local(const LocalArgs& a, cudaStream_t st) {
     return check_launch("aotb_local_attention_f32");
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Tiled variant for the AOT head shape (d = dv = 32): one CTA = one head x an 8x8 tile of query pixels.
+// The (8+14)^2 K halo is staged once in shared memory with coalesced 128-byte row loads (the per-warp kernel
+// above issues one scattered 16-byte load per lane and tap), scores are computed with taps on lanes, the
+// softmax probabilities of the tile's 64 queries are parked in shared memory, then the same halo buffer is
+// refilled with V and the aggregate runs with channels on lanes.
+// relv_t is relative_emb_v transposed to [H][225][32] so the per-tap row is one coalesced 128-byte read.
+template <int TY, int TX>
+__global__ void __launch_bounds__(256, 1) local_attn_tile_kernel(const LocalArgs p, const float* __restrict__ relv_t) {
+    constexpr int D = 32, HH = TY + 2 * LR, HWD = TX + 2 * LR, NPOS = HH * HWD, LD = 33;
+    constexpr int QPW = TY * TX / 8;
+    extern __shared__ __align__(16) float smem[];
+    float* halo = smem;                 // [NPOS][LD]
+    float* wk = halo + NPOS * LD;       // [225][LD]
+    float* bk = wk + LTAPS * LD;        // [225]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_x = (p.w + TX - 1) / TX;
+    const int ty0 = (blockIdx.x / tiles_x) * TY, tx0 = (blockIdx.x % tiles_x) * TX;
+    const int g = blockIdx.y;
+
+    for (int f = tid; f < LTAPS * 8; f += 256) {
+        const int r = f >> 3, c4 = (f & 7) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.relk_w + ((size_t)g * LTAPS + r) * D + c4));
+        float* d = wk + r * LD + c4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    for (int t = tid; t < LTAPS; t += 256) bk[t] = __ldg(p.relk_b + g * LTAPS + t);
+
+    auto load_halo = [&](const float* src, int ld) {
+        for (int f = tid; f < NPOS * 8; f += 256) {
+            const int pos = f >> 3, c4 = (f & 7) * 4;
+            const int hy = pos / HWD, hx = pos - hy * HWD;
+            const int yy = ty0 - LR + hy, xx = tx0 - LR + hx;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w)
+                v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(yy * p.w + xx) * ld + g * D + c4));
+            float* d = halo + pos * LD + c4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    };
+    load_halo(p.k, p.ldk);
+    __syncthreads();
+
+    // ---- phase 1: scores + softmax, taps on lanes; probabilities of all TY*TX queries parked in shared memory
+    float* prob = bk + LTAPS + 7;       // [TY*TX][PLD]
+    constexpr int PLD = 228;
+    const float invT = 1.f / p.T;
+#pragma unroll 1
+    for (int qi = 0; qi < QPW; ++qi) {
+        const int ql = warp * QPW + qi;
+        const int ly = ql / TX, lx = ql - ly * TX;
+        const int y = ty0 + ly, x = tx0 + lx;
+        if (y >= p.h || x >= p.w) continue;      // warp-uniform
+        float qv[D];
+        const float4* qp = reinterpret_cast<const float4*>(p.q + (size_t)(y * p.w + x) * p.ldq + g * D);
+#pragma unroll
+        for (int c = 0; c < D / 4; ++c) {
+            const float4 t = __ldg(qp + c);
+            qv[4 * c] = t.x; qv[4 * c + 1] = t.y; qv[4 * c + 2] = t.z; qv[4 * c + 3] = t.w;
+        }
+        float sc[8];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int wi = lane + 32 * j;
+            float s1 = -INFINITY;
+            if (wi < LTAPS) {
+                const int dy = wi / LW, dx = wi - dy * LW;       // 0..14
+                const int yy = y + dy - LR, xx = x + dx - LR;
+                const bool inside = (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w);
+                const float* kr = halo + ((ly + dy) * HWD + lx + dx) * LD;
+                const float* wr = wk + wi * LD;
+                float dot = 0.f, rel = bk[wi];
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    dot = fmaf(qv[c], kr[c], dot);
+                    rel = fmaf(wr[c], qv[c], rel);
+                }
+                s1 = inside ? fmaf(dot, invT, rel) : (rel - 1e8f);
+            }
+            sc[j] = s1;
+            mx = fmaxf(mx, s1);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = (lane + 32 * j < LTAPS) ? expf(sc[j] - mx) : 0.f;
+            sum += sc[j];
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (lane + 32 * j < LTAPS) prob[ql * PLD + lane + 32 * j] = sc[j] * inv;
+    }
+    __syncthreads();          // every warp is done with the K halo
+    load_halo(p.v, p.ldv);
+    __syncthreads();
+
+    // ---- phase 2: aggregate, channels on lanes
+    const float* rv = relv_t + (size_t)g * LTAPS * D + lane;
+#pragma unroll 1
+    for (int qi = 0; qi < QPW; ++qi) {
+        const int ql = warp * QPW + qi;
+        const int ly = ql / TX, lx = ql - ly * TX;
+        const int y = ty0 + ly, x = tx0 + lx;
+        if (y >= p.h || x >= p.w) continue;     // warp-uniform
+        const float* pq = prob + ql * PLD;
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int dy = 0; dy < LW; ++dy) {
+            const float* vrow = halo + ((ly + dy) * HWD + lx) * LD + lane;   // zero outside the frame
+#pragma unroll
+            for (int dx = 0; dx < LW; ++dx) {
+                const int wi = dy * LW + dx;
+                const float pv = pq[wi];
+                const float vv = vrow[dx * LD] + __ldg(rv + wi * D);
+                if (dx & 1) acc1 = fmaf(pv, vv, acc1); else acc0 = fmaf(pv, vv, acc0);
+            }
+        }
+        p.out[(size_t)(y * p.w + x) * p.ldo + g * D + lane] = acc0 + acc1;
+    }
+}
+
+static int launch_local_tile(const LocalArgs& a, const float* relv_t, cudaStream_t st) {
+    constexpr int TY = 8, TX = 8;
+    const size_t smem = sizeof(float) * (size_t)((TY + 14) * (TX + 14) * 33 + LTAPS * 33 + LTAPS + 8 + TY * TX * 228);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(local_attn_tile_kernel<TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) {
+            set_error("aotb_local_attention_tile_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return AOTB_ERR_CUDA;
+        }
+        configured = true;
+    }
+    dim3 grid(cdiv(a.h, TY) * cdiv(a.w, TX), a.H);
+    local_attn_tile_kernel<TY, TX><<<grid, 256, smem, st>>>(a, relv_t);
+    return check_launch("aotb_local_attention_tile_f32");
+}
+
 }  // namespace aotb
 
 using namespace aotb;
@@ -199,4 +343,18 @@ extern "C" int aotb_local_attention_f32(const float* q, int ldq, const float* k,
     if (d_att == 128 && d_v == 1024 && !relv) return launch_local<128, 1024, false, false>(a, st);
     set_error("aotb_local_attention_f32: unsupported head shape d_att=%d d_v=%d relv=%d", d_att, d_v, relv != nullptr);
     return AOTB_ERR_UNSUPPORTED;
+}
+
+// Tiled kernel for the AOT head shape (d_att = d_v = 32).  relv_t = relative_emb_v transposed to [H][225][32].
+extern "C" int aotb_local_attention_tile_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                                             const float* relk_w, const float* relk_b, const float* relv_t, float* out,
+                                             int ldo, int h, int w, int H, void* stream) {
+    AOTB_REQUIRE(q && k && v && relk_w && relk_b && relv_t && out && h > 0 && w > 0 && H > 0,
+                 "aotb_local_attention_tile_f32: bad args");
+    AOTB_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "aotb_local_attention_tile_f32: ld %% 4");
+    LocalArgs a;
+    a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv;
+    a.relk_w = relk_w; a.relk_b = relk_b; a.relv = nullptr; a.out = out; a.ldo = ldo;
+    a.h = h; a.w = w; a.H = H; a.T = sqrtf(32.f);
+    return launch_local_tile(a, relv_t, (cudaStream_t)stream);
 }

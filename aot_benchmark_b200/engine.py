@@ -35,10 +35,51 @@ LT_PROBE = None
 #   "simt"     fp32 CUDA-core flash kernel                          (attention_simt.cu)
 import os as _os
 LT_IMPL = _os.environ.get("AOTB_LT_IMPL", "tc_exact")
+LOCAL_IMPL = _os.environ.get("AOTB_LOCAL_IMPL", "tile")      # "tile" (halo in smem) | "warp" (generic kernel)
 _LT_NAMES = {"simt": "attn_f32_kernel<32,32> (fp32 SIMT flash attention)",
              "tc_exact": "lt_attn_tc_kernel (tcgen05 fp16x2 exact: 6+16 MMAs/tile)",
              "tc_fast": "lt_attn_tc_kernel (tcgen05 fp16 fast: 2+8 MMAs/tile)"}
 LT_KERNEL_NAME = _LT_NAMES.get(LT_IMPL, LT_IMPL)
+
+
+# Whole-call CUDA graphs (encoder / LSTT / decoder / memory update are each captured once per video geometry and
+# replayed; the live key count and the bank append offset are read from a device counter inside the kernels).
+USE_GRAPHS = _os.environ.get("AOTB_GRAPHS", "1") == "1"
+BANK_INIT_FRAMES = int(_os.environ.get("AOTB_BANK_FRAMES", "24"))   # initial long-term bank capacity (memory frames)
+
+
+class GraphCache:
+    """key -> [eager_runs, CUDAGraph | None, result]; first call runs eagerly (warm-up: lazy module loads,
+    cudaFuncSetAttribute, buffer allocation), second call is captured, later calls replay."""
+
+    def __init__(self):
+        self.slots = {}
+
+    def clear(self):
+        self.slots.clear()
+
+    def run(self, key, fn, enabled=True):
+        if not (enabled and USE_GRAPHS and LT_PROBE is None):
+            return fn()
+        slot = self.slots.get(key)
+        if slot is None:
+            slot = self.slots[key] = [0, None, None]
+        if slot[1] is not None:
+            slot[1].replay()
+            return slot[2]
+        if slot[0] < 1:
+            slot[0] += 1
+            return fn()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = fn()
+        g.replay()                     # capture records only; replay produces this call's results
+        slot[1], slot[2] = g, out
+        return out
+
+
+def _cur_stream():
+    return torch.cuda.current_stream().cuda_stream
 
 
 def lt_splits(n_queries, heads, tk, sms=148):
@@ -106,8 +147,19 @@ class _Encoder:
         if img.dim() != 4 or img.shape[0] != 1 or img.shape[1] != 3:
             raise ValueError("expected an image tensor [1,3,H,W]")
         H, W = img.shape[2], img.shape[3]
+        if getattr(self, "_gkey", None) != (id(P), H, W):
+            self.graphs = GraphCache()
+            self._gkey = (id(P), H, W)
         x = self._buf("in", (1, H, W, 3))
-        ops.nchw_to_nhwc(img.float(), x, stream=st)
+        ops.nchw_to_nhwc(img.float(), x, stream=st)          # caller's tensor -> static NHWC input (eager)
+        nhwc = self.graphs.run("enc", lambda: self._body(x))
+        out = EncEmbs(t.permute(0, 3, 1, 2) for t in nhwc)
+        out.nhwc = nhwc
+        return out
+
+    def _body(self, x):
+        P = self.plan
+        st = _cur_stream()
         if P.encoder_name == "resnet50":
             feats = self._resnet(x, st)
         else:
@@ -115,10 +167,7 @@ class _Encoder:
         f16 = feats[-1]
         proj = self._buf("proj", (1, f16.shape[1], f16.shape[2], P.C))
         ops.conv2d(f16, P.proj.w, P.proj.b, proj, stream=st)
-        nhwc = [feats[0], feats[1], feats[2], proj]
-        out = EncEmbs(t.permute(0, 3, 1, 2) for t in nhwc)
-        out.nhwc = nhwc
-        return out
+        return [feats[0], feats[1], feats[2], proj]
 
     def _resnet(self, x, st):
         e = self.plan.enc
@@ -192,7 +241,10 @@ class AOTEngine(nn.Module):
         self.losses = None
         self._enc = None
         self._ws = None
+        self._ws_key = None
         self._P = None
+        self.graphs = GraphCache()
+        self.tk_dev = None
         self.restart_engine()
 
     # ------------------------------------------------------------------ protocol
@@ -219,6 +271,8 @@ class AOTEngine(nn.Module):
         self.curr_id_embs = None
         self.pred_id_logits = None
         self._have_lstt = False
+        if self.tk_dev is not None:
+            self.tk_dev.zero_()
 
     def update_size(self, input_size, enc_size):
         self.input_size_2d = tuple(int(s) for s in input_size)
@@ -238,6 +292,16 @@ class AOTEngine(nn.Module):
         N = self.enc_hw
         C = P.C
         L = P.L
+        key = (id(P), N, tuple(self.enc_size_2d), tuple(self.input_size_2d), LT_IMPL)
+        if self._ws is not None and self._ws_key == key:
+            # same geometry and weights as the previous video: keep buffers and captured graphs
+            self.bank_len = 0
+            self.tk_dev.zero_()
+            self._st_ring = []
+            return
+        self._ws_key = key
+        self.graphs.clear()
+        self.tk_dev = torch.zeros(1, dtype=torch.int32, device=dev)    # live rows of the long-term bank
         f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
         ws = type("WS", (), {})()
         ws.N = N
@@ -280,7 +344,9 @@ class AOTEngine(nn.Module):
             self.st_K = [f(N, d) for _ in range(L)]
             self.st_V = [f(N, 4 * C) for _ in range(L)]   # cat[V | ID_V] (transformer.py:625-626)
             self._kdim, self._vdim = d, 4 * C
-        cap = 4 * N
+        ws.mask = f(*self.input_size_2d)                            # static copy of the caller's label map
+        self._dec_out = {}
+        cap = BANK_INIT_FRAMES * N
         self.bank_cap = cap
         self.bank_K = [f(cap, self._kdim) for _ in range(L)]
         self.bank_V = [f(cap, self._vdim) for _ in range(L)]
@@ -314,6 +380,7 @@ class AOTEngine(nn.Module):
                     nb[:, : self.bank_len].copy_(old[:, : self.bank_len])
                     lst[i] = nb
         self.bank_cap = new_cap
+        self.graphs.clear()            # captured launches point at the old bank
 
     # ------------------------------------------------------------------ reference-shaped views
     @property
@@ -374,9 +441,16 @@ class AOTEngine(nn.Module):
                 ops.layernorm(ws.id_emb, P.id_norm[0], P.id_norm[1], ws.id_emb, stream=st)
             return ws.id_emb
         m2 = mask.reshape(mask.shape[-2], mask.shape[-1]).float().contiguous()
-        ops.id_embed(m2, P.id_wt, P.id_b, ws.id_emb, P.C, P.nid, P.id_k, P.id_stride, P.id_pad,
-                     ln_gamma=P.id_norm[0] if P.deaot else None, ln_beta=P.id_norm[1] if P.deaot else None, stream=st)
+        if tuple(m2.shape) == tuple(ws.mask.shape):
+            ops.eltwise(ops.EW_COPY, m2, None, ws.mask, stream=st)      # static buffer: graph replays read it
+            m2 = ws.mask
+        self._id_from_static_mask(m2, st)
         return ws.id_emb
+
+    def _id_from_static_mask(self, m2, st):
+        P = self._plan()
+        ops.id_embed(m2, P.id_wt, P.id_b, self._ws.id_emb, P.C, P.nid, P.id_k, P.id_stride, P.id_pad,
+                     ln_gamma=P.id_norm[0] if P.deaot else None, ln_beta=P.id_norm[1] if P.deaot else None, stream=st)
 
     def add_reference_frame(self, img=None, mask=None, frame_step=-1, obj_nums=None, img_embs=None):
         if self.obj_nums is None and obj_nums is None:
@@ -420,28 +494,57 @@ class AOTEngine(nn.Module):
             self._check_img(img)
             img_embs = self._encode(img, st)
         self.curr_enc_embs = img_embs
-        self._lstt_forward(img_embs, None, st)
+        splits = lt_splits(self.enc_hw, self._plan().H, max(self.bank_len, 1)) if getattr(self, "_tc", False) else 0
+        self.graphs.run(("lstt", splits, id(img_embs.nhwc[-1])),
+                        lambda: self._lstt_forward(img_embs, None, _cur_stream()),
+                        enabled=self.short_term_mem_skip <= 1)
 
     def update_short_term_memory(self, curr_mask, curr_id_emb=None, skip_long_term_update=False):
         st = torch.cuda.current_stream().cuda_stream
+        append = False
+        if self.frame_step - self.last_mem_step >= self.long_term_mem_gap:
+            append = not skip_long_term_update
+            self.last_mem_step = self.frame_step
+        if append:
+            self._bank_reserve(self.enc_hw)          # may re-allocate (and drop graphs) before anything is captured
+        ws = self._ws
+        label_map = curr_id_emb is None and not (curr_mask.dim() == 4 and curr_mask.shape[1] != 1) and \
+            tuple(curr_mask.shape[-2:]) == tuple(ws.mask.shape)
+        if label_map and self.short_term_mem_skip <= 1:
+            m2 = curr_mask.reshape(ws.mask.shape).float().contiguous()
+            ops.eltwise(ops.EW_COPY, m2, None, ws.mask, stream=st)
+
+            def body():
+                s2 = _cur_stream()
+                self._id_from_static_mask(ws.mask, s2)
+                self._fuse_memories(ws.id_emb, s2)
+                if append:
+                    self._append_short_to_bank(s2, count=False)
+            self.graphs.run(("upd", append), body)
+            if append:
+                self.bank_len += self.enc_hw
+            return
         id_emb = self.assign_identity_from_mask(curr_mask, st) if curr_id_emb is None else curr_id_emb
         self._fuse_memories(id_emb, st)
-        if self.frame_step - self.last_mem_step >= self.long_term_mem_gap:
-            if not skip_long_term_update:
-                self._append_short_to_bank(st)
-            self.last_mem_step = self.frame_step
+        if append:
+            self._append_short_to_bank(st)
 
-    def _append_short_to_bank(self, st):
+    def _append_short_to_bank(self, st, count=True):
+        """Append the newest fused K/V of every layer at the device-side row counter, then advance it."""
         N = self.enc_hw
-        self._bank_reserve(N)
+        if count:
+            self._bank_reserve(N)
         K_src, V_src = self._latest_kv()
+        off = self.tk_dev
         for li in range(self._plan().L):
-            ops.bank_append(K_src[li], self.bank_K[li], self.bank_len, stream=st)
-            ops.bank_append(V_src[li], self.bank_V[li], self.bank_len, stream=st)
+            ops.bank_append(K_src[li], self.bank_K[li], 0, offset_dev=off, stream=st)
+            ops.bank_append(V_src[li], self.bank_V[li], 0, offset_dev=off, stream=st)
             if self._tc:
-                ops.tc_pack_rows(K_src[li], self.bank_Kp[li], self.bank_len, stream=st)
-                ops.tc_pack_rows(V_src[li], self.bank_Vp[li], self.bank_len, stream=st)
-        self.bank_len += N
+                ops.tc_pack_rows(K_src[li], self.bank_Kp[li], 0, row_off_dev=off, stream=st)
+                ops.tc_pack_rows(V_src[li], self.bank_Vp[li], 0, row_off_dev=off, stream=st)
+        ops.counter_add(off, N, stream=st)
+        if count:
+            self.bank_len += N
 
     def _latest_kv(self):
         return self._new_K, self._new_V
@@ -485,8 +588,12 @@ class AOTEngine(nn.Module):
             else:
                 gK, gV, Tk = self.bank_K[li], self.bank_V[li], self.bank_len
             self._long_term_attention(li, cQ, gK, gV, Tk, ws.core[:, :C], st)
-            ops.local_attention(cQ, stK[li], stV[li], Lw.relk_w, Lw.relk_b, Lw.relv, ws.core[:, C:], h, w, H, d, d,
-                                stream=st)
+            if d == 32 and LOCAL_IMPL == "tile":
+                ops.local_attention_tile(cQ, stK[li], stV[li], Lw.relk_w, Lw.relk_b, Lw.relv_t, ws.core[:, C:], h, w, H,
+                                         stream=st)
+            else:
+                ops.local_attention(cQ, stK[li], stV[li], Lw.relk_w, Lw.relk_b, Lw.relv, ws.core[:, C:], h, w, H, d, d,
+                                    stream=st)
             ops.linear(ws.core, Lw.lst_proj_w, Lw.lst_proj_b, x, res=x, stream=st)
             # 3) feed-forward (transformer.py:354-359, basic.py:27-35)
             ops.layernorm(x, Lw.norm3[0], Lw.norm3[1], ws.ln, stream=st)
@@ -512,16 +619,17 @@ class AOTEngine(nn.Module):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         if use_tc:
-            self._tc_attention(None, None, None, self.bank_Kp[li], self.bank_Vp[li], Tk, out, st)
+            self._tc_attention(None, None, None, self.bank_Kp[li], self.bank_Vp[li], Tk, out, st, Tk_dev=self.tk_dev)
         elif self._tc:
             self._tc_attention(Q, K, V, None, None, Tk, out, st)     # reference frame: Tk = N, own K/V
         else:
-            ops.attention(Q, K, V, out, P.H, d, d, Tk=Tk, stream=st)
+            ops.attention(Q, K, V, out, P.H, d, d, Tk=Tk, Tk_dev=self.tk_dev if K is self.bank_K[li] else None,
+                          stream=st)
         if probe is not None:
             e1.record()
             probe.append((e0, e1, 4.0 * Q.shape[0] * Tk * P.C))
 
-    def _tc_attention(self, Q, K, V, Kp, Vp, Tk, out, st):
+    def _tc_attention(self, Q, K, V, Kp, Vp, Tk, out, st, Tk_dev=None):
         """softmax(Q K^T / T) V on the tcgen05 kernel.  Q/K/V fp32 [rows, C] are packed into the split-fp16
         operand buffers first unless already-packed banks (Kp, Vp) are given (then Q was packed by the caller)."""
         P = self._plan()
@@ -542,8 +650,8 @@ class AOTEngine(nn.Module):
                 fz = lambda *s: torch.empty(s, dtype=torch.float32, device=out.device)
                 part = (fz(splits, N, P.C), fz(splits, P.H, N), fz(splits, P.H, N))
                 ws.part[splits] = part
-        ops.lt_attention_tc(ws.Qp, Kp, Vp, N, Tk, O=out, splits=splits, exact=(LT_IMPL == "tc_exact"), part=part,
-                            stream=st)
+        ops.lt_attention_tc(ws.Qp, Kp, Vp, N, Tk, O=out, Tk_dev=Tk_dev, splits=splits, exact=(LT_IMPL == "tc_exact"),
+                            part=part, stream=st)
 
     # short-term memory slots (TEST_SHORT_TERM_MEM_SKIP ring, aot_engine.py:329-332)
     def _next_short_slot(self):
@@ -621,16 +729,25 @@ class AOTEngine(nn.Module):
         return lg
 
     def decode_current_logits(self, output_size=None):
-        st = torch.cuda.current_stream().cuda_stream
+        """aot_engine.py:356-380.  The returned tensor (and ``pred_id_logits``) are per-engine static buffers that
+        the next call overwrites -- clone them to keep a frame's logits."""
         P = self._plan()
-        lg = self._decode(st)
-        h4, w4, NC = lg.shape[1], lg.shape[2], lg.shape[3]
-        lo = torch.empty((1, NC, h4, w4), dtype=torch.float32, device=lg.device)
-        out = None
-        if output_size is not None:
-            oh, ow = int(output_size[0]), int(output_size[1])
-            out = torch.empty((1, NC, oh, ow), dtype=torch.float32, device=lg.device)
-        ops.logits_postproc(lg, lo, out, int(self.obj_nums[0]), P.align_corners, stream=st)
+        size = None if output_size is None else (int(output_size[0]), int(output_size[1]))
+        obj = int(self.obj_nums[0])
+
+        def body():
+            st = _cur_stream()
+            lg = self._decode(st)
+            h4, w4, NC = lg.shape[1], lg.shape[2], lg.shape[3]
+            bufs = self._dec_out.get(size)
+            if bufs is None:
+                lo = torch.empty((1, NC, h4, w4), dtype=torch.float32, device=lg.device)
+                out = None if size is None else torch.empty((1, NC) + size, dtype=torch.float32, device=lg.device)
+                bufs = self._dec_out[size] = (lo, out)
+            ops.logits_postproc(lg, bufs[0], bufs[1], obj, P.align_corners, stream=st)
+            return bufs
+
+        lo, out = self.graphs.run(("dec", size, obj, id(self.curr_enc_embs.nhwc[0])), body)
         self.pred_id_logits = lo
         return lo if out is None else out
 
@@ -701,7 +818,7 @@ class DeAOTEngine(AOTEngine):
                 gK, gV, Tk = stK[li], stV[li], N
             else:
                 gK, gV, Tk = self.bank_K[li], self.bank_V[li], self.bank_len
-            ops.attention(cQ, gK, gV, ws.core, 1, d, C4, Tk=Tk, stream=st)
+            ops.attention(cQ, gK, gV, ws.core, 1, d, C4, Tk=Tk, Tk_dev=None if is_ref else self.tk_dev, stream=st)
             self._gated_tail(ws.core, ws.catU, Lw.lt_dw, ws.dw[:, :C4], h, w, st)
             ops.local_attention(cQ, stK[li], stV[li], Lw.relk_w, Lw.relk_b, None, ws.core, h, w, 1, d, C4, stream=st)
             self._gated_tail(ws.core, ws.catU, Lw.st_dw, ws.dw[:, C4:], h, w, st)

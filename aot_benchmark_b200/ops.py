@@ -209,6 +209,15 @@ def local_attention(q, k, v, relk_w, relk_b, relv, out, h, w, H, d_att, d_v, str
     return out
 
 
+def local_attention_tile(q, k, v, relk_w, relk_b, relv_t, out, h, w, H, stream=None):
+    """AOT head shape (d = 32): halo-in-shared-memory kernel; relv_t [H, 225, 32]."""
+    _chk(q, k, v, relk_w, relk_b, relv_t, out)
+    check(lib().aotb_local_attention_tile_f32(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(relk_w),
+                                              _p(relk_b), _p(relv_t), _p(out), out.stride(0), h, w, H, _st(stream)),
+          "aotb_local_attention_tile_f32")
+    return out
+
+
 def id_embed(mask, wt, bias, out, C, nid, ksize, stride, pad, ln_gamma=None, ln_beta=None, stream=None):
     """mask [Hm, Wm] float ids -> out [ho*wo, C]."""
     _chk(mask, wt, bias, out, ln_gamma, ln_beta)

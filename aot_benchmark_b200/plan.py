@@ -177,6 +177,7 @@ class Plan:
         n.relk_w = self._f(rk.reshape(rk.shape[0], rk.shape[1]))       # [H*225, d]
         n.relk_b = self._f(sd[p + "short_term_attn.relative_emb_k.bias"])
         n.relv = self._f(sd[p + "short_term_attn.relative_emb_v"])     # [H, d, 225]
+        n.relv_t = n.relv.permute(0, 2, 1).contiguous()                # [H, 225, d] for the tiled kernel
         n.norm3 = self._norm(p + "norm3")
         n.lin1_w, n.lin1_b = self._lin(p + "linear1")
         n.gn = self._norm(p + "activation.gn")

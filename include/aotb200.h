@@ -94,6 +94,12 @@ int aotb_local_attention_f32(const float* q, int ldq, const float* k, int ldk, c
                              const float* relk_w, const float* relk_b, const float* relv, float* out, int ldo,
                              int h, int w, int H, int d_att, int d_v, void* stream);
 
+/* Same computation for the AOT head shape (d_att = d_v = 32) with the K / V window halos staged in shared
+ * memory per 8x8 query tile; relv_t is relative_emb_v transposed to [H][225][32]. */
+int aotb_local_attention_tile_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                                  const float* relk_w, const float* relk_b, const float* relv_t, float* out, int ldo,
+                                  int h, int w, int H, void* stream);
+
 /* one_hot_mask + patch_wise_id_bank conv as a gather-sum (+ LayerNorm for DeAOT):
  * utils/image.py:69-74; networks/models/aot.py:50-63,76-79; networks/models/deaot.py:51-55.
  * mask [Hm][Wm] float ids; wt [(ky*KS+kx)*nid + id][C]. */

@@ -1,24 +1,30 @@
 #!/bin/bash
 # One GPU trip: parity tests, smoke, bench, and the ncu launch list of the bench command.
-# Usage (from the repo root, under gpurun): bash scripts/gpu_check.sh [quick|tc]
+# Usage (from the repo root, under gpurun): bash scripts/gpu_check.sh [quick|tc|impls]
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 if [ "$1" == "tc" ]; then
   echo "== tensor-core kernel tests first"
-  timeout 300 python -m pytest tests/test_gpu_tc.py -m gpu -x -q -s 2>&1 | tail -40 | tee gpurun_out/pytest_tc.log
+  timeout 300 python -m pytest tests/test_gpu_tc.py -m gpu -q -s 2>&1 | tail -40 | tee gpurun_out/pytest_tc.log
 fi
 echo "== pytest -m gpu"
-timeout 1200 python -m pytest tests -m gpu -q -s 2>&1 | tail -60 | tee gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q -s > gpurun_out/pytest_gpu.log 2>&1; tail -25 gpurun_out/pytest_gpu.log; grep -a -E "dlogit|sharp" gpurun_out/pytest_gpu.log
 echo "== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
 if [ "$1" == "quick" ]; then
   timeout 600 python bench.py --steps 30 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench_short.log
   exit 0
 fi
-for impl in simt tc_exact tc_fast; do
-  echo "== bench full clip AOTB_LT_IMPL=$impl"
-  AOTB_LT_IMPL=$impl timeout 900 python bench.py 2>&1 | tail -2 | tee gpurun_out/bench_full_$impl.log
-done
-echo "== ncu launch list (tc_exact)"
-AOTB_LT_IMPL=tc_exact timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2500 -c 1200 --csv --log-file gpurun_out/launches_tc_exact.csv python bench.py --steps 12 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
-tail -2 gpurun_out/bench_under_ncu.log | cut -c1-300
+echo "== bench full clip (defaults)"
+timeout 900 python bench.py 2>&1 | tail -2 | tee gpurun_out/bench_full.log
+if [ "$1" == "impls" ]; then
+  for impl in simt tc_fast; do
+    echo "== bench full clip AOTB_LT_IMPL=$impl"
+    AOTB_LT_IMPL=$impl timeout 900 python bench.py 2>&1 | tail -2 | tee gpurun_out/bench_full_$impl.log
+  done
+  echo "== bench full clip AOTB_CONV_IMPL=simt"
+  AOTB_CONV_IMPL=simt timeout 900 python bench.py 2>&1 | tail -2 | tee gpurun_out/bench_full_convsimt.log
+fi
+echo "== ncu launch list"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2500 -c 1200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 12 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
+tail -2 gpurun_out/bench_under_ncu.log | cut -c1-200

@@ -332,3 +332,29 @@ def test_errors_are_loud():
     with pytest.raises(AotbError):
         ops.attention(torch.zeros(4, 40, device=d), torch.zeros(4, 40, device=d), torch.zeros(4, 40, device=d),
                       torch.zeros(4, 40, device=d), 1, 40, 40)  # unsupported head shape
+
+
+@pytest.mark.parametrize("h,w", [(13, 22), (31, 54), (8, 8), (5, 40)])
+def test_local_attention_tile_aot(h, w):
+    """Halo-in-shared-memory kernel vs the fp64 oracle and vs the generic per-warp kernel."""
+    from aot_benchmark_b200 import ops
+    from oracle import aot_oracle as O
+    d = _dev()
+    g = torch.Generator().manual_seed(13 + h)
+    H, dd = 8, 32
+    q = torch.randn(1, 256, h, w, generator=g) * 2
+    k = torch.randn(1, 256, h, w, generator=g)
+    v = torch.randn(1, 256, h, w, generator=g)
+    rkw = torch.randn(1800, 32, 1, 1, generator=g) * 0.2
+    rkb = torch.randn(1800, generator=g) * 0.1
+    rv = torch.randn(8, 32, 225, generator=g) * 0.3
+    ref = O.local_attention(q.double(), k.double(), v.double(), rkw.double(), rkb.double(), rv.double(), H)[:, 0]
+    tok = lambda t: t[0].permute(1, 2, 0).reshape(h * w, -1).contiguous().to(d)
+    out = torch.full((h * w, 512), float("nan"), device=d)
+    ops.local_attention_tile(tok(q), tok(k), tok(v), rkw.view(1800, 32).contiguous().to(d), rkb.to(d),
+                             rv.permute(0, 2, 1).contiguous().to(d), out[:, 256:], h, w, H)
+    assert (out[:, 256:].cpu().double() - ref).abs().max().item() < 2e-5
+    out2 = torch.empty(h * w, 256, device=d)
+    ops.local_attention(tok(q), tok(k), tok(v), rkw.view(1800, 32).contiguous().to(d), rkb.to(d), rv.to(d), out2,
+                        h, w, H, dd, dd)
+    assert (out[:, 256:] - out2).abs().max().item() < 1e-5
