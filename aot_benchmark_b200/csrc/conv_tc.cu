@@ -5,8 +5,8 @@
 //
 // Same reference sites as conv_igemm.cu (resnet.py:34-54,140-157 with FrozenBatchNorm2d folded,
 // aot.py:19-21,83, fpn.py:34-58, every nn.Linear of transformer.py:321-367,582-665).  Eligibility:
-// Cin % 64 == 0, Cout % 64 == 0, dilation 1 (everything on the R50-AOTL path except the 3-channel stem and
-// the 11-channel conv_out, which stay on conv_igemm.cu).
+// Cin % 4 == 0, Cout % 64 == 0, dilation 1 (everything on the R50-AOTL path except the 11-channel conv_out;
+// the 7x7 stem runs on a 4-channel zero-padded copy of the image).
 //
 // One CTA = 128 output pixels x BN output channels, 320 threads:
 //   warps 0-7  A producers (two chunks of loads in flight per thread): gather the fp32 activation rows of a 64-wide K chunk straight from NHWC global
@@ -94,22 +94,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int cpt = a.Cin >> 6;  // 64-wide chunks per filter tap
+    const int cpt = (a.Cin % 64 == 0) ? (a.Cin >> 6) : 0;  // 64-wide chunks per filter tap (0: general Cin % 4 path)
 
     if (warp < 8) {
         // ======================= A producers (8 warps, register double-buffered) =======================
         const int q = tid & 15, rsub = tid >> 4;      // rsub 0..15
         auto load_chunk = [&](int kc, float4* v) {
-            const int tap = kc / cpt, c0 = (kc - tap * cpt) << 6;
+            // this thread's 4-channel segment of the chunk: k = kc*64 + q*4 -> (filter tap, channel offset)
+            int tap, c0;
+            if (cpt > 0) { tap = kc / cpt; c0 = ((kc - tap * cpt) << 6) + q * 4; }       // Cin % 64 == 0
+            else { const int k = kc * 64 + q * 4; tap = k / a.Cin; c0 = k - tap * a.Cin; }  // Cin % 4 == 0 (stem)
+            const bool kvalid = tap < a.KH * a.KW;                                         // zero padding of K
             const int ky = tap / a.KW, kx = tap - ky * a.KW;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const RowInfo ri = rinfo[i * 16 + rsub];
                 const int iy = ri.iy0 + ky, ix = ri.ix0 + kx;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ri.valid && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+                if (kvalid && ri.valid && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
                     v[i] = __ldg(reinterpret_cast<const float4*>(
-                        a.in + (size_t)(ri.pix_base + iy * a.W + ix) * a.ldin + c0 + q * 4));
+                        a.in + (size_t)(ri.pix_base + iy * a.W + ix) * a.ldin + c0));
             }
         };
         auto store_chunk = [&](int kc, const float4* v) {
@@ -192,21 +196,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
         // ======================= MMA issuer =======================
         if (elect_one()) {
             constexpr uint32_t IDESC = idesc_f16(128, BN, 0, 0);
+            // descriptors of stage 0, built once; +STAGE_BYTES>>4 per stage, +2 per 32-byte k-slice
+            const uint64_t dAh0 = smem_desc_sw128(smem_u32(smem));
+            const uint64_t dAl0 = dAh0 + (SM::A_BYTES >> 4);
+            const uint64_t dBh0 = dAl0 + (SM::A_BYTES >> 4);
+            const uint64_t dBl0 = dBh0 + (SM::B_BYTES >> 4);
             for (int kc = 0; kc < a.nchunks; ++kc) {
                 const int s = kc % STAGES;
                 const uint32_t ph = (kc / STAGES) & 1;
                 mbar_wait(&a_full[s], ph);
                 mbar_wait(&b_full[s], ph);
                 tc_fence_after();
-                const uint32_t ah = smem_u32(smem + s * SM::STAGE_BYTES), al = ah + SM::A_BYTES;
-                const uint32_t bh = al + SM::A_BYTES, bl = bh + SM::B_BYTES;
+                const uint64_t so = (uint64_t)(s * (SM::STAGE_BYTES >> 4));
+                const uint64_t ah = dAh0 + so, al = dAl0 + so, bh = dBh0 + so, bl = dBl0 + so;
+                mma_ss(tmem, ah, bh, IDESC, kc ? 1u : 0u);
+                mma_ss(tmem, al, bh, IDESC, 1u);
+                mma_ss(tmem, ah, bl, IDESC, 1u);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t dah = smem_desc_sw128(ah + ks * 32), dal = smem_desc_sw128(al + ks * 32);
-                    const uint64_t dbh = smem_desc_sw128(bh + ks * 32), dbl = smem_desc_sw128(bl + ks * 32);
-                    mma_ss(tmem, dah, dbh, IDESC, (kc | ks) ? 1u : 0u);
-                    mma_ss(tmem, dal, dbh, IDESC, 1u);
-                    mma_ss(tmem, dah, dbl, IDESC, 1u);
+                for (int ks = 1; ks < 4; ++ks) {
+                    mma_ss(tmem, ah + 2 * ks, bh + 2 * ks, IDESC, 1u);
+                    mma_ss(tmem, al + 2 * ks, bh + 2 * ks, IDESC, 1u);
+                    mma_ss(tmem, ah + 2 * ks, bl + 2 * ks, IDESC, 1u);
                 }
                 mma_commit(&s_free[s]);
             }
@@ -266,12 +276,12 @@ static int launch_conv_tc(const CUtensorMap& th, const CUtensorMap& tl, const Co
 
 using namespace aotb;
 
-// wh / wl: pre-split weights [Cout][K] fp16 (K = KH*KW*Cin, ordered (ky,kx,ci)), from aotb-side packing.
+// wh / wl: pre-split weights [Cout][Kpad] fp16 (K = KH*KW*Cin ordered (ky,kx,ci), zero-padded to a multiple of 64).
 extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* wl, const float* bias, const float* res,
                                    float* out, int B, int H, int W, int Cin, int ldin, int Cout, int ldout, int ldres,
                                    int KH, int KW, int stride, int pad, int act, void* stream) {
     AOTB_REQUIRE(in && wh && wl && out, "aotb_conv2d_nhwc_tc: null pointer");
-    AOTB_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "aotb_conv2d_nhwc_tc: Cin and Cout must be multiples of 64");
+    AOTB_REQUIRE(Cin % 4 == 0 && Cout % 64 == 0, "aotb_conv2d_nhwc_tc: Cin must be a multiple of 4, Cout of 64");
     AOTB_REQUIRE(ldin % 4 == 0 && ldout % 4 == 0 && (!res || ldres % 4 == 0) && ((uintptr_t)in % 16 == 0) &&
                      ((uintptr_t)out % 16 == 0) && (!res || (uintptr_t)res % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0),
                  "aotb_conv2d_nhwc_tc: 16-byte alignment required");
@@ -283,7 +293,7 @@ extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* 
     AOTB_REQUIRE(a.Ho > 0 && a.Wo > 0, "aotb_conv2d_nhwc_tc: empty output");
     a.Cout = Cout; a.ldout = ldout; a.ldres = ldres; a.KH = KH; a.KW = KW; a.stride = stride; a.pad = pad;
     a.M = B * a.Ho * a.Wo;
-    const int K = KH * KW * Cin;
+    const int K = ((KH * KW * Cin + 63) / 64) * 64;   // weights are zero-padded to a multiple of 64 along K
     a.nchunks = K / 64;
     a.act = act;
     // tile width: widest BN that still gives >= ~1 wave of CTAs, else the narrowest

@@ -29,6 +29,12 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
     }
 }
 
+// image [3][HW] (NCHW, batch 1) -> [HW][4] NHWC with a zero 4th channel (so the stem conv reads 16-byte pixels)
+__global__ void image_to_nhwc4_kernel(const float* __restrict__ in, float4* __restrict__ out, int HW) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
+        out[i] = make_float4(in[i], in[HW + i], in[2 * HW + i], 0.f);
+}
+
 // ---------------------------------------------------------------- max-pool 3x3 s2 p1 (NHWC, C%4==0)
 __global__ void maxpool3x3s2_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W,
                                     int C4, int Ho, int Wo) {
@@ -177,6 +183,14 @@ extern "C" int aotb_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, 
     dim3 grid(cdiv(HW, 32), cdiv(C, 32), B), block(32, 8);
     transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, C, HW);
     return check_launch("aotb_nchw_to_nhwc_f32");
+}
+
+extern "C" int aotb_image_to_nhwc4_f32(const float* in, float* out, int HW, void* stream) {
+    AOTB_REQUIRE(in && out && HW > 0, "aotb_image_to_nhwc4_f32: bad args");
+    int g = (HW + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    image_to_nhwc4_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<float4*>(out), HW);
+    return check_launch("aotb_image_to_nhwc4_f32");
 }
 
 extern "C" int aotb_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int HW, void* stream) {

@@ -12,7 +12,7 @@
 //   warps 4-7   softmax warpgroup 1 (query rows 128..255)  ex2 / row sum in registers -> P back into TMEM
 //               (aliasing S) as the A operand of the PV MMA; the two groups ping-pong so MUFU and the
 //               tensor pipe overlap (issue order PV_0, S_0', PV_1, S_1').
-//   TMEM        S_0 | S_1 (128 fp32 columns each, P aliases them) | O_0 | O_1 (64 columns each)
+//   TMEM        S_0 | S_1 (128 fp32 columns each; P_hi aliases the first 64) | O_0 | O_1 | Plo_0 | Plo_1 (64 each)
 //
 // Precision ("fp16x2"): every fp32 operand x is carried as hi = fp16(x), lo = fp16(x - hi); rows of the
 // packed operands are [hi(32) | lo(32)] halfs = 128 bytes (the same bytes as fp32, one TMA swizzle atom).
@@ -90,6 +90,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         : "memory");
 }
 
+template <bool EXACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const LtArgs a) {
@@ -141,32 +142,33 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (elect_one() && T > 0) {
             constexpr uint32_t IDESC_S = idesc_f16(128, 128, 0, 0);
             constexpr uint32_t IDESC_O = idesc_f16(128, 64, 0, 1);
-            const uint32_t qaddr = smem_u32(sQ), kaddr = smem_u32(sK), vaddr = smem_u32(sV);
+            // Descriptors are built once; per-MMA work is a 64-bit add (byte offsets >> 4 land in the 14-bit
+            // start-address field: +2 per 32 B k-slice, +1024 per 16 KB stage, +128 per 16 key rows of V).
+            const uint64_t dQ0 = smem_desc_sw128(smem_u32(sQ)), dQ1 = smem_desc_sw128(smem_u32(sQ) + TILE_BYTES);
+            const uint64_t dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
             auto issue_S = [&](int i, int s) {
-                const uint32_t qa = qaddr + i * TILE_BYTES, ka = kaddr + s * TILE_BYTES;
+                const uint64_t q = i ? dQ1 : dQ0;
+                const uint64_t k = dK + (uint64_t)(s * (TILE_BYTES >> 4));
                 const uint32_t d = tmem + i * 128;
                 // k-slices of 16 halfs = 32 B inside the 128 B row: 0,1 = hi ; 2,3 = lo
-                mma_ss(d, smem_desc_sw128(qa + 0), smem_desc_sw128(ka + 0), IDESC_S, 0);
-                mma_ss(d, smem_desc_sw128(qa + 32), smem_desc_sw128(ka + 32), IDESC_S, 1);
-                if (a.exact) {
-                    mma_ss(d, smem_desc_sw128(qa + 64), smem_desc_sw128(ka + 0), IDESC_S, 1);
-                    mma_ss(d, smem_desc_sw128(qa + 96), smem_desc_sw128(ka + 32), IDESC_S, 1);
-                    mma_ss(d, smem_desc_sw128(qa + 0), smem_desc_sw128(ka + 64), IDESC_S, 1);
-                    mma_ss(d, smem_desc_sw128(qa + 32), smem_desc_sw128(ka + 96), IDESC_S, 1);
+                mma_ss(d, q, k, IDESC_S, 0);
+                mma_ss(d, q + 2, k + 2, IDESC_S, 1);
+                if (EXACT) {
+                    mma_ss(d, q + 4, k, IDESC_S, 1);          // Ql Kh
+                    mma_ss(d, q + 6, k + 2, IDESC_S, 1);
+                    mma_ss(d, q, k + 4, IDESC_S, 1);          // Qh Kl
+                    mma_ss(d, q + 2, k + 6, IDESC_S, 1);
                 }
             };
             auto issue_PV = [&](int i, int s, uint32_t acc) {
-                const uint32_t va = vaddr + s * TILE_BYTES;
+                const uint64_t v = dV + (uint64_t)(s * (TILE_BYTES >> 4));
                 const uint32_t d = tmem + 256 + i * 64;
                 const uint32_t p = tmem + i * 128;
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    mma_ts(d, p + 8 * kk, smem_desc_sw128(va + kk * 2048), IDESC_O, (kk > 0) ? 1u : acc);
-                }
-                if (a.exact) {
+                for (int kk = 0; kk < 8; ++kk) mma_ts(d, p + 8 * kk, v + 128 * kk, IDESC_O, (kk > 0) ? 1u : acc);
+                if (EXACT) {
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        mma_ts(d, p + 64 + 8 * kk, smem_desc_sw128(va + kk * 2048), IDESC_O, 1);
+                    for (int kk = 0; kk < 8; ++kk) mma_ts(d, tmem + 384 + i * 64 + 8 * kk, v + 128 * kk, IDESC_O, 1);
                 }
             };
             mbar_wait(&B->q_full, 0);
@@ -192,7 +194,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 }
             }
         }
-    } else {
+    } else if (warp < 8) {
         // ======================= softmax warpgroups =======================
         const int wg = warp >> 2, wq = warp & 3;
         const int row = wq * 32 + lane;
@@ -206,27 +208,28 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int j = 0; j < T; ++j) {
             mbar_wait(&B->s_full[wg], j & 1);
             tc_fence_after();
-            uint32_t sr[128];
-            tmem_ld32(tS + 0, sr);
-            tmem_ld32(tS + 32, sr + 32);
-            tmem_ld32(tS + 64, sr + 64);
-            tmem_ld32(tS + 96, sr + 96);
-            tmem_wait_ld();
-            if (dump && j == 0) {
-#pragma unroll
-                for (int k = 0; k < 128; ++k) a.dbg[row * 128 + k] = __uint_as_float(sr[k]);
-            }
             const int key0 = (tb + j) * BN;
+            const bool tail = key0 + BN > Tk;
+            // ---- pass 1: row max (32-column chunks, next chunk's tcgen05.ld in flight while this one is reduced)
+            uint32_t ca[32], cb[32];
             float mt = -INFINITY;
-            if (key0 + BN > Tk) {
+            tmem_ld32(tS + 0, ca);
 #pragma unroll
-                for (int k = 0; k < 128; ++k) {
-                    if (key0 + k >= Tk) sr[k] = __float_as_uint(-INFINITY);
-                    mt = fmaxf(mt, __uint_as_float(sr[k]));
+            for (int c = 0; c < 4; ++c) {
+                uint32_t* cur = (c & 1) ? cb : ca;
+                uint32_t* nxt = (c & 1) ? ca : cb;
+                tmem_wait_ld();
+                if (c < 3) tmem_ld32(tS + 32 * (c + 1), nxt);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    float v = __uint_as_float(cur[k]);
+                    if (tail && key0 + 32 * c + k >= Tk) v = -INFINITY;
+                    mt = fmaxf(mt, v);
                 }
-            } else {
+                if (dump && j == 0) {
 #pragma unroll
-                for (int k = 0; k < 128; ++k) mt = fmaxf(mt, __uint_as_float(sr[k]));
+                    for (int k = 0; k < 32; ++k) a.dbg[row * 128 + 32 * c + k] = __uint_as_float(cur[k]);
+                }
             }
             const float m_new = fmaxf(m_used, mt);
             const bool grow = (m_new > m_used) && (j > 0);
@@ -234,34 +237,48 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 // rescale the running output / sum of this warp's rows (O_i is quiescent here: every MMA issued
                 // before S_i(j) has completed, PV_i(j) is not issued until we arrive on p_full)
                 const float f = grow ? ex2((m_used - m_new) * LOG2E) : 1.f;
-                uint32_t orr[32];
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    tmem_ld32(tO + 32 * c, orr);
+                    tmem_ld32(tO + 32 * c, ca);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) orr[k] = __float_as_uint(__uint_as_float(orr[k]) * f);
-                    tmem_st32(tO + 32 * c, orr);
+                    for (int k = 0; k < 32; ++k) ca[k] = __float_as_uint(__uint_as_float(ca[k]) * f);
+                    tmem_st32(tO + 32 * c, ca);
                 }
                 l *= f;
             }
             m_used = m_new;
             const float neg = m_used * LOG2E;
+            // ---- pass 2: p = 2^(s*log2e - m*log2e), row sum, split into fp16 hi / lo, back into TMEM.
+            // P_hi chunk c lands on columns [16c, 16c+16) of the S region -- always inside chunks already consumed.
+            const uint32_t tPl = tmem + lane_addr + 384 + wg * 64;
+            tmem_ld32(tS + 0, ca);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
+                uint32_t* cur = (c & 1) ? cb : ca;
+                uint32_t* nxt = (c & 1) ? ca : cb;
+                tmem_wait_ld();
+                if (c < 3) tmem_ld32(tS + 32 * (c + 1), nxt);
                 uint32_t ph[16], pl[16];
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
-                    const float p0 = ex2(fmaf(__uint_as_float(sr[32 * c + 2 * t]), LOG2E, -neg));
-                    const float p1 = ex2(fmaf(__uint_as_float(sr[32 * c + 2 * t + 1]), LOG2E, -neg));
+                    float s0 = __uint_as_float(cur[2 * t]), s1 = __uint_as_float(cur[2 * t + 1]);
+                    if (tail) {
+                        if (key0 + 32 * c + 2 * t >= Tk) s0 = -INFINITY;
+                        if (key0 + 32 * c + 2 * t + 1 >= Tk) s1 = -INFINITY;
+                    }
+                    const float p0 = ex2(fmaf(s0, LOG2E, -neg));
+                    const float p1 = ex2(fmaf(s1, LOG2E, -neg));
                     l += p0 + p1;
                     const __half2 hi = __floats2half2_rn(p0, p1);
-                    const __half2 lo = __floats2half2_rn(p0 - __low2float(hi), p1 - __high2float(hi));
                     ph[t] = *reinterpret_cast<const uint32_t*>(&hi);
-                    pl[t] = *reinterpret_cast<const uint32_t*>(&lo);
+                    if (EXACT) {
+                        const __half2 lo = __floats2half2_rn(p0 - __low2float(hi), p1 - __high2float(hi));
+                        pl[t] = *reinterpret_cast<const uint32_t*>(&lo);
+                    }
                 }
-                tmem_st16(tS + 16 * c, ph);         // P_hi: columns [0, 64) of the S region
-                tmem_st16(tS + 64 + 16 * c, pl);    // P_lo: columns [64, 128)
+                tmem_st16(tS + 16 * c, ph);
+                if (EXACT) tmem_st16(tPl + 16 * c, pl);
             }
             tmem_wait_st();
             tc_fence_before();
@@ -380,7 +397,9 @@ extern "C" int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp,
     const size_t smem = aotb_lt_attn_tc_smem_bytes();
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::lt_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc::lt_attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc::lt_attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("aotb_lt_attn_tc_f16x2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return AOTB_ERR_CUDA;
@@ -391,6 +410,7 @@ extern "C" int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp,
     a.N = N; a.Tk = Tk; a.Tk_dev = Tk_dev; a.H = H; a.O = O; a.ldo = ldo;
     a.Opart = Opart; a.Mpart = Mpart; a.Lpart = Lpart; a.splits = splits; a.exact = exact; a.dbg = dbg;
     dim3 grid(cdiv(N, 2 * tc::BM), H, splits);
-    tc::lt_attn_tc_kernel<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(tq, tk, tv, a);
+    if (exact) tc::lt_attn_tc_kernel<true><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(tq, tk, tv, a);
+    else tc::lt_attn_tc_kernel<false><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(tq, tk, tv, a);
     return check_launch("aotb_lt_attn_tc_f16x2");
 }

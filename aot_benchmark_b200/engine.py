@@ -150,8 +150,8 @@ class _Encoder:
         if getattr(self, "_gkey", None) != (id(P), H, W):
             self.graphs = GraphCache()
             self._gkey = (id(P), H, W)
-        x = self._buf("in", (1, H, W, 3))
-        ops.nchw_to_nhwc(img.float(), x, stream=st)          # caller's tensor -> static NHWC input (eager)
+        x = self._buf("in", (1, H, W, 4))
+        ops.image_to_nhwc4(img.float(), x, stream=st)        # caller's tensor -> static NHWC4 input (eager)
         nhwc = self.graphs.run("enc", lambda: self._body(x))
         out = EncEmbs(t.permute(0, 3, 1, 2) for t in nhwc)
         out.nhwc = nhwc

@@ -55,8 +55,11 @@ def register_tc_weights(w, wh, wl):
 
 
 def split_fp16(w_kn):
-    """fp32 [K, N] -> (hi, lo) fp16 [N, K] with hi + lo ~= w to 2^-22."""
+    """fp32 [K, N] -> (hi, lo) fp16 [N, Kpad] (K zero-padded to a multiple of 64) with hi + lo ~= w to 2^-22."""
+    K = w_kn.shape[0]
     wt = w_kn.t().contiguous()
+    if K % 64:
+        wt = torch.nn.functional.pad(wt, (0, 64 - K % 64))
     hi = wt.half()
     lo = (wt - hi.float()).half()
     return hi.contiguous(), lo.contiguous()
@@ -113,6 +116,14 @@ def nchw_to_nhwc(x, out, stream=None):
     _chk(x, out)
     B, C, H, W = x.shape
     check(lib().aotb_nchw_to_nhwc_f32(_p(x.contiguous()), _p(out), B, C, H * W, _st(stream)), "aotb_nchw_to_nhwc_f32")
+    return out
+
+
+def image_to_nhwc4(img, out, stream=None):
+    """img [1,3,H,W] -> out [1,H,W,4] (4th channel zero)."""
+    _chk(img, out)
+    check(lib().aotb_image_to_nhwc4_f32(_p(img.contiguous()), _p(out), img.shape[2] * img.shape[3], _st(stream)),
+          "aotb_image_to_nhwc4_f32")
     return out
 
 

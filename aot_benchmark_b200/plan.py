@@ -66,7 +66,7 @@ class Plan:
         from . import ops
         K, N = w.shape
         cin = K if cin is None else cin
-        if cin % 64 == 0 and N % 64 == 0:
+        if cin % 4 == 0 and N % 64 == 0 and (cin % 64 == 0 or K != cin):   # general-Cin path only for real convs (stem)
             wh, wl = ops.split_fp16(w)
             ops.register_tc_weights(w, wh, wl)
             self._tc_keys.append(w.data_ptr())
@@ -107,9 +107,11 @@ class Plan:
         shift = sd[name + ".bias"].double() - sd[name + ".running_mean"].double() * scale
         return scale, shift
 
-    def _conv_bn(self, conv, bn, depthwise=False):
+    def _conv_bn(self, conv, bn, depthwise=False, pad_cin_to=None):
         scale, shift = self._bn(bn)
         w = self.sd[conv + ".weight"]
+        if pad_cin_to is not None and w.shape[1] < pad_cin_to:
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, pad_cin_to - w.shape[1]))   # zero input channels
         ns = NS(b=self._f(shift.float()), k=w.shape[2], cin=w.shape[1], cout=w.shape[0])
         ns.w = self._dw_w(w, scale) if depthwise else self._reg(self._conv_w(w, scale), w.shape[1])
         return ns
@@ -125,7 +127,7 @@ class Plan:
         self.encoder_name = name
         p = "encoder."
         if name == "resnet50":
-            e = NS(stem=self._conv_bn(p + "conv1", p + "bn1"), stages=[])
+            e = NS(stem=self._conv_bn(p + "conv1", p + "bn1", pad_cin_to=4), stages=[])   # image is fed as NHWC4
             for li, (nblk, stride) in enumerate(((3, 1), (4, 2), (6, 2)), start=1):
                 blocks = []
                 for bi in range(nblk):
@@ -138,7 +140,7 @@ class Plan:
                 e.stages.append(blocks)
             self.enc = e
         elif name == "mobilenetv2":
-            e = NS(stem=self._conv_bn(p + "features.0.0", p + "features.0.1"), blocks=[])
+            e = NS(stem=self._conv_bn(p + "features.0.0", p + "features.0.1", pad_cin_to=4), blocks=[])
             for idx, (inp, oup, stride, dil, t) in enumerate(mobilenetv2_plan(16), start=1):
                 q = f"{p}features.{idx}.conv."
                 b = NS(stride=stride, dil=dil, res=(stride == 1 and inp == oup), expand=None, tap=idx in (3, 6, 13))

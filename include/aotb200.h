@@ -35,7 +35,8 @@ int aotb_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, con
 
 /* Same contract as aotb_conv2d_nhwc_f32 (dilation 1) on the tcgen05 tensor cores, fp32-faithful through split-fp16
  * operands: wh / wl are the weights pre-split as hi = fp16(w), lo = fp16(w - hi), laid out [Cout][KH*KW*Cin] (K-major,
- * K ordered (ky,kx,ci)); activations are split on the fly.  Requires Cin % 64 == 0 and Cout % 64 == 0. */
+ * K ordered (ky,kx,ci), zero-padded to a multiple of 64); activations are split on the fly.
+ * Requires Cin % 4 == 0 and Cout % 64 == 0. */
 int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* wl, const float* bias, const float* res,
                         float* out, int B, int H, int W, int Cin, int ldin, int Cout, int ldout, int ldres,
                         int KH, int KW, int stride, int pad, int act, void* stream);
@@ -48,6 +49,8 @@ int aotb_linear_f32(const float* in, const float* wt, const float* bias, const f
 /* Layout changes at the API edge (callers hand NCHW images, read NCHW features). */
 int aotb_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int HW, void* stream);
 int aotb_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int HW, void* stream);
+/* [3][HW] image -> [HW][4] NHWC with a zero 4th channel (16-byte pixels for the stem convolution). */
+int aotb_image_to_nhwc4_f32(const float* in, float* out, int HW, void* stream);
 
 /* nn.MaxPool2d(3, 2, 1): networks/encoders/resnet.py:79,146. */
 int aotb_maxpool3x3s2_nhwc_f32(const float* in, float* out, int B, int H, int W, int C, void* stream);

@@ -28,3 +28,9 @@ fi
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2500 -c 1200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 12 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
 tail -2 gpurun_out/bench_under_ncu.log | cut -c1-200
+if [ "$2" == "prof" ] || [ "$1" == "prof" ]; then
+  echo "== ncu --set full: long-term attention kernel (late frame, large bank) and conv kernel"
+  AOTB_GRAPHS=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:lt_attn_tc_kernel -s 345 -c 1 -o gpurun_out/prof_lt python bench.py --steps 99 --warmup 3 > gpurun_out/prof_lt.log 2>&1
+  AOTB_GRAPHS=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 2000 -c 4 -o gpurun_out/prof_conv python bench.py --steps 20 --warmup 3 > gpurun_out/prof_conv.log 2>&1
+  ls -la gpurun_out/*.ncu-rep
+fi

@@ -120,6 +120,7 @@ def _pack_w(w):  # [Cout,Cin,KH,KW] -> fp32 [K, Cout] (k = (ky,kx,ci))
     (1, 31, 54, 1024, 256, 1, 1, 0, False, 0),     # projector, K = 1024
     (2, 20, 24, 128, 192, 3, 1, 1, True, 0),       # batch 2, Cout = 192 (BN = 64 only)
     (1, 1674, 1, 512, 256, 1, 1, 0, True, 0),      # linear with in-place style residual
+    (1, 65, 97, 4, 64, 7, 2, 3, False, 1),         # 7x7 stem on the zero-padded 4-channel image (K = 196 -> 256)
 ])
 def test_conv2d_tc(cfg):
     from aot_benchmark_b200 import ops
