@@ -245,6 +245,7 @@ class AOTEngine(nn.Module):
         self._P = None
         self.graphs = GraphCache()
         self.tk_dev = None
+        self.kv_shard = None          # (rank, world, process_group) when the long-term bank is sharded over GPUs
         self.restart_engine()
 
     # ------------------------------------------------------------------ protocol
@@ -271,8 +272,21 @@ class AOTEngine(nn.Module):
         self.curr_id_embs = None
         self.pred_id_logits = None
         self._have_lstt = False
+        self._mem_frames = 0          # memory frames stored so far (global count, all shards)
         if self.tk_dev is not None:
             self.tk_dev.zero_()
+
+    def enable_kv_sharding(self, rank, world, group=None):
+        """BASELINE config 4: shard the long-term bank by memory frame round-robin over `world` ranks.  Every rank
+        runs the rest of the network redundantly on identical inputs; rank `f % world` keeps memory frame f; each
+        rank's long-term attention produces un-normalised partials (m, l, O) over its shard which are all-gathered
+        (one NCCL collective per layer) and merged exactly (log-sum-exp) on every rank."""
+        if not (LT_IMPL.startswith("tc") and not self._plan_is_deaot()):
+            raise NotImplementedError("sharded long-term attention is implemented for the AOT tensor-core kernel")
+        self.kv_shard = (int(rank), int(world), group)
+
+    def _plan_is_deaot(self):
+        return self.AOT.cfg.MODEL_VOS == "deaot"
 
     def update_size(self, input_size, enc_size):
         self.input_size_2d = tuple(int(s) for s in input_size)
@@ -497,7 +511,7 @@ class AOTEngine(nn.Module):
         splits = lt_splits(self.enc_hw, self._plan().H, max(self.bank_len, 1)) if getattr(self, "_tc", False) else 0
         self.graphs.run(("lstt", splits, id(img_embs.nhwc[-1])),
                         lambda: self._lstt_forward(img_embs, None, _cur_stream()),
-                        enabled=self.short_term_mem_skip <= 1)
+                        enabled=self.short_term_mem_skip <= 1 and self.kv_shard is None)
 
     def update_short_term_memory(self, curr_mask, curr_id_emb=None, skip_long_term_update=False):
         st = torch.cuda.current_stream().cuda_stream
@@ -510,7 +524,7 @@ class AOTEngine(nn.Module):
         ws = self._ws
         label_map = curr_id_emb is None and not (curr_mask.dim() == 4 and curr_mask.shape[1] != 1) and \
             tuple(curr_mask.shape[-2:]) == tuple(ws.mask.shape)
-        if label_map and self.short_term_mem_skip <= 1:
+        if label_map and self.short_term_mem_skip <= 1 and self.kv_shard is None:
             m2 = curr_mask.reshape(ws.mask.shape).float().contiguous()
             ops.eltwise(ops.EW_COPY, m2, None, ws.mask, stream=st)
 
@@ -532,6 +546,13 @@ class AOTEngine(nn.Module):
     def _append_short_to_bank(self, st, count=True):
         """Append the newest fused K/V of every layer at the device-side row counter, then advance it."""
         N = self.enc_hw
+        if self.kv_shard is not None and count:
+            owner = self._mem_frames % self.kv_shard[1]
+            self._mem_frames += 1
+            if owner != self.kv_shard[0]:
+                return                # another rank keeps this memory frame
+        elif count:
+            self._mem_frames += 1
         if count:
             self._bank_reserve(N)
         K_src, V_src = self._latest_kv()
@@ -618,7 +639,9 @@ class AOTEngine(nn.Module):
         if probe is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        if use_tc:
+        if use_tc and self.kv_shard is not None:
+            self._sharded_attention(li, out, st)
+        elif use_tc:
             self._tc_attention(None, None, None, self.bank_Kp[li], self.bank_Vp[li], Tk, out, st, Tk_dev=self.tk_dev)
         elif self._tc:
             self._tc_attention(Q, K, V, None, None, Tk, out, st)     # reference frame: Tk = N, own K/V
@@ -652,6 +675,33 @@ class AOTEngine(nn.Module):
                 ws.part[splits] = part
         ops.lt_attention_tc(ws.Qp, Kp, Vp, N, Tk, O=out, Tk_dev=Tk_dev, splits=splits, exact=(LT_IMPL == "tc_exact"),
                             part=part, stream=st)
+
+    def _sharded_attention(self, li, out, st):
+        """Split-KV over ranks: local partials -> all_gather -> exact LSE merge.  Q was packed by the caller."""
+        import torch.distributed as dist
+        rank, world, group = self.kv_shard
+        P = self._plan()
+        ws = self._ws
+        N = self.enc_hw
+        frames_per_rank = (self._mem_frames + world - 1) // world
+        splits = max(2, lt_splits(N, P.H, max(frames_per_rank, 1) * N))      # identical on every rank
+        key = ("shard", splits)
+        bufs = ws.part.get(key)
+        if bufs is None:
+            fz = lambda *s: torch.empty(s, dtype=torch.float32, device=out.device)
+            bufs = (fz(splits, N, P.C), fz(splits, P.H, N), fz(splits, P.H, N),
+                    fz(world * splits, N, P.C), fz(world * splits, P.H, N), fz(world * splits, P.H, N))
+            ws.part[key] = bufs
+        Op, Mp, Lp, Og, Mg, Lg = bufs
+        if self.bank_len > 0:
+            ops.lt_attention_tc(ws.Qp, self.bank_Kp[li], self.bank_Vp[li], N, self.bank_len, O=None, Tk_dev=self.tk_dev,
+                                splits=splits, exact=(LT_IMPL == "tc_exact"), part=(Op, Mp, Lp), stream=st, merge=False)
+        else:                                  # this rank holds no memory frame yet: neutral partial
+            Op.zero_(); Lp.zero_(); Mp.fill_(float("-inf"))
+        dist.all_gather_into_tensor(Og, Op, group=group)
+        dist.all_gather_into_tensor(Mg, Mp, group=group)
+        dist.all_gather_into_tensor(Lg, Lp, group=group)
+        ops.attn_merge(Og, Mg, Lg, out, P.H, P.C // P.H, stream=st)
 
     # short-term memory slots (TEST_SHORT_TERM_MEM_SKIP ring, aot_engine.py:329-332)
     def _next_short_slot(self):

@@ -273,6 +273,14 @@ def bank_append(src, bank, offset, offset_dev=None, stream=None):
     return bank
 
 
+def counter_add(counter, delta, stream=None):
+    """counter: int32 CUDA tensor [1]; *counter += delta on the stream (bank row counter)."""
+    if not counter.is_cuda or counter.dtype != torch.int32:
+        raise AotbError("counter must be an int32 CUDA tensor")
+    check(lib().aotb_counter_add(counter.data_ptr(), int(delta), _st(stream)), "aotb_counter_add")
+    return counter
+
+
 # ------------------------------------------------------------------ tensor-core long-term attention
 def tc_pack_rows(src, dst, row_off=0, div=1.0, row_off_dev=None, stream=None):
     """src fp32 [rows, H*32] -> dst fp16 [H, cap, 64] rows [row_off, row_off+rows) as [hi(32) | lo(32)]."""
@@ -287,7 +295,8 @@ def tc_pack_rows(src, dst, row_off=0, div=1.0, row_off_dev=None, stream=None):
     return dst
 
 
-def lt_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True, part=None, dbg=None, stream=None):
+def lt_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True, part=None, dbg=None, stream=None,
+                    merge=True):
     """Qp [H, Nq_cap, 64], Kp/Vp [H, kv_cap, 64] packed fp16x2; O [N, H*32] fp32.
     With splits > 1, `part` = (Opart [S,N,H*32], Mpart [S,H,N], Lpart [S,H,N]) and O receives the merge."""
     H, nq_cap, _ = Qp.shape
@@ -301,6 +310,6 @@ def lt_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True
                                       _p(O) if splits == 1 else None, O.stride(0) if O is not None else 0,
                                       _p(Op), _p(Mp), _p(Lp), splits, 1 if exact else 0, _p(dbg), _st(stream)),
           "aotb_lt_attn_tc_f16x2")
-    if splits > 1:
+    if splits > 1 and merge:
         attn_merge(Op, Mp, Lp, O, H, 32, stream=stream)
     return O

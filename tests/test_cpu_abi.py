@@ -82,3 +82,30 @@ def test_overlay_resolves_in_front_of_reference():
                 REPO, os.path.join(REPO, "aot_benchmark_b200", "overlay"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert "OK" in r.stdout, r.stderr[-1500:]
+
+
+def test_every_ops_attribute_used_by_the_engine_exists():
+    """Static check (no GPU here): every `ops.<name>` / `engine_mod.<name>` referenced by the engine, the bench and
+    the entry points exists -- a missing wrapper must fail on the CPU box, not on a GPU trip."""
+    import ast
+    from aot_benchmark_b200 import engine, ops
+    for path, aliases in ((os.path.join(REPO, "aot_benchmark_b200", "engine.py"), {"ops": ops}),
+                          (os.path.join(REPO, "bench.py"), {"ops": ops, "engine_mod": engine}),
+                          (os.path.join(REPO, "__graft_entry__.py"), {})):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name) and node.value.id in aliases:
+                assert hasattr(aliases[node.value.id], node.attr), f"{path}: {node.value.id}.{node.attr} does not exist"
+
+
+def test_every_ops_wrapper_binds_a_declared_symbol():
+    import ast
+    import inspect
+    from aot_benchmark_b200 import _lib, ops
+    decl = set(_lib.parse_header())
+    src = inspect.getsource(ops)
+    used = set()
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.Attribute) and node.attr.startswith("aotb_"):
+            used.add(node.attr)
+    assert used <= decl, used - decl
