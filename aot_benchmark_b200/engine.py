@@ -934,7 +934,14 @@ class AOTInferEngine(nn.Module):
         self.long_term_mem_gap = long_term_mem_gap
         self.short_term_mem_skip = short_term_mem_skip
         self.aot_engines = []
+        self._kv_shard = None
         self.restart_engine()
+
+    def enable_kv_sharding(self, rank, world, group=None):
+        """Shard the long-term memory bank over `world` ranks (see AOTEngine.enable_kv_sharding)."""
+        self._kv_shard = (rank, world, group)
+        for e in self.aot_engines:
+            e.enable_kv_sharding(rank, world, group)
 
     def restart_engine(self):
         # keep the engines (and their device buffers) across videos; just reset their state
@@ -995,6 +1002,8 @@ class AOTInferEngine(nn.Module):
             else:
                 new_engine = self._engine_cls(self.AOT, self.gpu_id, self.long_term_mem_gap, self.short_term_mem_skip)
             new_engine.eval()
+            if self._kv_shard is not None:
+                new_engine.enable_kv_sharding(*self._kv_shard)
             self.aot_engines.append(new_engine)
         separated_masks, separated_obj_nums = self.separate_mask(mask, obj_nums)
         img_embs = None

@@ -1,0 +1,51 @@
+"""torchrun --nproc-per-node 2 scripts/test_sharded_2gpu.py
+Split-KV long-term attention across ranks (BASELINE config 4 mechanism, on R50-AOTL): every rank runs the clip with the
+memory bank sharded round-robin over the ranks (NCCL all-gather of the (m, l, O) partials per layer) and compares its
+logits with an unsharded engine on the same GPU.  Prints max |dlogit| per rank; exits non-zero on mismatch."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from aot_benchmark_b200 import EngineConfig, build_engine, build_vos_model  # noqa: E402
+from oracle import aot_oracle as O  # noqa: E402  (input generator + evaluator-loop driver only)
+from oracle import weights as OW  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = EngineConfig("shard", "r50_aotl")
+    sd = OW.build_state_dict("r50_aotl", seed=1)
+    model = build_vos_model(cfg.MODEL_VOS, cfg)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    frames, mask = O.synthetic_video(9, 241, 321, 10, seed=3)
+    frames = [f.cuda() for f in frames]
+    mask = mask.cuda()
+    outs = {}
+    for mode in ("plain", "sharded"):
+        eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=local, long_term_mem_gap=1)
+        if mode == "sharded":
+            eng.enable_kv_sharding(rank, world)
+        with torch.no_grad():
+            lo, labels = O.run_video(eng, frames, mask, 10, (240, 320),
+                                     forced_masks=outs["plain"][1] if mode == "sharded" else None)
+        outs[mode] = (lo, labels)
+        if mode == "sharded":
+            e0 = eng.aot_engines[0]
+            print(f"rank {rank}: local bank rows {e0.bank_len} of {e0._mem_frames} memory frames x {e0.enc_hw}")
+    d = max((a[:, :11] - b[:, :11]).abs().max().item() for a, b in zip(outs["plain"][0], outs["sharded"][0]))
+    print(f"rank {rank}/{world}: max |dlogit| sharded vs unsharded = {d:.3e}")
+    t = torch.tensor([d], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.destroy_process_group()
+    if t.item() > 1e-4:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
