@@ -40,6 +40,8 @@ struct ConvTcArgs {
     int KH, KW, stride, pad;
     int M, nchunks;
     int act;
+    int splits;          // split-K: blockIdx.z handles chunks [z*per, (z+1)*per); partial tiles go to `part`
+    float* part;         // [splits][M][Cout] fp32 (bias / residual / activation applied by splitk_finish_kernel)
 };
 
 struct RowInfo { int pix_base, iy0, ix0, valid; };
@@ -95,6 +97,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const int cpt = (a.Cin % 64 == 0) ? (a.Cin >> 6) : 0;  // 64-wide chunks per filter tap (0: general Cin % 4 path)
+    const int per = (a.nchunks + a.splits - 1) / a.splits;
+    const int kbeg = blockIdx.z * per;
+    const int nloc = max(0, min(per, a.nchunks - kbeg));     // chunks of this CTA (local index it <-> chunk kbeg + it)
 
     if (warp < 8) {
         // ======================= A producers (8 warps, register double-buffered) =======================
@@ -116,9 +121,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
                         a.in + (size_t)(ri.pix_base + iy * a.W + ix) * a.ldin + c0));
             }
         };
-        auto store_chunk = [&](int kc, const float4* v) {
-            const int s = kc % STAGES;
-            if (kc >= STAGES) mbar_wait(&s_free[s], ((kc / STAGES) - 1) & 1);
+        auto store_chunk = [&](int it, const float4* v) {
+            const int s = it % STAGES;
+            if (it >= STAGES) mbar_wait(&s_free[s], ((it / STAGES) - 1) & 1);
             uint8_t* Ah = smem + s * SM::STAGE_BYTES;
             uint8_t* Al = Ah + SM::A_BYTES;
 #pragma unroll
@@ -137,17 +142,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
             fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&a_full[s]);
         };
-        float4 va[8], vb[8];
-        load_chunk(0, va);
-        for (int kc = 0; kc < a.nchunks; kc += 2) {
-            if (kc + 1 < a.nchunks) load_chunk(kc + 1, vb);     // next chunk's loads in flight while this one is stored
-            store_chunk(kc, va);
-            if (kc + 2 < a.nchunks) load_chunk(kc + 2, va);
-            if (kc + 1 < a.nchunks) store_chunk(kc + 1, vb);
+        // three chunks of global loads in flight per thread (register ring), so the ~L2 latency of a chunk is
+        // covered by the convert+store work of the two chunks before it
+        float4 v0[8], v1[8], v2[8];
+        if (nloc > 0) load_chunk(kbeg, v0);
+        if (nloc > 1) load_chunk(kbeg + 1, v1);
+        for (int it = 0; it < nloc; it += 3) {
+            if (it + 2 < nloc) load_chunk(kbeg + it + 2, v2);
+            store_chunk(it, v0);
+            if (it + 1 < nloc) {
+                if (it + 3 < nloc) load_chunk(kbeg + it + 3, v0);
+                store_chunk(it + 1, v1);
+            }
+            if (it + 2 < nloc) {
+                if (it + 4 < nloc) load_chunk(kbeg + it + 4, v1);
+                store_chunk(it + 2, v2);
+            }
         }
         // ======================= epilogue (warps 0-3: columns [0, BN/2), warps 4-7: [BN/2, BN)) =======================
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
+        if (nloc > 0) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+        }
         const int wq = warp & 3;
         const int m = m0 + wq * 32 + lane;
         const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
@@ -155,9 +171,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
 #pragma unroll 1
         for (int c = cbeg; c < cbeg + BN / 2; c += 32) {
             uint32_t r[32];
-            tmem_ld32(trow + c, r);
-            tmem_wait_ld();
-            if (m < a.M) {
+            if (nloc > 0) {
+                tmem_ld32(trow + c, r);
+                tmem_wait_ld();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            if (m < a.M && a.splits > 1) {
+                float* prow = a.part + ((size_t)blockIdx.z * a.M + m) * a.Cout + n0 + c;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(prow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            } else if (m < a.M) {
                 float* orow = a.out + (size_t)m * a.ldout + n0 + c;
                 const float* rrow = a.res ? a.res + (size_t)m * a.ldres + n0 + c : nullptr;
 #pragma unroll
@@ -183,13 +210,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
         // ======================= weight TMA producer =======================
         if (elect_one()) {
             tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
-            for (int kc = 0; kc < a.nchunks; ++kc) {
-                const int s = kc % STAGES;
-                if (kc >= STAGES) mbar_wait(&s_free[s], ((kc / STAGES) - 1) & 1);
+            for (int it = 0; it < nloc; ++it) {
+                const int s = it % STAGES;
+                if (it >= STAGES) mbar_wait(&s_free[s], ((it / STAGES) - 1) & 1);
                 uint8_t* Bh = smem + s * SM::STAGE_BYTES + 2 * SM::A_BYTES;
                 mbar_arrive_expect_tx(&b_full[s], 2 * SM::B_BYTES);
-                tma_load_2d(Bh, &tmWh, &b_full[s], kc * 64, n0);
-                tma_load_2d(Bh + SM::B_BYTES, &tmWl, &b_full[s], kc * 64, n0);
+                tma_load_2d(Bh, &tmWh, &b_full[s], (kbeg + it) * 64, n0);
+                tma_load_2d(Bh + SM::B_BYTES, &tmWl, &b_full[s], (kbeg + it) * 64, n0);
             }
         }
     } else {
@@ -201,7 +228,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
             const uint64_t dAl0 = dAh0 + (SM::A_BYTES >> 4);
             const uint64_t dBh0 = dAl0 + (SM::A_BYTES >> 4);
             const uint64_t dBl0 = dBh0 + (SM::B_BYTES >> 4);
-            for (int kc = 0; kc < a.nchunks; ++kc) {
+            for (int kc = 0; kc < nloc; ++kc) {
                 const int s = kc % STAGES;
                 const uint32_t ph = (kc / STAGES) & 1;
                 mbar_wait(&a_full[s], ph);
@@ -220,12 +247,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
                 }
                 mma_commit(&s_free[s]);
             }
-            mma_commit(acc_full);
+            if (nloc > 0) mma_commit(acc_full);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 9) tmem_dealloc<BN>(tmem);
+}
+
+// out[m][n] = act( sum_z part[z][m][n] + bias[n] + res[m][n] )  (fixed summation order: deterministic)
+__global__ void splitk_finish_kernel(const float* __restrict__ part, int splits, const float* __restrict__ bias,
+                                     const float* res, int ldres, float* out, int ldout, int M, int Cout, int act) {
+    const int C4 = Cout >> 2;
+    const size_t total = (size_t)M * C4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int m = i / C4, n = (i - (size_t)m * C4) * 4;
+        float4 acc = *reinterpret_cast<const float4*>(part + (size_t)m * Cout + n);
+        for (int z = 1; z < splits; ++z) {
+            const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)z * M + m) * Cout + n);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
+            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+        }
+        if (res) {
+            const float4 r = *reinterpret_cast<const float4*>(res + (size_t)m * ldres + n);
+            acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+        }
+        acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act);
+        acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act);
+        *reinterpret_cast<float4*>(out + (size_t)m * ldout + n) = acc;
+    }
 }
 
 static int make_tmap_weights(CUtensorMap* out, const void* base, int Kpad, int Cout, int BN) {
@@ -266,8 +319,15 @@ static int launch_conv_tc(const CUtensorMap& th, const CUtensorMap& tl, const Co
         }
         configured = true;
     }
-    dim3 grid(cdiv(a.M, 128), a.Cout / BN);
+    dim3 grid(cdiv(a.M, 128), a.Cout / BN, a.splits);
     conv_tc_kernel<BN, STAGES><<<grid, 320, smem, st>>>(th, tl, a);
+    if (a.splits > 1) {
+        const size_t total = (size_t)a.M * (a.Cout / 4);
+        int g = (int)((total + 255) / 256);
+        if (g > 148 * 8) g = 148 * 8;
+        splitk_finish_kernel<<<g, 256, 0, st>>>(a.part, a.splits, a.bias, a.res, a.ldres, a.out, a.ldout, a.M, a.Cout, a.act);
+        return check_launch("aotb_conv2d_nhwc_tc", 2);
+    }
     return check_launch("aotb_conv2d_nhwc_tc");
 }
 
@@ -279,7 +339,8 @@ using namespace aotb;
 // wh / wl: pre-split weights [Cout][Kpad] fp16 (K = KH*KW*Cin ordered (ky,kx,ci), zero-padded to a multiple of 64).
 extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* wl, const float* bias, const float* res,
                                    float* out, int B, int H, int W, int Cin, int ldin, int Cout, int ldout, int ldres,
-                                   int KH, int KW, int stride, int pad, int act, void* stream) {
+                                   int KH, int KW, int stride, int pad, int act, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
     AOTB_REQUIRE(in && wh && wl && out, "aotb_conv2d_nhwc_tc: null pointer");
     AOTB_REQUIRE(Cin % 4 == 0 && Cout % 64 == 0, "aotb_conv2d_nhwc_tc: Cin must be a multiple of 4, Cout of 64");
     AOTB_REQUIRE(ldin % 4 == 0 && ldout % 4 == 0 && (!res || ldres % 4 == 0) && ((uintptr_t)in % 16 == 0) &&
@@ -301,6 +362,19 @@ extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* 
     int BN = 64;
     if (Cout % 256 == 0 && mt * (Cout / 256) >= 120) BN = 256;
     else if (Cout % 128 == 0 && mt * (Cout / 128) >= 120) BN = 128;
+    // split-K for few-CTA, deep-K layers (16x-stride maps: 14 row tiles): fill one wave of 148 SMs, >= 4 chunks each
+    a.splits = 1;
+    a.part = nullptr;
+    const int ctas = mt * (Cout / BN);
+    if (workspace && ctas <= 74 && a.nchunks >= 8) {
+        int sp = 148 / ctas;
+        if (sp > a.nchunks / 4) sp = a.nchunks / 4;
+        if (sp > 8) sp = 8;
+        if (sp > 1 && (size_t)sp * a.M * Cout * sizeof(float) <= workspace_bytes) {
+            a.splits = sp;
+            a.part = (float*)workspace;
+        }
+    }
     CUtensorMap th, tl;
     int rc;
     if ((rc = tc::make_tmap_weights(&th, wh, K, Cout, BN)) != AOTB_OK) return rc;

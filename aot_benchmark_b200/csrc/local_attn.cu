@@ -189,9 +189,9 @@ static int launch_local(const LocalArgs& a, cudaStream_t st) {
 // refilled with V and the aggregate runs with channels on lanes.
 // relv_t is relative_emb_v transposed to [H][225][32] so the per-tap row is one coalesced 128-byte read.
 template <int TY, int TX>
-__global__ void __launch_bounds__(256, 1) local_attn_tile_kernel(const LocalArgs p, const float* __restrict__ relv_t) {
+__global__ void __launch_bounds__(512, 1) local_attn_tile_kernel(const LocalArgs p, const float* __restrict__ relv_t) {
     constexpr int D = 32, HH = TY + 2 * LR, HWD = TX + 2 * LR, NPOS = HH * HWD, LD = 33;
-    constexpr int QPW = TY * TX / 8;
+    constexpr int NT = 512, QPW = TY * TX / (NT / 32);
     extern __shared__ __align__(16) float smem[];
     float* halo = smem;                 // [NPOS][LD]
     float* wk = halo + NPOS * LD;       // [225][LD]
@@ -202,16 +202,16 @@ __global__ void __launch_bounds__(256, 1) local_attn_tile_kernel(const LocalArgs
     const int ty0 = (blockIdx.x / tiles_x) * TY, tx0 = (blockIdx.x % tiles_x) * TX;
     const int g = blockIdx.y;
 
-    for (int f = tid; f < LTAPS * 8; f += 256) {
+    for (int f = tid; f < LTAPS * 8; f += NT) {
         const int r = f >> 3, c4 = (f & 7) * 4;
         const float4 v = __ldg(reinterpret_cast<const float4*>(p.relk_w + ((size_t)g * LTAPS + r) * D + c4));
         float* d = wk + r * LD + c4;
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
-    for (int t = tid; t < LTAPS; t += 256) bk[t] = __ldg(p.relk_b + g * LTAPS + t);
+    for (int t = tid; t < LTAPS; t += NT) bk[t] = __ldg(p.relk_b + g * LTAPS + t);
 
     auto load_halo = [&](const float* src, int ld) {
-        for (int f = tid; f < NPOS * 8; f += 256) {
+        for (int f = tid; f < NPOS * 8; f += NT) {
             const int pos = f >> 3, c4 = (f & 7) * 4;
             const int hy = pos / HWD, hx = pos - hy * HWD;
             const int yy = ty0 - LR + hy, xx = tx0 - LR + hx;
@@ -320,7 +320,7 @@ static int launch_local_tile(const LocalArgs& a, const float* relv_t, cudaStream
         configured = true;
     }
     dim3 grid(cdiv(a.h, TY) * cdiv(a.w, TX), a.H);
-    local_attn_tile_kernel<TY, TX><<<grid, 256, smem, st>>>(a, relv_t);
+    local_attn_tile_kernel<TY, TX><<<grid, 512, smem, st>>>(a, relv_t);
     return check_launch("aotb_local_attention_tile_f32");
 }
 

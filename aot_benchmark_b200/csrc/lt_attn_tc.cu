@@ -220,12 +220,13 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 uint32_t* nxt = (c & 1) ? ca : cb;
                 tmem_wait_ld();
                 if (c < 3) tmem_ld32(tS + 32 * (c + 1), nxt);
+                if (tail) {                       // warp-uniform: only the last key tile of the bank is ragged
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    float v = __uint_as_float(cur[k]);
-                    if (tail && key0 + 32 * c + k >= Tk) v = -INFINITY;
-                    mt = fmaxf(mt, v);
+                    for (int k = 0; k < 32; ++k)
+                        if (key0 + 32 * c + k >= Tk) cur[k] = __float_as_uint(-INFINITY);
                 }
+#pragma unroll
+                for (int k = 0; k < 32; ++k) mt = fmaxf(mt, __uint_as_float(cur[k]));
                 if (dump && j == 0) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) a.dbg[row * 128 + 32 * c + k] = __uint_as_float(cur[k]);
@@ -259,14 +260,15 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 uint32_t* nxt = (c & 1) ? ca : cb;
                 tmem_wait_ld();
                 if (c < 3) tmem_ld32(tS + 32 * (c + 1), nxt);
+                if (tail) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (key0 + 32 * c + k >= Tk) cur[k] = __float_as_uint(-INFINITY);
+                }
                 uint32_t ph[16], pl[16];
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
-                    float s0 = __uint_as_float(cur[2 * t]), s1 = __uint_as_float(cur[2 * t + 1]);
-                    if (tail) {
-                        if (key0 + 32 * c + 2 * t >= Tk) s0 = -INFINITY;
-                        if (key0 + 32 * c + 2 * t + 1 >= Tk) s1 = -INFINITY;
-                    }
+                    const float s0 = __uint_as_float(cur[2 * t]), s1 = __uint_as_float(cur[2 * t + 1]);
                     const float p0 = ex2(fmaf(s0, LOG2E, -neg));
                     const float p1 = ex2(fmaf(s1, LOG2E, -neg));
                     l += p0 + p1;

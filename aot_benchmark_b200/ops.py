@@ -50,6 +50,17 @@ _TC_WEIGHTS = {}
 CONV_IMPL = os.environ.get("AOTB_CONV_IMPL", "tc")     # "tc" (tcgen05, fp16x2 split) | "simt" (fp32 CUDA cores)
 
 
+_TC_WS = {}
+
+
+def _tc_workspace(device):
+    """Per-device split-K scratch for the tensor-core conv (16 MB: 4 splits x 1674 x 512 fp32 and more)."""
+    ws = _TC_WS.get(device)
+    if ws is None:
+        ws = _TC_WS[device] = torch.empty(16 << 20, dtype=torch.uint8, device=device)
+    return ws
+
+
 def register_tc_weights(w, wh, wl):
     _TC_WEIGHTS[w.data_ptr()] = (wh, wl, w)     # keep w alive so the pointer key stays unique
 
@@ -70,9 +81,10 @@ def conv2d_tc(x, wh, wl, bias, out, res=None, KH=1, KW=1, stride=1, pad=0, act=A
     _chk(x, bias, out, res)
     B, H, W, Cin = x.shape
     Cout = wh.shape[0]
+    ws = _tc_workspace(x.device)
     check(lib().aotb_conv2d_nhwc_tc(_p(x), wh.data_ptr(), wl.data_ptr(), _p(bias), _p(res), _p(out), B, H, W, Cin,
                                     _nhwc_ld(x), Cout, _nhwc_ld(out), _nhwc_ld(res) if res is not None else 0, KH, KW,
-                                    stride, pad, act, _st(stream)), "aotb_conv2d_nhwc_tc")
+                                    stride, pad, act, ws.data_ptr(), ws.numel(), _st(stream)), "aotb_conv2d_nhwc_tc")
     return out
 
 
@@ -100,9 +112,11 @@ def linear(x, wt, bias, out, res=None, act=ACT_NONE, stream=None):
             _chk(x, bias, out, res)
             M, K = x.shape
             N = wt.shape[1]
+            ws = _tc_workspace(x.device)
             check(lib().aotb_conv2d_nhwc_tc(_p(x), t[0].data_ptr(), t[1].data_ptr(), _p(bias), _p(res), _p(out), 1, M, 1,
                                             K, x.stride(0), N, out.stride(0), res.stride(0) if res is not None else 0,
-                                            1, 1, 1, 0, act, _st(stream)), "aotb_conv2d_nhwc_tc")
+                                            1, 1, 1, 0, act, ws.data_ptr(), ws.numel(), _st(stream)),
+                  "aotb_conv2d_nhwc_tc")
             return out
     _chk(x, wt, bias, out, res)
     M, K = x.shape

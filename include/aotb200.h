@@ -36,10 +36,12 @@ int aotb_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, con
 /* Same contract as aotb_conv2d_nhwc_f32 (dilation 1) on the tcgen05 tensor cores, fp32-faithful through split-fp16
  * operands: wh / wl are the weights pre-split as hi = fp16(w), lo = fp16(w - hi), laid out [Cout][KH*KW*Cin] (K-major,
  * K ordered (ky,kx,ci), zero-padded to a multiple of 64); activations are split on the fly.
- * Requires Cin % 4 == 0 and Cout % 64 == 0. */
+ * Requires Cin % 4 == 0 and Cout % 64 == 0.  `workspace` (optional, caller-owned device memory) enables split-K for
+ * few-tile deep-K layers: partial tiles [splits][M][Cout] are summed in a fixed order by a finishing kernel. */
 int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* wl, const float* bias, const float* res,
                         float* out, int B, int H, int W, int Cin, int ldin, int Cout, int ldout, int ldres,
-                        int KH, int KW, int stride, int pad, int act, void* stream);
+                        int KH, int KW, int stride, int pad, int act, void* workspace, size_t workspace_bytes,
+                        void* stream);
 
 /* nn.Linear on tokens: out[M][N] = act(in[M][K] @ wt[K][N] + bias + res).
  * networks/layers/transformer.py:321-367,582-665; networks/layers/attention.py:76-79,119,710,858. */

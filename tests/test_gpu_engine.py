@@ -177,3 +177,39 @@ def test_engine_tc_exact_vs_oracle_sharp_attention():
         res[impl] = max((a.cpu()[:, :11] - b[:, :11]).abs().max().item() for a, b in zip(c_lo, o_lo))
     print("sharp-attention max |dlogit| vs oracle:", res)
     assert res["tc_exact"] < 1e-3 and res["simt"] < 1e-3
+
+
+def test_cuda_graph_replay_matches_eager():
+    """Whole-call CUDA graphs (encoder / LSTT / decode / memory update, bank growth through the device counter)
+    must reproduce the eager launches bit for bit, also across two videos on the same engine."""
+    from aot_benchmark_b200 import engine as engine_mod
+    from oracle import aot_oracle as O
+    from oracle import weights as OW
+    sd = OW.build_state_dict("r50_aotl", seed=7)
+    frames, mask = O.synthetic_video(10, 161, 241, 6, seed=21)
+    frames = [f.cuda() for f in frames]
+    mask = mask.cuda()
+    res = {}
+    for use in (False, True):
+        old = engine_mod.USE_GRAPHS
+        engine_mod.USE_GRAPHS = use
+        try:
+            eng = _build_cuda_engine("r50_aotl", sd, 2)
+            outs = []
+            for rep in range(2):                      # second video reuses buffers and captured graphs
+                with torch.no_grad():
+                    lo, labels = O.run_video(eng, frames, mask, 6, (160, 240))
+                outs.append(([t.clone() for t in lo], labels))
+            if use:
+                e0 = eng.aot_engines[0]
+                assert any(slot[1] is not None for slot in e0.graphs.slots.values()), "no graph was captured"
+        finally:
+            engine_mod.USE_GRAPHS = old
+        res[use] = outs
+    for rep in range(2):
+        for a, b in zip(res[False][rep][0], res[True][rep][0]):
+            assert torch.equal(a, b)
+        for a, b in zip(res[False][rep][1], res[True][rep][1]):
+            assert torch.equal(a, b)
+    for a, b in zip(res[True][0][0], res[True][1][0]):
+        assert torch.equal(a, b)
