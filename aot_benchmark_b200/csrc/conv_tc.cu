@@ -103,41 +103,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
 
     if (warp < 8) {
         // ======================= A producers (8 warps, register double-buffered) =======================
-        const int q = tid & 15, rsub = tid >> 4;      // rsub 0..15
+        const int q = tid & 15, rsub = tid >> 4;      // rsub 0..15; this thread serves rows i*16 + rsub, i = 0..7
+        // Per-row source pointers for the current filter tap (nullptr = zero padding / out of range); recomputed only when
+        // the tap changes (never for 1x1 convs and linears, every Cin/64 chunks for 3x3), so the steady-state work per
+        // 16-byte segment is one LDG, the hi/lo split and two 8-byte swizzled STS.
+        const float* rowptr[8];
+        int cur_tap = -1;
         auto load_chunk = [&](int kc, float4* v) {
-            // this thread's 4-channel segment of the chunk: k = kc*64 + q*4 -> (filter tap, channel offset)
             int tap, c0;
             if (cpt > 0) { tap = kc / cpt; c0 = ((kc - tap * cpt) << 6) + q * 4; }       // Cin % 64 == 0
             else { const int k = kc * 64 + q * 4; tap = k / a.Cin; c0 = k - tap * a.Cin; }  // Cin % 4 == 0 (stem)
-            const bool kvalid = tap < a.KH * a.KW;                                         // zero padding of K
-            const int ky = tap / a.KW, kx = tap - ky * a.KW;
+            if (tap != cur_tap) {
+                cur_tap = tap;
+                const bool kvalid = tap < a.KH * a.KW;                                     // zero padding of K
+                const int ky = tap / a.KW, kx = tap - ky * a.KW;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const RowInfo ri = rinfo[i * 16 + rsub];
-                const int iy = ri.iy0 + ky, ix = ri.ix0 + kx;
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (kvalid && ri.valid && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
-                    v[i] = __ldg(reinterpret_cast<const float4*>(
-                        a.in + (size_t)(ri.pix_base + iy * a.W + ix) * a.ldin + c0));
+                for (int i = 0; i < 8; ++i) {
+                    const RowInfo ri = rinfo[i * 16 + rsub];
+                    const int iy = ri.iy0 + ky, ix = ri.ix0 + kx;
+                    rowptr[i] = (kvalid && ri.valid && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+                                    ? a.in + (size_t)(ri.pix_base + iy * a.W + ix) * a.ldin
+                                    : nullptr;
+                }
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                v[i] = rowptr[i] ? __ldg(reinterpret_cast<const float4*>(rowptr[i] + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
+        // byte offset of this thread's 8-byte slot inside a 128x64 half tile (128B swizzle; row & 7 == rsub & 7)
+        const uint32_t soff = rsub * 128 + (((q >> 1) ^ (rsub & 7)) << 4) + ((q & 1) << 3);
         auto store_chunk = [&](int it, const float4* v) {
             const int s = it % STAGES;
             if (it >= STAGES) mbar_wait(&s_free[s], ((it / STAGES) - 1) & 1);
-            uint8_t* Ah = smem + s * SM::STAGE_BYTES;
+            uint8_t* Ah = smem + s * SM::STAGE_BYTES + soff;
             uint8_t* Al = Ah + SM::A_BYTES;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int row = i * 16 + rsub;
-                const uint32_t off = row * 128 + (((q >> 1) ^ (row & 7)) << 4) + ((q & 1) << 3);
                 const __half2 h0 = __floats2half2_rn(v[i].x, v[i].y), h1 = __floats2half2_rn(v[i].z, v[i].w);
                 const __half2 l0 = __floats2half2_rn(v[i].x - __low2float(h0), v[i].y - __high2float(h0));
                 const __half2 l1 = __floats2half2_rn(v[i].z - __low2float(h1), v[i].w - __high2float(h1));
                 uint2 ph, pl;
                 ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
                 pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
-                *reinterpret_cast<uint2*>(Ah + off) = ph;
-                *reinterpret_cast<uint2*>(Al + off) = pl;
+                *reinterpret_cast<uint2*>(Ah + i * 2048) = ph;      // row i*16 + rsub
+                *reinterpret_cast<uint2*>(Al + i * 2048) = pl;
             }
             fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&a_full[s]);

@@ -66,6 +66,80 @@ __global__ void __launch_bounds__(256) id_embed_kernel(const float* __restrict__
     }
 }
 
+// Run-length variant: a label map is piecewise constant, so along each of the KS window rows the ids form a few runs.
+// With wp[ky][j][id][c] = sum_{kx < j} W[c, id, ky, kx] (exclusive prefix along kx, built in float64 by the host) a run
+// [a, b) of one id contributes wp[ky][b][id] - wp[ky][a][id]: ~2 table rows per run instead of one per tap
+// (typically ~40 instead of 289 one-KB rows per output pixel).
+template <bool LN>
+__global__ void __launch_bounds__(256) id_embed_runs_kernel(const float* __restrict__ mask, int Hm, int Wm,
+                                                            const float* __restrict__ wp, const float* __restrict__ bias,
+                                                            const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                                                            float* __restrict__ out, int ldo, int ho, int wo, int C,
+                                                            int NID, int KS, int stride, int pad) {
+    __shared__ int ids[17 * 17];
+    __shared__ int run_pos[17 * 18];     // per row: up to KS runs, stored as (start | end<<8 | id<<16)
+    __shared__ int run_cnt[17];
+    __shared__ float red[2][8];
+    const int pix = blockIdx.x;
+    const int oy = pix / wo, ox = pix - oy * wo;
+    for (int t = threadIdx.x; t < KS * KS; t += blockDim.x) {
+        const int ky = t / KS, kx = t - ky * KS;
+        const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+        int id = -1;
+        if (iy >= 0 && iy < Hm && ix >= 0 && ix < Wm) {
+            const float v = __ldg(mask + (size_t)iy * Wm + ix);
+            const int iv = (int)v;
+            if ((float)iv == v && iv >= 0 && iv < NID) id = iv;
+        }
+        ids[t] = id;
+    }
+    __syncthreads();
+    if (threadIdx.x < KS) {
+        const int ky = threadIdx.x;
+        int n = 0, start = 0, cur = ids[ky * KS];
+        for (int kx = 1; kx <= KS; ++kx) {
+            const int v = (kx < KS) ? ids[ky * KS + kx] : -2;
+            if (v != cur) {
+                if (cur >= 0) run_pos[ky * 18 + n++] = start | (kx << 8) | (cur << 16);
+                start = kx;
+                cur = v;
+            }
+        }
+        run_cnt[ky] = n;
+    }
+    __syncthreads();
+    const int c = threadIdx.x;      // C == blockDim.x == 256 (checked on the host)
+    float acc = 0.f;
+    for (int ky = 0; ky < KS; ++ky) {
+        const int n = run_cnt[ky];
+        const float* row = wp + (size_t)ky * (KS + 1) * NID * C + c;
+        for (int r = 0; r < n; ++r) {
+            const int e = run_pos[ky * 18 + r];
+            const int a = e & 0xff, b = (e >> 8) & 0xff, id = e >> 16;
+            acc += __ldg(row + ((size_t)b * NID + id) * C) - __ldg(row + ((size_t)a * NID + id) * C);
+        }
+    }
+    acc += __ldg(bias + c);
+    if constexpr (!LN) out[(size_t)pix * ldo + c] = acc;
+    else {
+        float s = warp_sum(acc);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) red[0][wid] = s;
+        __syncthreads();
+        float tot = 0.f;
+        for (int w2 = 0; w2 < 8; ++w2) tot += red[0][w2];
+        const float mean = tot / (float)C;
+        const float d = acc - mean;
+        float q = warp_sum(d * d);
+        if (lane == 0) red[1][wid] = q;
+        __syncthreads();
+        float tq = 0.f;
+        for (int w2 = 0; w2 < 8; ++w2) tq += red[1][w2];
+        const float rstd = rsqrtf(tq / (float)C + 1e-5f);
+        out[(size_t)pix * ldo + c] = d * rstd * __ldg(ln_g + c) + __ldg(ln_b + c);
+    }
+}
+
 __device__ __forceinline__ void bl_src(int dst, int in_sz, int out_sz, int align, int& i0, int& i1, float& l1) {
     float src;
     if (align) {
@@ -184,6 +258,26 @@ extern "C" int aotb_id_embed_f32(const float* mask, int Hm, int Wm, const float*
                                                         nid, ksize, stride, pad);
     }
     return check_launch("aotb_id_embed_f32");
+}
+
+// wp: exclusive prefix sums of the ID-bank weights along kx: [KS][KS+1][nid][C] (C must be 256).
+extern "C" int aotb_id_embed_runs_f32(const float* mask, int Hm, int Wm, const float* wp, const float* bias,
+                                      const float* ln_gamma, const float* ln_beta, float* out, int ldo, int C, int nid,
+                                      int ksize, int stride, int pad, void* stream) {
+    AOTB_REQUIRE(mask && wp && bias && out && Hm > 0 && Wm > 0, "aotb_id_embed_runs_f32: bad args");
+    AOTB_REQUIRE(ksize <= 17 && ksize > 0 && stride > 0 && C == 256 && nid < 128, "aotb_id_embed_runs_f32: unsupported shape");
+    const int ho = (Hm + 2 * pad - ksize) / stride + 1, wo = (Wm + 2 * pad - ksize) / stride + 1;
+    AOTB_REQUIRE(ho > 0 && wo > 0, "aotb_id_embed_runs_f32: empty output");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ln_gamma) {
+        AOTB_REQUIRE(ln_beta, "aotb_id_embed_runs_f32: ln_beta");
+        id_embed_runs_kernel<true><<<ho * wo, 256, 0, st>>>(mask, Hm, Wm, wp, bias, ln_gamma, ln_beta, out, ldo, ho, wo,
+                                                            C, nid, ksize, stride, pad);
+    } else {
+        id_embed_runs_kernel<false><<<ho * wo, 256, 0, st>>>(mask, Hm, Wm, wp, bias, nullptr, nullptr, out, ldo, ho, wo,
+                                                             C, nid, ksize, stride, pad);
+    }
+    return check_launch("aotb_id_embed_runs_f32");
 }
 
 extern "C" int aotb_logits_postproc_f32(const float* logits_nhwc, float* lowres_nchw, float* out_nchw, int h, int w,

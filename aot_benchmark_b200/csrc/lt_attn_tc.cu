@@ -90,8 +90,22 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 template <bool EXACT>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __maxnreg__(192)
 lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const LtArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -210,67 +224,55 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             tc_fence_after();
             const int key0 = (tb + j) * BN;
             const bool tail = key0 + BN > Tk;
-            // ---- pass 1: row max (32-column chunks, next chunk's tcgen05.ld in flight while this one is reduced)
-            uint32_t ca[32], cb[32];
-            float mt = -INFINITY;
-            tmem_ld32(tS + 0, ca);
+            // ---- the whole 128-key score row of this thread in registers (4 tcgen05.ld in flight, one wait)
+            uint32_t sr[128];
+            tmem_ld32(tS + 0, sr);
+            tmem_ld32(tS + 32, sr + 32);
+            tmem_ld32(tS + 64, sr + 64);
+            tmem_ld32(tS + 96, sr + 96);
+            tmem_wait_ld();
+            if (dump && j == 0) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t* cur = (c & 1) ? cb : ca;
-                uint32_t* nxt = (c & 1) ? ca : cb;
-                tmem_wait_ld();
-                if (c < 3) tmem_ld32(tS + 32 * (c + 1), nxt);
-                if (tail) {                       // warp-uniform: only the last key tile of the bank is ragged
-#pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        if (key0 + 32 * c + k >= Tk) cur[k] = __float_as_uint(-INFINITY);
-                }
-#pragma unroll
-                for (int k = 0; k < 32; ++k) mt = fmaxf(mt, __uint_as_float(cur[k]));
-                if (dump && j == 0) {
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) a.dbg[row * 128 + 32 * c + k] = __uint_as_float(cur[k]);
-                }
+                for (int k = 0; k < 128; ++k) a.dbg[row * 128 + k] = __uint_as_float(sr[k]);
             }
+            if (tail) {                          // warp-uniform: only the last key tile of the bank is ragged
+#pragma unroll
+                for (int k = 0; k < 128; ++k)
+                    if (key0 + k >= Tk) sr[k] = __float_as_uint(-INFINITY);
+            }
+            float mt = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 128; ++k) mt = fmaxf(mt, __uint_as_float(sr[k]));
             const float m_new = fmaxf(m_used, mt);
             const bool grow = (m_new > m_used) && (j > 0);
             if (__any_sync(0xffffffffu, grow)) {
                 // rescale the running output / sum of this warp's rows (O_i is quiescent here: every MMA issued
                 // before S_i(j) has completed, PV_i(j) is not issued until we arrive on p_full)
                 const float f = grow ? ex2((m_used - m_new) * LOG2E) : 1.f;
+                uint32_t orr[16];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    tmem_ld32(tO + 32 * c, ca);
+                for (int c = 0; c < 4; ++c) {
+                    tmem_ld16(tO + 16 * c, orr);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) ca[k] = __float_as_uint(__uint_as_float(ca[k]) * f);
-                    tmem_st32(tO + 32 * c, ca);
+                    for (int k = 0; k < 16; ++k) orr[k] = __float_as_uint(__uint_as_float(orr[k]) * f);
+                    tmem_st16(tO + 16 * c, orr);
                 }
                 l *= f;
             }
             m_used = m_new;
             const float neg = m_used * LOG2E;
-            // ---- pass 2: p = 2^(s*log2e - m*log2e), row sum, split into fp16 hi / lo, back into TMEM.
-            // P_hi chunk c lands on columns [16c, 16c+16) of the S region -- always inside chunks already consumed.
+            // ---- p = 2^(s*log2e - m*log2e), row sum, fp16 hi / lo split, back into TMEM 16 keys at a time.
+            // P_hi for keys [16c, 16c+16) lands on columns [8c, 8c+8) of the S region (dead: the row is in registers),
+            // P_lo in its own 64-column region.
             const uint32_t tPl = tmem + lane_addr + 384 + wg * 64;
-            tmem_ld32(tS + 0, ca);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t* cur = (c & 1) ? cb : ca;
-                uint32_t* nxt = (c & 1) ? ca : cb;
-                tmem_wait_ld();
-                if (c < 3) tmem_ld32(tS + 32 * (c + 1), nxt);
-                if (tail) {
+            for (int c = 0; c < 8; ++c) {
+                uint32_t ph[8], pl[8];
 #pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        if (key0 + 32 * c + k >= Tk) cur[k] = __float_as_uint(-INFINITY);
-                }
-                uint32_t ph[16], pl[16];
-#pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                    const float s0 = __uint_as_float(cur[2 * t]), s1 = __uint_as_float(cur[2 * t + 1]);
-                    const float p0 = ex2(fmaf(s0, LOG2E, -neg));
-                    const float p1 = ex2(fmaf(s1, LOG2E, -neg));
+                for (int t = 0; t < 8; ++t) {
+                    const float p0 = ex2(fmaf(__uint_as_float(sr[16 * c + 2 * t]), LOG2E, -neg));
+                    const float p1 = ex2(fmaf(__uint_as_float(sr[16 * c + 2 * t + 1]), LOG2E, -neg));
                     l += p0 + p1;
                     const __half2 hi = __floats2half2_rn(p0, p1);
                     ph[t] = *reinterpret_cast<const uint32_t*>(&hi);
@@ -279,8 +281,8 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         pl[t] = *reinterpret_cast<const uint32_t*>(&lo);
                     }
                 }
-                tmem_st16(tS + 16 * c, ph);
-                if (EXACT) tmem_st16(tPl + 16 * c, pl);
+                tmem_st8(tS + 8 * c, ph);
+                if (EXACT) tmem_st8(tPl + 8 * c, pl);
             }
             tmem_wait_st();
             tc_fence_before();

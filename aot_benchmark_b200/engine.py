@@ -48,9 +48,12 @@ USE_GRAPHS = _os.environ.get("AOTB_GRAPHS", "1") == "1"
 BANK_INIT_FRAMES = int(_os.environ.get("AOTB_BANK_FRAMES", "24"))   # initial long-term bank capacity (memory frames)
 
 
+REPLAYED_KERNELS = [0]      # kernels launched through graph replays (bench.py adds this to the library's eager count)
+
+
 class GraphCache:
-    """key -> [eager_runs, CUDAGraph | None, result]; first call runs eagerly (warm-up: lazy module loads,
-    cudaFuncSetAttribute, buffer allocation), second call is captured, later calls replay."""
+    """key -> [eager_runs, CUDAGraph | None, result, kernels_in_graph]; first call runs eagerly (warm-up: lazy module
+    loads, cudaFuncSetAttribute, buffer allocation), second call is captured, later calls replay."""
 
     def __init__(self):
         self.slots = {}
@@ -66,15 +69,20 @@ class GraphCache:
             slot = self.slots[key] = [0, None, None]
         if slot[1] is not None:
             slot[1].replay()
+            REPLAYED_KERNELS[0] += slot[3]
             return slot[2]
         if slot[0] < 1:
             slot[0] += 1
             return fn()
+        from ._lib import lib
+        n0 = lib().aotb_launch_count()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             out = fn()
+        n_kernels = int(lib().aotb_launch_count() - n0)     # kernels recorded into this graph
         g.replay()                     # capture records only; replay produces this call's results
         slot[1], slot[2] = g, out
+        slot.append(n_kernels)
         return out
 
 
@@ -463,8 +471,13 @@ class AOTEngine(nn.Module):
 
     def _id_from_static_mask(self, m2, st):
         P = self._plan()
-        ops.id_embed(m2, P.id_wt, P.id_b, self._ws.id_emb, P.C, P.nid, P.id_k, P.id_stride, P.id_pad,
-                     ln_gamma=P.id_norm[0] if P.deaot else None, ln_beta=P.id_norm[1] if P.deaot else None, stream=st)
+        if P.C == 256:
+            ops.id_embed_runs(m2, P.id_wp, P.id_b, self._ws.id_emb, P.C, P.nid, P.id_k, P.id_stride, P.id_pad,
+                              ln_gamma=P.id_norm[0] if P.deaot else None, ln_beta=P.id_norm[1] if P.deaot else None,
+                              stream=st)
+        else:
+            ops.id_embed(m2, P.id_wt, P.id_b, self._ws.id_emb, P.C, P.nid, P.id_k, P.id_stride, P.id_pad,
+                         ln_gamma=P.id_norm[0] if P.deaot else None, ln_beta=P.id_norm[1] if P.deaot else None, stream=st)
 
     def add_reference_frame(self, img=None, mask=None, frame_step=-1, obj_nums=None, img_embs=None):
         if self.obj_nums is None and obj_nums is None:

@@ -252,6 +252,15 @@ def id_embed(mask, wt, bias, out, C, nid, ksize, stride, pad, ln_gamma=None, ln_
     return out
 
 
+def id_embed_runs(mask, wp, bias, out, C, nid, ksize, stride, pad, ln_gamma=None, ln_beta=None, stream=None):
+    """Run-length form of id_embed; wp [ksize, ksize+1, nid, C] exclusive prefix sums along kx."""
+    _chk(mask, wp, bias, out, ln_gamma, ln_beta)
+    Hm, Wm = mask.shape
+    check(lib().aotb_id_embed_runs_f32(_p(mask), Hm, Wm, _p(wp), _p(bias), _p(ln_gamma), _p(ln_beta), _p(out),
+                                       out.stride(0), C, nid, ksize, stride, pad, _st(stream)), "aotb_id_embed_runs_f32")
+    return out
+
+
 def logits_postproc(logits_nhwc, lowres_nchw, out_nchw, obj_num, align_corners, stream=None):
     _chk(logits_nhwc, lowres_nchw, out_nchw)
     h, w, NC = logits_nhwc.shape[-3:]

@@ -249,4 +249,10 @@ class Plan:
         self.id_stride = 16
         self.id_pad = 8 if self.align_corners else 0       # aot.py:50-63
         self.id_wt = self._conv_w(w)                        # [(ky*K+kx)*11 + id, C]
+        # exclusive prefix sums along kx (float64) for the run-length gather: [K, K+1, 11, C]
+        k = self.id_k
+        t = w.double().permute(2, 3, 1, 0)                  # [ky, kx, id, C]
+        pre = torch.zeros(k, k + 1, t.shape[2], t.shape[3], dtype=torch.float64, device=t.device)
+        pre[:, 1:] = torch.cumsum(t, dim=1)
+        self.id_wp = self._f(pre.float())
         self.id_b = self._f(self.sd["patch_wise_id_bank.bias"])

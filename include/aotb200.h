@@ -112,6 +112,11 @@ int aotb_id_embed_f32(const float* mask, int Hm, int Wm, const float* wt, const 
                       const float* ln_gamma, const float* ln_beta, float* out, int ldo, int C, int nid,
                       int ksize, int stride, int pad, void* stream);
 
+/* Same result through run lengths: wp = exclusive prefix sums of the table along kx, [ksize][ksize+1][nid][C=256]. */
+int aotb_id_embed_runs_f32(const float* mask, int Hm, int Wm, const float* wp, const float* bias,
+                           const float* ln_gamma, const float* ln_beta, float* out, int ldo, int C, int nid,
+                           int ksize, int stride, int pad, void* stream);
+
 /* networks/engines/aot_engine.py:367-378: mask ids > obj_num with -1e10, bilinear upsample to NCHW. */
 int aotb_logits_postproc_f32(const float* logits_nhwc, float* lowres_nchw, float* out_nchw, int h, int w,
                              int NC, int obj_num, int Ho, int Wo, int align_corners, void* stream);

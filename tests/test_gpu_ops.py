@@ -358,3 +358,32 @@ def test_local_attention_tile_aot(h, w):
     ops.local_attention(tok(q), tok(k), tok(v), rkw.view(1800, 32).contiguous().to(d), rkb.to(d), rv.to(d), out2,
                         h, w, H, dd, dd)
     assert (out[:, 256:] - out2).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("align,ln", [(True, False), (True, True), (False, False)])
+def test_id_embed_runs(align, ln):
+    """Run-length / prefix-sum gather == dense conv of the one-hot mask (random blocky mask incl. invalid ids)."""
+    from aot_benchmark_b200 import ops
+    d = _dev()
+    g = torch.Generator().manual_seed(21)
+    k, pad = (17, 8) if align else (16, 0)
+    Hm, Wm = (161, 241) if align else (160, 240)
+    mask = torch.randint(0, 13, (1, 1, Hm // 5, Wm // 3), generator=g).float()      # ids 11, 12 are out of range
+    mask = F.interpolate(mask, size=(Hm, Wm), mode="nearest")
+    mask[0, 0, 5:9, 7:30] = 2.5                                                     # non-integer labels match nothing
+    w = torch.randn(256, 11, k, k, generator=g) * 0.05
+    b = torch.randn(256, generator=g) * 0.1
+    onehot = (mask == torch.arange(11).view(1, -1, 1, 1)).float()
+    ref = F.conv2d(onehot.double(), w.double(), b.double(), 16, pad)
+    ga, be = torch.randn(256, generator=g), torch.randn(256, generator=g)
+    if ln:
+        ref = F.layer_norm(ref.permute(0, 2, 3, 1), (256,), ga.double(), be.double()).permute(0, 3, 1, 2)
+    ho, wo = ref.shape[2:]
+    t = w.double().permute(2, 3, 1, 0)
+    pre = torch.zeros(k, k + 1, 11, 256, dtype=torch.float64)
+    pre[:, 1:] = torch.cumsum(t, dim=1)
+    out = torch.empty(ho * wo, 256, device=d)
+    ops.id_embed_runs(mask[0, 0].to(d), pre.float().to(d), b.to(d), out, 256, 11, k, 16, pad,
+                      ln_gamma=ga.to(d) if ln else None, ln_beta=be.to(d) if ln else None)
+    err = (out.cpu().double() - ref[0].permute(1, 2, 0).reshape(ho * wo, 256)).abs().max().item()
+    assert err < (2e-4 if ln else 3e-6), err
