@@ -105,7 +105,7 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 
 template <bool EXACT>
-__global__ void __maxnreg__(192)
+__global__ void __launch_bounds__(NTHREADS, 1)
 lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const LtArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -224,25 +224,28 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             tc_fence_after();
             const int key0 = (tb + j) * BN;
             const bool tail = key0 + BN > Tk;
-            // ---- the whole 128-key score row of this thread in registers (4 tcgen05.ld in flight, one wait)
-            uint32_t sr[128];
-            tmem_ld32(tS + 0, sr);
-            tmem_ld32(tS + 32, sr + 32);
-            tmem_ld32(tS + 64, sr + 64);
-            tmem_ld32(tS + 96, sr + 96);
-            tmem_wait_ld();
-            if (dump && j == 0) {
-#pragma unroll
-                for (int k = 0; k < 128; ++k) a.dbg[row * 128 + k] = __uint_as_float(sr[k]);
-            }
-            if (tail) {                          // warp-uniform: only the last key tile of the bank is ragged
-#pragma unroll
-                for (int k = 0; k < 128; ++k)
-                    if (key0 + k >= Tk) sr[k] = __float_as_uint(-INFINITY);
-            }
+            // ---- pass 1: row max.  All four tcgen05.ld of the 128-key row are in flight together (one exposed latency);
+            // the values are dropped again so that pass 2 can run in a 64-register window.
             float mt = -INFINITY;
+            {
+                uint32_t sr[128];
+                tmem_ld32(tS + 0, sr);
+                tmem_ld32(tS + 32, sr + 32);
+                tmem_ld32(tS + 64, sr + 64);
+                tmem_ld32(tS + 96, sr + 96);
+                tmem_wait_ld();
+                if (dump && j == 0) {
 #pragma unroll
-            for (int k = 0; k < 128; ++k) mt = fmaxf(mt, __uint_as_float(sr[k]));
+                    for (int k = 0; k < 128; ++k) a.dbg[row * 128 + k] = __uint_as_float(sr[k]);
+                }
+                if (tail) {                          // warp-uniform: only the last key tile of the bank is ragged
+#pragma unroll
+                    for (int k = 0; k < 128; ++k)
+                        if (key0 + k >= Tk) sr[k] = __float_as_uint(-INFINITY);
+                }
+#pragma unroll
+                for (int k = 0; k < 128; ++k) mt = fmaxf(mt, __uint_as_float(sr[k]));
+            }
             const float m_new = fmaxf(m_used, mt);
             const bool grow = (m_new > m_used) && (j > 0);
             if (__any_sync(0xffffffffu, grow)) {
@@ -262,17 +265,28 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
             m_used = m_new;
             const float neg = m_used * LOG2E;
-            // ---- p = 2^(s*log2e - m*log2e), row sum, fp16 hi / lo split, back into TMEM 16 keys at a time.
-            // P_hi for keys [16c, 16c+16) lands on columns [8c, 8c+8) of the S region (dead: the row is in registers),
-            // P_lo in its own 64-column region.
+            // ---- pass 2: p = 2^(s*log2e - m*log2e), row sum, fp16 hi / lo split, back into TMEM; 32-key chunks with the
+            // next chunk's tcgen05.ld in flight.  P_hi chunk c lands on columns [16c, 16c+16) of the S region -- always
+            // inside chunks already consumed; P_lo has its own 64-column region.
             const uint32_t tPl = tmem + lane_addr + 384 + wg * 64;
+            uint32_t ca[32], cb[32];
+            tmem_ld32(tS + 0, ca);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint32_t ph[8], pl[8];
+            for (int c = 0; c < 4; ++c) {
+                uint32_t* cur = (c & 1) ? cb : ca;
+                uint32_t* nxt = (c & 1) ? ca : cb;
+                tmem_wait_ld();
+                if (c < 3) tmem_ld32(tS + 32 * (c + 1), nxt);
+                if (tail) {
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const float p0 = ex2(fmaf(__uint_as_float(sr[16 * c + 2 * t]), LOG2E, -neg));
-                    const float p1 = ex2(fmaf(__uint_as_float(sr[16 * c + 2 * t + 1]), LOG2E, -neg));
+                    for (int k = 0; k < 32; ++k)
+                        if (key0 + 32 * c + k >= Tk) cur[k] = __float_as_uint(-INFINITY);
+                }
+                uint32_t ph[16], pl[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const float p0 = ex2(fmaf(__uint_as_float(cur[2 * t]), LOG2E, -neg));
+                    const float p1 = ex2(fmaf(__uint_as_float(cur[2 * t + 1]), LOG2E, -neg));
                     l += p0 + p1;
                     const __half2 hi = __floats2half2_rn(p0, p1);
                     ph[t] = *reinterpret_cast<const uint32_t*>(&hi);
@@ -281,8 +295,8 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         pl[t] = *reinterpret_cast<const uint32_t*>(&lo);
                     }
                 }
-                tmem_st8(tS + 8 * c, ph);
-                if (EXACT) tmem_st8(tPl + 8 * c, pl);
+                tmem_st16(tS + 16 * c, ph);
+                if (EXACT) tmem_st16(tPl + 16 * c, pl);
             }
             tmem_wait_st();
             tc_fence_before();

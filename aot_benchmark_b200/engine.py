@@ -881,7 +881,14 @@ class DeAOTEngine(AOTEngine):
                 gK, gV, Tk = stK[li], stV[li], N
             else:
                 gK, gV, Tk = self.bank_K[li], self.bank_V[li], self.bank_len
+            probe = LT_PROBE if not is_ref else None
+            if probe is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             ops.attention(cQ, gK, gV, ws.core, 1, d, C4, Tk=Tk, Tk_dev=None if is_ref else self.tk_dev, stream=st)
+            if probe is not None:
+                e1.record()
+                probe.append((e0, e1, 2.0 * N * Tk * (d + C4)))      # FLOPs = 2*N*Tk*(d_qk + d_v), SURVEY 8d
             self._gated_tail(ws.core, ws.catU, Lw.lt_dw, ws.dw[:, :C4], h, w, st)
             ops.local_attention(cQ, stK[li], stV[li], Lw.relk_w, Lw.relk_b, None, ws.core, h, w, 1, d, C4, stream=st)
             self._gated_tail(ws.core, ws.catU, Lw.st_dw, ws.dw[:, C4:], h, w, st)

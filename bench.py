@@ -235,11 +235,14 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(frames_host[1].numel() * 4), "d2h_bytes_per_step": int(label_host.numel()),
                 "path": "AOTInferEngine drop-in API as networks/managers/evaluator.py drives it, pinned host frames"},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": engine_mod.LT_KERNEL_NAME, "bound": "tensor", "achieved": round(achieved, 2),
+        "roofline": {"kernel": engine_mod.LT_KERNEL_NAME if cfg.MODEL_VOS == "aot"
+                     else "attn_f32_kernel<128,256> (fp32 SIMT flash attention, DeAOT 1 x 128 / 1024 head)",
+                     "bound": "tensor", "achieved": round(achieved, 2),
                      "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": traffic_note,
                      "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({how})",
                      "launches": len(eng_probe), "avg_launch_us": round(1e3 * lt_ms / max(len(eng_probe), 1), 2),
-                     "algorithmic": "FLOPs = 4*N*Tk*C per launch (N=1674, C=256, Tk=1674*m)",
+                     "algorithmic": "FLOPs = 4*N*Tk*C per launch (N=1674, C=256, Tk=1674*m)" if cfg.MODEL_VOS == "aot"
+                     else "FLOPs = 2*N*Tk*(128+1024) per launch (N=1674, Tk=1674*m)",
                      "timing": "CUDA events around every launch in an eager (graph-free) probe pass of the same clip"},
         "clocks": clocks,
     }

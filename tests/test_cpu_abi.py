@@ -109,3 +109,31 @@ def test_every_ops_wrapper_binds_a_declared_symbol():
         if isinstance(node, ast.Attribute) and node.attr.startswith("aotb_"):
             used.add(node.attr)
     assert used <= decl, used - decl
+
+
+def test_kernel_register_budgets_fit_their_block_sizes():
+    """A kernel whose registers x threads exceed the 64K register file (allocation granularity: 4 warps) fails at launch
+    with 'too many resources requested' -- catch that here, without a GPU, from the cubin resource usage."""
+    import re
+    from aot_benchmark_b200 import _lib
+    r = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    blocks = {"lt_attn_tc_kernel": 320, "conv_tc_kernel": 320, "local_attn_tile_kernel": 512, "conv_igemm_kernel": 256,
+              "attn_f32_kernel": 256, "local_attn_kernel": 256}
+    cur, seen = None, 0
+    for line in r.stdout.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            cur = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+)", line)
+        if m and cur:
+            regs = int(m.group(1))
+            for name, threads in blocks.items():
+                if name in cur:
+                    warps = (threads + 31) // 32
+                    warps4 = (warps + 3) // 4 * 4
+                    assert regs * 32 * warps4 <= 65536, f"{cur}: {regs} regs x {threads} threads does not fit"
+                    seen += 1
+    assert seen >= 6
