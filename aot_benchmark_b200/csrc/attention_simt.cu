@@ -30,6 +30,7 @@ struct AttnArgs {
 
 template <int DQK, int DVC>
 __global__ void __launch_bounds__(256) attn_f32_kernel(const AttnArgs p) {
+    pdl_sync();
     constexpr int BM = 64, BN = 64, LDS_ = BM + 4;
     constexpr int TNV = DVC / 16;
     extern __shared__ __align__(16) float smem[];
@@ -198,7 +199,7 @@ static int launch_attn(const AttnArgs& a, int H, cudaStream_t st) {
         configured = true;
     }
     dim3 grid(cdiv(a.N, 64), H, a.dv_head / DVC);
-    attn_f32_kernel<DQK, DVC><<<grid, 256, smem, st>>>(a);
+    launch(attn_f32_kernel<DQK, DVC>, dim3(grid), dim3(256), smem, st, a);
     return check_launch("aotb_attention_f32");
 }
 
@@ -233,6 +234,7 @@ namespace aotb {
 __global__ void attn_merge_kernel(const float* __restrict__ Opart, const float* __restrict__ Mpart,
                                   const float* __restrict__ Lpart, float* __restrict__ O, int R, int N, int H,
                                   int dv, int ldo) {
+    pdl_sync();
     // Opart [R][N][H*dv], Mpart/Lpart [R][H][N]
     const size_t total = (size_t)N * H * dv;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -259,6 +261,6 @@ extern "C" int aotb_attn_merge_f32(const float* Opart, const float* Mpart, const
     const size_t total = (size_t)N * H * d_v;
     int g = (int)((total + 255) / 256);
     if (g > 148 * 8) g = 148 * 8;
-    attn_merge_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(Opart, Mpart, Lpart, O, R, N, H, d_v, ldo);
+    launch(attn_merge_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, Opart, Mpart, Lpart, O, R, N, H, d_v, ldo);
     return check_launch("aotb_attn_merge_f32");
 }

@@ -13,7 +13,12 @@ void set_error(const char* fmt, ...) {
 }
 static unsigned long long g_launches = 0;
 void count_launches(int n) { g_launches += (unsigned long long)n; }
+static bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
 }  // namespace aotb
+
+// enable / disable programmatic dependent launch for every kernel of the library (default off)
+extern "C" void aotb_set_pdl(int on) { aotb::g_pdl = on != 0; }
 
 // number of kernels this library has launched in this process (bench.py's gpu_launches)
 extern "C" unsigned long long aotb_launch_count(void) { return aotb::g_launches; }

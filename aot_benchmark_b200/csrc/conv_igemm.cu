@@ -34,6 +34,7 @@ struct ConvArgs {
 
 template <int BM, int BN, int TM, int TN, bool AVEC, bool BVEC>
 __global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvArgs p) {
+    pdl_sync();
     constexpr int BK = 16;
     constexpr int PAD = 4;
     static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvArgs p) {
 template <int BM, int BN, int TM, int TN, bool AVEC, bool BVEC>
 static void launch_conv(const ConvArgs& a, cudaStream_t st) {
     dim3 grid(cdiv(a.M, BM), cdiv(a.Cout, BN));
-    conv_igemm_kernel<BM, BN, TM, TN, AVEC, BVEC><<<grid, 256, 0, st>>>(a);
+    launch(conv_igemm_kernel<BM, BN, TM, TN, AVEC, BVEC>, dim3(grid), dim3(256), 0, st, a);
 }
 
 int conv2d_dispatch(const ConvArgs& a, cudaStream_t st) {

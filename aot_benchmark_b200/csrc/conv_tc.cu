@@ -57,6 +57,7 @@ struct ConvSmem {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(320, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, const ConvTcArgs a) {
+    
     using SM = ConvSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -69,6 +70,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+    pdl_trigger();      // the next kernel may start its prologue; it waits for this grid before reading our output
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 256); mbar_init(&b_full[s], 1); mbar_init(&s_free[s], 1); }
@@ -96,6 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();         // activations / residual below were written by earlier kernels
     const int cpt = (a.Cin % 64 == 0) ? (a.Cin >> 6) : 0;  // 64-wide chunks per filter tap (0: general Cin % 4 path)
     const int per = (a.nchunks + a.splits - 1) / a.splits;
     const int kbeg = blockIdx.z * per;
@@ -267,6 +270,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
 // out[m][n] = act( sum_z part[z][m][n] + bias[n] + res[m][n] )  (fixed summation order: deterministic)
 __global__ void splitk_finish_kernel(const float* __restrict__ part, int splits, const float* __restrict__ bias,
                                      const float* res, int ldres, float* out, int ldout, int M, int Cout, int act) {
+    pdl_sync();
     const int C4 = Cout >> 2;
     const size_t total = (size_t)M * C4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -329,12 +333,12 @@ static int launch_conv_tc(const CUtensorMap& th, const CUtensorMap& tl, const Co
         configured = true;
     }
     dim3 grid(cdiv(a.M, 128), a.Cout / BN, a.splits);
-    conv_tc_kernel<BN, STAGES><<<grid, 320, smem, st>>>(th, tl, a);
+    launch(conv_tc_kernel<BN, STAGES>, dim3(grid), dim3(320), smem, st, th, tl, a);
     if (a.splits > 1) {
         const size_t total = (size_t)a.M * (a.Cout / 4);
         int g = (int)((total + 255) / 256);
         if (g > 148 * 8) g = 148 * 8;
-        splitk_finish_kernel<<<g, 256, 0, st>>>(a.part, a.splits, a.bias, a.res, a.ldres, a.out, a.ldout, a.M, a.Cout, a.act);
+        launch(splitk_finish_kernel, dim3(g), dim3(256), 0, st, a.part, a.splits, a.bias, a.res, a.ldres, a.out, a.ldout, a.M, a.Cout, a.act);
         return check_launch("aotb_conv2d_nhwc_tc", 2);
     }
     return check_launch("aotb_conv2d_nhwc_tc");

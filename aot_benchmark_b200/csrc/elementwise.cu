@@ -12,6 +12,7 @@ namespace aotb {
 // ---------------------------------------------------------------- NCHW <-> NHWC (tiled transpose)
 // in [B][R][Cc] -> out [B][Cc][R]
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc) {
+    pdl_sync();
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const float* ib = in + (size_t)b * R * Cc;
@@ -31,6 +32,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 
 // image [3][HW] (NCHW, batch 1) -> [HW][4] NHWC with a zero 4th channel (so the stem conv reads 16-byte pixels)
 __global__ void image_to_nhwc4_kernel(const float* __restrict__ in, float4* __restrict__ out, int HW) {
+    pdl_sync();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
         out[i] = make_float4(in[i], in[HW + i], in[2 * HW + i], 0.f);
 }
@@ -38,6 +40,7 @@ __global__ void image_to_nhwc4_kernel(const float* __restrict__ in, float4* __re
 // ---------------------------------------------------------------- max-pool 3x3 s2 p1 (NHWC, C%4==0)
 __global__ void maxpool3x3s2_kernel(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W,
                                     int C4, int Ho, int Wo) {
+    pdl_sync();
     const size_t total = (size_t)B * Ho * Wo * C4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         int c = i % C4;
@@ -68,6 +71,7 @@ __global__ void dwconv_kernel(const float* __restrict__ in, const float* __restr
                               const float* __restrict__ bias, float* __restrict__ out, int B, int H, int W, int C,
                               int ldin, int ldout, int Ho, int Wo, int KH, int KW, int stride, int pad, int dil,
                               int act) {
+    pdl_sync();
     const int C4 = C >> 2;
     const size_t total = (size_t)B * Ho * Wo * C4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -117,6 +121,7 @@ __device__ __forceinline__ void bilinear_src(int dst, int in_sz, int out_sz, int
 
 __global__ void bilinear_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W,
                                      int C, int Ho, int Wo, int align) {
+    pdl_sync();
     const int C4 = C >> 2;
     const size_t total = (size_t)B * Ho * Wo * C4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -151,6 +156,7 @@ enum { EW_COPY = 0, EW_ADD = 1, EW_MUL = 2, EW_SILU = 3, EW_SILU_MUL = 4, EW_FIL
 
 __global__ void eltwise_kernel(int op, const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
                                float* __restrict__ out, int ldo, int rows, int cols, float scalar) {
+    pdl_sync();
     const size_t total = (size_t)rows * cols;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int r = i / cols, c = i - (size_t)r * cols;
@@ -181,7 +187,7 @@ using namespace aotb;
 extern "C" int aotb_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int HW, void* stream) {
     AOTB_REQUIRE(in && out && B > 0 && C > 0 && HW > 0, "aotb_nchw_to_nhwc_f32: bad args");
     dim3 grid(cdiv(HW, 32), cdiv(C, 32), B), block(32, 8);
-    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, C, HW);
+    launch(transpose_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, in, out, C, HW);
     return check_launch("aotb_nchw_to_nhwc_f32");
 }
 
@@ -189,14 +195,14 @@ extern "C" int aotb_image_to_nhwc4_f32(const float* in, float* out, int HW, void
     AOTB_REQUIRE(in && out && HW > 0, "aotb_image_to_nhwc4_f32: bad args");
     int g = (HW + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    image_to_nhwc4_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<float4*>(out), HW);
+    launch(image_to_nhwc4_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, in, reinterpret_cast<float4*>(out), HW);
     return check_launch("aotb_image_to_nhwc4_f32");
 }
 
 extern "C" int aotb_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int HW, void* stream) {
     AOTB_REQUIRE(in && out && B > 0 && C > 0 && HW > 0, "aotb_nhwc_to_nchw_f32: bad args");
     dim3 grid(cdiv(C, 32), cdiv(HW, 32), B), block(32, 8);
-    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, out, HW, C);
+    launch(transpose_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, in, out, HW, C);
     return check_launch("aotb_nhwc_to_nchw_f32");
 }
 
@@ -204,8 +210,7 @@ extern "C" int aotb_maxpool3x3s2_nhwc_f32(const float* in, float* out, int B, in
     AOTB_REQUIRE(in && out && C % 4 == 0, "aotb_maxpool3x3s2_nhwc_f32: C %% 4 != 0 or null");
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const size_t total = (size_t)B * Ho * Wo * (C / 4);
-    maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), B, H, W, C / 4, Ho, Wo);
+    launch(maxpool3x3s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), B, H, W, C / 4, Ho, Wo);
     return check_launch("aotb_maxpool3x3s2_nhwc_f32");
 }
 
@@ -217,7 +222,7 @@ extern "C" int aotb_dwconv_nhwc_f32(const float* in, const float* w, const float
     const int Ho = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
     const int Wo = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
     const size_t total = (size_t)B * Ho * Wo * (C / 4);
-    dwconv_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, w, bias, out, B, H, W, C, ldin, ldout,
+    launch(dwconv_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, in, w, bias, out, B, H, W, C, ldin, ldout,
                                                                          Ho, Wo, KH, KW, stride, pad, dil, act);
     return check_launch("aotb_dwconv_nhwc_f32");
 }
@@ -226,7 +231,7 @@ extern "C" int aotb_bilinear_nhwc_f32(const float* in, float* out, int B, int H,
                                       int align_corners, void* stream) {
     AOTB_REQUIRE(in && out && C % 4 == 0 && Ho > 0 && Wo > 0, "aotb_bilinear_nhwc_f32: bad args");
     const size_t total = (size_t)B * Ho * Wo * (C / 4);
-    bilinear_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, Ho, Wo,
+    launch(bilinear_nhwc_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, in, out, B, H, W, C, Ho, Wo,
                                                                                 align_corners);
     return check_launch("aotb_bilinear_nhwc_f32");
 }
@@ -236,7 +241,7 @@ extern "C" int aotb_eltwise_f32(int op, const float* a, int lda, const float* b,
     AOTB_REQUIRE(out && rows > 0 && cols > 0 && op >= 0 && op <= 5, "aotb_eltwise_f32: bad args");
     AOTB_REQUIRE(op == EW_FILL || a, "aotb_eltwise_f32: null a");
     const size_t total = (size_t)rows * cols;
-    eltwise_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(op, a, lda, b, ldb, out, ldo, rows, cols,
+    launch(eltwise_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, op, a, lda, b, ldb, out, ldo, rows, cols,
                                                                           scalar);
     return check_launch("aotb_eltwise_f32");
 }

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256) id_embed_kernel(const float* __restrict__
                                                        const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                                                        float* __restrict__ out, int ldo, int ho, int wo, int C,
                                                        int NID, int KS, int stride, int pad) {
+    pdl_sync();
     __shared__ int ids[17 * 17];
     __shared__ float red[2][8];
     const int pix = blockIdx.x;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(256) id_embed_runs_kernel(const float* __restr
                                                             const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                                                             float* __restrict__ out, int ldo, int ho, int wo, int C,
                                                             int NID, int KS, int stride, int pad) {
+    pdl_sync();
     __shared__ int ids[17 * 17];
     __shared__ int run_pos[17 * 18];     // per row: up to KS runs, stored as (start | end<<8 | id<<16)
     __shared__ int run_cnt[17];
@@ -159,6 +161,7 @@ __device__ __forceinline__ void bl_src(int dst, int in_sz, int out_sz, int align
 // logits_nhwc [h][w][NC] -> lowres NCHW [NC][h][w] with ids > obj_num masked to -1e10
 __global__ void logits_mask_kernel(const float* __restrict__ in, float* __restrict__ lo, int h, int w, int NC,
                                    int obj_num) {
+    pdl_sync();
     const int total = NC * h * w;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int c = i / (h * w), r = i - c * h * w;
@@ -169,6 +172,7 @@ __global__ void logits_mask_kernel(const float* __restrict__ in, float* __restri
 // lowres NCHW [NC][h][w] -> out NCHW [NC][Ho][Wo], bilinear
 __global__ void logits_upsample_kernel(const float* __restrict__ lo, float* __restrict__ out, int h, int w, int NC,
                                        int Ho, int Wo, int align) {
+    pdl_sync();
     const size_t total = (size_t)NC * Ho * Wo;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int ox = i % Wo;
@@ -189,6 +193,7 @@ __global__ void logits_upsample_kernel(const float* __restrict__ lo, float* __re
 // wins on ties, like torch.argmax.
 __global__ void logits_argmax_kernel(const float* __restrict__ lo, float* __restrict__ label, int h, int w, int NC,
                                      int Ho, int Wo, int align) {
+    pdl_sync();
     const int total = Ho * Wo;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int oy = i / Wo, ox = i - oy * Wo;
@@ -212,6 +217,7 @@ __global__ void logits_argmax_kernel(const float* __restrict__ lo, float* __rest
 // nearest-neighbour resize of a label map (F.interpolate(mode='nearest'), evaluator.py:418-421):
 // src = floor(dst * in / out)
 __global__ void nearest_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int Ho, int Wo) {
+    pdl_sync();
     const int total = Ho * Wo;
     const float sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -226,6 +232,7 @@ __global__ void nearest_kernel(const float* __restrict__ in, float* __restrict__
 // rows x cols copy into bank at row offset (host value or device counter)
 __global__ void bank_append_kernel(const float* __restrict__ src, int lds, float* __restrict__ bank, int ldb,
                                    int rows, int cols4, int offset, const int* __restrict__ offset_dev) {
+    pdl_sync();
     const int off = offset_dev ? *offset_dev : offset;
     const size_t total = (size_t)rows * cols4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -235,7 +242,8 @@ __global__ void bank_append_kernel(const float* __restrict__ src, int lds, float
     }
 }
 
-__global__ void counter_add_kernel(int* ctr, int delta) { *ctr += delta; }
+__global__ void counter_add_kernel(int* ctr, int delta) {
+    pdl_sync(); *ctr += delta; }
 
 }  // namespace aotb
 
@@ -251,10 +259,10 @@ extern "C" int aotb_id_embed_f32(const float* mask, int Hm, int Wm, const float*
     cudaStream_t st = (cudaStream_t)stream;
     if (ln_gamma) {
         AOTB_REQUIRE(C == 256 && ln_beta, "aotb_id_embed_f32: fused LayerNorm needs C == 256");
-        id_embed_kernel<true><<<ho * wo, 256, 0, st>>>(mask, Hm, Wm, wt, bias, ln_gamma, ln_beta, out, ldo, ho, wo, C,
+        launch(id_embed_kernel<true>, dim3(ho * wo), dim3(256), 0, st, mask, Hm, Wm, wt, bias, ln_gamma, ln_beta, out, ldo, ho, wo, C,
                                                        nid, ksize, stride, pad);
     } else {
-        id_embed_kernel<false><<<ho * wo, 256, 0, st>>>(mask, Hm, Wm, wt, bias, nullptr, nullptr, out, ldo, ho, wo, C,
+        launch(id_embed_kernel<false>, dim3(ho * wo), dim3(256), 0, st, mask, Hm, Wm, wt, bias, nullptr, nullptr, out, ldo, ho, wo, C,
                                                         nid, ksize, stride, pad);
     }
     return check_launch("aotb_id_embed_f32");
@@ -271,10 +279,10 @@ extern "C" int aotb_id_embed_runs_f32(const float* mask, int Hm, int Wm, const f
     cudaStream_t st = (cudaStream_t)stream;
     if (ln_gamma) {
         AOTB_REQUIRE(ln_beta, "aotb_id_embed_runs_f32: ln_beta");
-        id_embed_runs_kernel<true><<<ho * wo, 256, 0, st>>>(mask, Hm, Wm, wp, bias, ln_gamma, ln_beta, out, ldo, ho, wo,
+        launch(id_embed_runs_kernel<true>, dim3(ho * wo), dim3(256), 0, st, mask, Hm, Wm, wp, bias, ln_gamma, ln_beta, out, ldo, ho, wo,
                                                             C, nid, ksize, stride, pad);
     } else {
-        id_embed_runs_kernel<false><<<ho * wo, 256, 0, st>>>(mask, Hm, Wm, wp, bias, nullptr, nullptr, out, ldo, ho, wo,
+        launch(id_embed_runs_kernel<false>, dim3(ho * wo), dim3(256), 0, st, mask, Hm, Wm, wp, bias, nullptr, nullptr, out, ldo, ho, wo,
                                                              C, nid, ksize, stride, pad);
     }
     return check_launch("aotb_id_embed_runs_f32");
@@ -284,13 +292,13 @@ extern "C" int aotb_logits_postproc_f32(const float* logits_nhwc, float* lowres_
                                         int NC, int obj_num, int Ho, int Wo, int align_corners, void* stream) {
     AOTB_REQUIRE(logits_nhwc && lowres_nchw && h > 0 && w > 0 && NC > 0, "aotb_logits_postproc_f32: bad args");
     cudaStream_t st = (cudaStream_t)stream;
-    logits_mask_kernel<<<cdiv(NC * h * w, 256), 256, 0, st>>>(logits_nhwc, lowres_nchw, h, w, NC, obj_num);
+    launch(logits_mask_kernel, dim3(cdiv(NC * h * w, 256)), dim3(256), 0, st, logits_nhwc, lowres_nchw, h, w, NC, obj_num);
     if (out_nchw) {
         AOTB_REQUIRE(Ho > 0 && Wo > 0, "aotb_logits_postproc_f32: bad output size");
         const size_t total = (size_t)NC * Ho * Wo;
         int g = (int)((total + 255) / 256);
         if (g > 148 * 16) g = 148 * 16;
-        logits_upsample_kernel<<<g, 256, 0, st>>>(lowres_nchw, out_nchw, h, w, NC, Ho, Wo, align_corners);
+        launch(logits_upsample_kernel, dim3(g), dim3(256), 0, st, lowres_nchw, out_nchw, h, w, NC, Ho, Wo, align_corners);
     }
     return check_launch("aotb_logits_postproc_f32", out_nchw ? 2 : 1);
 }
@@ -299,14 +307,14 @@ extern "C" int aotb_logits_argmax_f32(const float* lowres_nchw, float* label, in
                                       int align_corners, void* stream) {
     AOTB_REQUIRE(lowres_nchw && label && h > 0 && w > 0 && NC > 0 && Ho > 0 && Wo > 0,
                  "aotb_logits_argmax_f32: bad args");
-    logits_argmax_kernel<<<cdiv(Ho * Wo, 256), 256, 0, (cudaStream_t)stream>>>(lowres_nchw, label, h, w, NC, Ho, Wo,
+    launch(logits_argmax_kernel, dim3(cdiv(Ho * Wo, 256)), dim3(256), 0, (cudaStream_t)stream, lowres_nchw, label, h, w, NC, Ho, Wo,
                                                                                align_corners);
     return check_launch("aotb_logits_argmax_f32");
 }
 
 extern "C" int aotb_nearest_resize_f32(const float* in, float* out, int H, int W, int Ho, int Wo, void* stream) {
     AOTB_REQUIRE(in && out && H > 0 && W > 0 && Ho > 0 && Wo > 0, "aotb_nearest_resize_f32: bad args");
-    nearest_kernel<<<cdiv(Ho * Wo, 256), 256, 0, (cudaStream_t)stream>>>(in, out, H, W, Ho, Wo);
+    launch(nearest_kernel, dim3(cdiv(Ho * Wo, 256)), dim3(256), 0, (cudaStream_t)stream, in, out, H, W, Ho, Wo);
     return check_launch("aotb_nearest_resize_f32");
 }
 
@@ -317,12 +325,12 @@ extern "C" int aotb_bank_append_f32(const float* src, int lds, float* bank, int 
     const size_t total = (size_t)rows * (cols / 4);
     int g = (int)((total + 255) / 256);
     if (g > 148 * 8) g = 148 * 8;
-    bank_append_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(src, lds, bank, ldb, rows, cols / 4, offset, offset_dev);
+    launch(bank_append_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, src, lds, bank, ldb, rows, cols / 4, offset, offset_dev);
     return check_launch("aotb_bank_append_f32");
 }
 
 extern "C" int aotb_counter_add(int* counter, int delta, void* stream) {
     AOTB_REQUIRE(counter, "aotb_counter_add: null");
-    counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
+    launch(counter_add_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, counter, delta);
     return check_launch("aotb_counter_add");
 }

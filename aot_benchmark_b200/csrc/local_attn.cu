@@ -34,6 +34,7 @@ struct LocalArgs {
 
 template <int D, int DV, bool HAS_RELV, bool STAGE_WK>
 __global__ void __launch_bounds__(256) local_attn_kernel(const LocalArgs p) {
+    pdl_sync();
     constexpr int WARPS = 8;
     constexpr int WKS = D + 4;                 // padded row stride of the staged rel-k weights
     extern __shared__ __align__(16) float smem[];
@@ -176,7 +177,7 @@ static int launch_local(const LocalArgs& a, cudaStream_t st) {
         configured = true;
     }
     dim3 grid(cdiv(a.h * a.w, 8), a.H);
-    local_attn_kernel<D, DV, HAS_RELV, STAGE_WK><<<grid, 256, smem, st>>>(a);
+    launch(local_attn_kernel<D, DV, HAS_RELV, STAGE_WK>, dim3(grid), dim3(256), smem, st, a);
     return check_launch("aotb_local_attention_f32");
 }
 
@@ -190,6 +191,7 @@ static int launch_local(const LocalArgs& a, cudaStream_t st) {
 // relv_t is relative_emb_v transposed to [H][225][32] so the per-tap row is one coalesced 128-byte read.
 template <int TY, int TX>
 __global__ void __launch_bounds__(512, 1) local_attn_tile_kernel(const LocalArgs p, const float* __restrict__ relv_t) {
+    pdl_sync();
     constexpr int D = 32, HH = TY + 2 * LR, HWD = TX + 2 * LR, NPOS = HH * HWD, LD = 33;
     constexpr int NT = 512, QPW = TY * TX / (NT / 32);
     extern __shared__ __align__(16) float smem[];
@@ -320,7 +322,7 @@ static int launch_local_tile(const LocalArgs& a, const float* relv_t, cudaStream
         configured = true;
     }
     dim3 grid(cdiv(a.h, TY) * cdiv(a.w, TX), a.H);
-    local_attn_tile_kernel<TY, TX><<<grid, 512, smem, st>>>(a, relv_t);
+    launch(local_attn_tile_kernel<TY, TX>, dim3(grid), dim3(512), smem, st, a, relv_t);
     return check_launch("aotb_local_attention_tile_f32");
 }
 

@@ -108,6 +108,7 @@ template <bool EXACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const LtArgs a) {
+    
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;                                  // 2 tiles
@@ -117,12 +118,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * (2 * BM), h = blockIdx.y, z = blockIdx.z;
-    const int Tk = a.Tk_dev ? *a.Tk_dev : a.Tk;
-    const int tiles_total = (Tk + BN - 1) / BN;
-    const int per = (tiles_total + a.splits - 1) / a.splits;
-    const int tb = z * per;
-    int T = tiles_total - tb;
-    T = T < 0 ? 0 : (T > per ? per : T);
+    pdl_trigger();      // the next kernel may start its prologue; it waits for this grid before reading our output
 
     if (tid == 0) {
         mbar_init(&B->q_full, 1);
@@ -135,6 +131,13 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = B->tmem_base;
+    pdl_wait();         // everything below reads tensors (and the key counter) written by earlier kernels
+    const int Tk = a.Tk_dev ? *a.Tk_dev : a.Tk;
+    const int tiles_total = (Tk + BN - 1) / BN;
+    const int per = (tiles_total + a.splits - 1) / a.splits;
+    const int tb = z * per;
+    int T = tiles_total - tb;
+    T = T < 0 ? 0 : (T > per ? per : T);
 
     if (warp == 8) {
         // ======================= TMA producer =======================
@@ -352,6 +355,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 // src fp32 [rows][ld] (head h at columns h*32) -> dst halfs [H][cap][64] at row offset: [hi(32) | lo(32)]
 __global__ void pack_rows64_kernel(const float* __restrict__ src, int ld, __half* __restrict__ dst, int cap, int rows,
                                    int H, int row_off, const int* __restrict__ row_off_dev, float div) {
+    pdl_sync();
     const int off = row_off_dev ? *row_off_dev : row_off;
     const size_t total = (size_t)rows * H * 8;  // 4 channels per thread
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -386,7 +390,7 @@ extern "C" int aotb_tc_pack_rows_f16x2(const float* src, int ld, void* dst, int 
     const size_t total = (size_t)rows * H * 8;
     int g = (int)((total + 255) / 256);
     if (g > 148 * 8) g = 148 * 8;
-    tc::pack_rows64_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(src, ld, (__half*)dst, cap, rows, H, row_off,
+    launch(tc::pack_rows64_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, src, ld, (__half*)dst, cap, rows, H, row_off,
                                                                 row_off_dev, div);
     return check_launch("aotb_tc_pack_rows_f16x2");
 }
@@ -428,7 +432,7 @@ extern "C" int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp,
     a.N = N; a.Tk = Tk; a.Tk_dev = Tk_dev; a.H = H; a.O = O; a.ldo = ldo;
     a.Opart = Opart; a.Mpart = Mpart; a.Lpart = Lpart; a.splits = splits; a.exact = exact; a.dbg = dbg;
     dim3 grid(cdiv(N, 2 * tc::BM), H, splits);
-    if (exact) tc::lt_attn_tc_kernel<true><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(tq, tk, tv, a);
-    else tc::lt_attn_tc_kernel<false><<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(tq, tk, tv, a);
+    if (exact) launch(tc::lt_attn_tc_kernel<true>, dim3(grid), dim3(tc::NTHREADS), smem, (cudaStream_t)stream, tq, tk, tv, a);
+    else launch(tc::lt_attn_tc_kernel<false>, dim3(grid), dim3(tc::NTHREADS), smem, (cudaStream_t)stream, tq, tk, tv, a);
     return check_launch("aotb_lt_attn_tc_f16x2");
 }

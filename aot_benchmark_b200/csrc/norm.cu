@@ -18,6 +18,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const flo
                                  const float* __restrict__ beta, const float* __restrict__ add, int ldadd,
                                  float* __restrict__ out, int ldo, float* __restrict__ out2, int ldo2, int rows,
                                  int C, float eps) {
+    pdl_sync();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -61,6 +62,7 @@ constexpr int GN_CHUNKS = 64;
 
 __global__ void groupnorm_stats_kernel(const float* __restrict__ x, int ldx, int P, int G, int Cg,
                                        double* __restrict__ partial) {
+    pdl_sync();
     const int chunk = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
     const int per = (P + GN_CHUNKS - 1) / GN_CHUNKS;
     const int p0 = chunk * per, p1 = min(P, p0 + per);
@@ -92,6 +94,7 @@ __global__ void groupnorm_apply_kernel(const float* __restrict__ x, int ldx, con
                                        const float* __restrict__ beta, const double* __restrict__ partial,
                                        float* __restrict__ out, int ldo, int P, int C, int G, int Cg, int act,
                                        float eps) {
+    pdl_sync();
     extern __shared__ float stat[];  // [G][2] mean, rstd for this batch element
     const int b = blockIdx.y;
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -137,8 +140,7 @@ extern "C" int aotb_layernorm_f32(const float* x, int ldx, const float* gamma, c
     AOTB_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "aotb_layernorm_f32: C/ld must be %%4");
     AOTB_REQUIRE(!out2 || (add && ldadd % 4 == 0 && ldo2 % 4 == 0), "aotb_layernorm_f32: out2 needs add");
     const int warps_per_block = 8;
-    layernorm_kernel<<<cdiv(rows, warps_per_block), warps_per_block * 32, 0, (cudaStream_t)stream>>>(
-        x, ldx, gamma, beta, add, ldadd, out, ldo, out2, ldo2, rows, C, 1e-5f);
+    launch(layernorm_kernel, dim3(cdiv(rows, warps_per_block)), dim3(warps_per_block * 32), 0, (cudaStream_t)stream, x, ldx, gamma, beta, add, ldadd, out, ldo, out2, ldo2, rows, C, 1e-5f);
     return check_launch("aotb_layernorm_f32");
 }
 
@@ -154,11 +156,11 @@ extern "C" int aotb_groupnorm_nhwc_f32(const float* x, int ldx, const float* gam
                  "aotb_groupnorm_nhwc_f32: unsupported channel/group configuration");
     const int Cg = C / G;
     cudaStream_t st = (cudaStream_t)stream;
-    groupnorm_stats_kernel<<<dim3(GN_CHUNKS, G, B), 256, 0, st>>>(x, ldx, P, G, Cg, (double*)workspace);
+    launch(groupnorm_stats_kernel, dim3(dim3(GN_CHUNKS, G, B)), dim3(256), 0, st, x, ldx, P, G, Cg, (double*)workspace);
     const size_t total = (size_t)P * (C / 4);
     int gx = (int)((total + 255) / 256);
     if (gx > 148 * 8) gx = 148 * 8;
-    groupnorm_apply_kernel<<<dim3(gx, B), 256, 2 * G * sizeof(float), st>>>(x, ldx, gamma, beta,
+    launch(groupnorm_apply_kernel, dim3(dim3(gx, B)), dim3(256), 2 * G * sizeof(float), st, x, ldx, gamma, beta,
                                                                              (const double*)workspace, out, ldo, P, C,
                                                                              G, Cg, act, 1e-5f);
     return check_launch("aotb_groupnorm_nhwc_f32", 2);

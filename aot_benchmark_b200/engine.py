@@ -45,6 +45,14 @@ LT_KERNEL_NAME = _LT_NAMES.get(LT_IMPL, LT_IMPL)
 # Whole-call CUDA graphs (encoder / LSTT / decoder / memory update are each captured once per video geometry and
 # replayed; the live key count and the bank append offset are read from a device counter inside the kernels).
 USE_GRAPHS = _os.environ.get("AOTB_GRAPHS", "1") == "1"
+# programmatic dependent launch: kernel N+1's prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps
+# kernel N's tail; every kernel waits (griddepcontrol.wait) before reading its inputs
+USE_PDL = _os.environ.get("AOTB_PDL", "0") == "1"
+
+
+def _apply_pdl():
+    from ._lib import lib
+    lib().aotb_set_pdl(1 if USE_PDL else 0)
 BANK_INIT_FRAMES = int(_os.environ.get("AOTB_BANK_FRAMES", "24"))   # initial long-term bank capacity (memory frames)
 
 
@@ -494,6 +502,7 @@ class AOTEngine(nn.Module):
             print('No mask for reference frame!')
             exit()
         st = torch.cuda.current_stream().cuda_stream
+        _apply_pdl()
         self._P = get_plan(self.AOT)   # picks up load_state_dict / .to() done since the last video
         if img_embs is None:
             self._check_img(img)

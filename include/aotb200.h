@@ -24,6 +24,8 @@ const char* aotb_arch(void);
 const char* aotb_last_error_string(void);
 /* kernels launched by this library in this process so far (bench.py reports the delta). */
 unsigned long long aotb_launch_count(void);
+/* Launch every kernel with programmatic dependent launch (prologues overlap the previous kernel's tail). */
+void aotb_set_pdl(int on);
 
 /* nn.Conv2d (+ folded FrozenBatchNorm2d, + residual, + activation) as im2col-free implicit GEMM.
  * networks/encoders/resnet.py:34-54,140-157; networks/layers/normalization.py:30-43;
