@@ -41,7 +41,8 @@ struct ConvTcArgs {
     int M, nchunks;
     int act;
     int splits;          // split-K: blockIdx.z handles chunks [z*per, (z+1)*per); partial tiles go to `part`
-    float* part;         // [splits][M][Cout] fp32 (bias / residual / activation applied by splitk_finish_kernel)
+    float* part;         // [splits][M][Cout] fp32 partial sums
+    int* counters;       // one arrival counter per output tile (zero on entry, reset by the finishing CTA)
 };
 
 struct RowInfo { int pix_base, iy0, ix0, valid; };
@@ -67,6 +68,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     uint64_t* s_free = b_full + STAGES;
     uint64_t* acc_full = s_free + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
@@ -180,6 +182,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
         const int m = m0 + wq * 32 + lane;
         const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
         const int cbeg = (warp >> 2) * (BN / 2);
+        auto finish = [&](float4 o, int n, float* orow, const float* rrow) {   // bias + residual + activation + store
+            if (a.bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            if (rrow) {
+                const float4 rr = *reinterpret_cast<const float4*>(rrow);
+                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+            }
+            o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act);
+            o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
+            *reinterpret_cast<float4*>(orow) = o;
+        };
 #pragma unroll 1
         for (int c = cbeg; c < cbeg + BN / 2; c += 32) {
             uint32_t r[32];
@@ -190,31 +205,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
-            if (m < a.M && a.splits > 1) {
+            if (m >= a.M) continue;
+            if (a.splits > 1) {
                 float* prow = a.part + ((size_t)blockIdx.z * a.M + m) * a.Cout + n0 + c;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(prow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            } else if (m < a.M) {
+                    __stcg(reinterpret_cast<float4*>(prow + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+            } else {
                 float* orow = a.out + (size_t)m * a.ldout + n0 + c;
                 const float* rrow = a.res ? a.res + (size_t)m * a.ldres + n0 + c : nullptr;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    o.x = __uint_as_float(r[j]); o.y = __uint_as_float(r[j + 1]);
-                    o.z = __uint_as_float(r[j + 2]); o.w = __uint_as_float(r[j + 3]);
-                    if (a.bias) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c + j));
-                        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                for (int j = 0; j < 32; j += 4)
+                    finish(make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                       __uint_as_float(r[j + 3])), n0 + c + j, orow + j, rrow ? rrow + j : nullptr);
+            }
+        }
+        if (a.splits > 1) {
+            // split-K: the CTA that arrives last on this output tile sums all partial tiles in split order (so the
+            // result does not depend on which CTA that is), applies the epilogue and re-arms the counter.
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid == 0) {
+                const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+                const int prev = atomicAdd(a.counters + tile, 1);
+                const int last = (prev == a.splits - 1);
+                if (last) a.counters[tile] = 0;
+                *last_flag = last;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (*last_flag && m < a.M) {
+                __threadfence();
+#pragma unroll 1
+                for (int c = cbeg; c < cbeg + BN / 2; c += 4) {
+                    const float* p0 = a.part + (size_t)m * a.Cout + n0 + c;
+                    float4 acc = __ldcg(reinterpret_cast<const float4*>(p0));
+                    for (int z = 1; z < a.splits; ++z) {
+                        const float4 v = __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)z * a.M * a.Cout));
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                     }
-                    if (rrow) {
-                        const float4 rr = *reinterpret_cast<const float4*>(rrow + j);
-                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                    }
-                    o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act);
-                    o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
-                    *reinterpret_cast<float4*>(orow + j) = o;
+                    finish(acc, n0 + c, a.out + (size_t)m * a.ldout + n0 + c,
+                           a.res ? a.res + (size_t)m * a.ldres + n0 + c : nullptr);
                 }
             }
         }
@@ -267,33 +298,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     if (warp == 9) tmem_dealloc<BN>(tmem);
 }
 
-// out[m][n] = act( sum_z part[z][m][n] + bias[n] + res[m][n] )  (fixed summation order: deterministic)
-__global__ void splitk_finish_kernel(const float* __restrict__ part, int splits, const float* __restrict__ bias,
-                                     const float* res, int ldres, float* out, int ldout, int M, int Cout, int act) {
-    pdl_sync();
-    const int C4 = Cout >> 2;
-    const size_t total = (size_t)M * C4;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int m = i / C4, n = (i - (size_t)m * C4) * 4;
-        float4 acc = *reinterpret_cast<const float4*>(part + (size_t)m * Cout + n);
-        for (int z = 1; z < splits; ++z) {
-            const float4 v = *reinterpret_cast<const float4*>(part + ((size_t)z * M + m) * Cout + n);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
-        if (bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
-            acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
-        }
-        if (res) {
-            const float4 r = *reinterpret_cast<const float4*>(res + (size_t)m * ldres + n);
-            acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
-        }
-        acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act);
-        acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act);
-        *reinterpret_cast<float4*>(out + (size_t)m * ldout + n) = acc;
-    }
-}
-
 static int make_tmap_weights(CUtensorMap* out, const void* base, int Kpad, int Cout, int BN) {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
@@ -334,13 +338,6 @@ static int launch_conv_tc(const CUtensorMap& th, const CUtensorMap& tl, const Co
     }
     dim3 grid(cdiv(a.M, 128), a.Cout / BN, a.splits);
     launch(conv_tc_kernel<BN, STAGES>, dim3(grid), dim3(320), smem, st, th, tl, a);
-    if (a.splits > 1) {
-        const size_t total = (size_t)a.M * (a.Cout / 4);
-        int g = (int)((total + 255) / 256);
-        if (g > 148 * 8) g = 148 * 8;
-        launch(splitk_finish_kernel, dim3(g), dim3(256), 0, st, a.part, a.splits, a.bias, a.res, a.ldres, a.out, a.ldout, a.M, a.Cout, a.act);
-        return check_launch("aotb_conv2d_nhwc_tc", 2);
-    }
     return check_launch("aotb_conv2d_nhwc_tc");
 }
 
@@ -370,22 +367,25 @@ extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* 
     const int K = ((KH * KW * Cin + 63) / 64) * 64;   // weights are zero-padded to a multiple of 64 along K
     a.nchunks = K / 64;
     a.act = act;
-    // tile width: widest BN that still gives >= ~1 wave of CTAs, else the narrowest
+    // Tile width: the widest BN dividing Cout.  A 128 x BN x 16 MMA reads (4 + BN/32) KB of shared memory per BN/2 math
+    // cycles, i.e. 192 / 128 / 96 B/clk for BN = 64 / 128 / 256 against 128 B/clk of shared-memory bandwidth, and the
+    // fp16x2 split issues three of them per k-step: narrow tiles are smem-bound.  Parallelism for the small maps comes
+    // from split-K instead (>= 2 chunks per split, about one wave of CTAs).
     const int mt = cdiv(a.M, 128);
-    int BN = 64;
-    if (Cout % 256 == 0 && mt * (Cout / 256) >= 120) BN = 256;
-    else if (Cout % 128 == 0 && mt * (Cout / 128) >= 120) BN = 128;
-    // split-K for few-CTA, deep-K layers (16x-stride maps: 14 row tiles): fill one wave of 148 SMs, >= 4 chunks each
+    const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
     a.splits = 1;
     a.part = nullptr;
+    a.counters = nullptr;
     const int ctas = mt * (Cout / BN);
-    if (workspace && ctas <= 74 && a.nchunks >= 8) {
+    constexpr size_t kCounterBytes = 16384;
+    if (workspace && workspace_bytes > kCounterBytes && ctas < 100 && a.nchunks >= 4 && ctas <= 4096) {
         int sp = 148 / ctas;
-        if (sp > a.nchunks / 4) sp = a.nchunks / 4;
-        if (sp > 8) sp = 8;
-        if (sp > 1 && (size_t)sp * a.M * Cout * sizeof(float) <= workspace_bytes) {
+        if (sp > a.nchunks / 2) sp = a.nchunks / 2;
+        if (sp > 16) sp = 16;
+        if (sp > 1 && (size_t)sp * a.M * Cout * sizeof(float) + kCounterBytes <= workspace_bytes) {
             a.splits = sp;
-            a.part = (float*)workspace;
+            a.counters = (int*)workspace;                                 // zero-initialised by the owner of the workspace
+            a.part = (float*)((char*)workspace + kCounterBytes);
         }
     }
     CUtensorMap th, tl;

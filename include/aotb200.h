@@ -39,7 +39,8 @@ int aotb_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, con
  * operands: wh / wl are the weights pre-split as hi = fp16(w), lo = fp16(w - hi), laid out [Cout][KH*KW*Cin] (K-major,
  * K ordered (ky,kx,ci), zero-padded to a multiple of 64); activations are split on the fly.
  * Requires Cin % 4 == 0 and Cout % 64 == 0.  `workspace` (optional, caller-owned device memory) enables split-K for
- * few-tile deep-K layers: partial tiles [splits][M][Cout] are summed in a fixed order by a finishing kernel. */
+ * few-tile deep-K layers: its first 16 KB are per-tile arrival counters (zero on first use, re-armed by the kernel),
+ * the rest holds partial tiles [splits][M][Cout]; the last-arriving CTA of a tile sums them in split order. */
 int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* wl, const float* bias, const float* res,
                         float* out, int B, int H, int W, int Cin, int ldin, int Cout, int ldout, int ldres,
                         int KH, int KW, int stride, int pad, int act, void* workspace, size_t workspace_bytes,

@@ -34,3 +34,8 @@ if [ "$2" == "prof" ] || [ "$1" == "prof" ]; then
   AOTB_GRAPHS=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 2000 -c 4 -o gpurun_out/prof_conv python bench.py --steps 20 --warmup 3 > gpurun_out/prof_conv.log 2>&1
   ls -la gpurun_out/*.ncu-rep
 fi
+if [ "$2" == "pdl" ] || [ "$3" == "pdl" ]; then
+  echo "== programmatic dependent launch: parity tests + bench with AOTB_PDL=1"
+  AOTB_PDL=1 timeout 900 python -m pytest tests/test_gpu_engine.py tests/test_gpu_tc.py -m gpu -q > gpurun_out/pytest_pdl.log 2>&1; tail -3 gpurun_out/pytest_pdl.log
+  AOTB_PDL=1 timeout 900 python bench.py 2>&1 | tail -2 | tee gpurun_out/bench_full_pdl.log
+fi
