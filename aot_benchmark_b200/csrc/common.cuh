@@ -40,19 +40,36 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // start its prologue) and pdl_wait() before their first read of data produced by the previous kernel.
 bool pdl_enabled();
 
+// cluster_z > 1 launches thread-block clusters of (1, 1, cluster_z) CTAs (grid.z must be a multiple of it).
 template <typename... KArgs, typename... Args>
-inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+inline void launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_z,
+                           Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_z > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = 1;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = (unsigned)cluster_z;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = n;
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    launch_cluster(kernel, grid, block, smem, st, 1, args...);
 }
 
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -40,18 +40,36 @@ struct ConvTcArgs {
     int KH, KW, stride, pad;
     int M, nchunks;
     int act;
-    int splits;          // split-K: blockIdx.z handles chunks [z*per, (z+1)*per); partial tiles go to `part`
-    float* part;         // [splits][M][Cout] fp32 partial sums
-    int* counters;       // one arrival counter per output tile (zero on entry, reset by the finishing CTA)
+    int splits;          // split-K: the `splits` CTAs (blockIdx.z) of one output tile form a thread-block cluster; CTA z
+                         // handles chunks [z*per, (z+1)*per) and the partial tiles are summed over distributed smem
 };
 
+static int g_conv_tiling = 0;      // aotb_set_conv_tiling
+
 struct RowInfo { int pix_base, iy0, ix0, valid; };
+
+// bias + residual + activation + store of four consecutive output channels starting at n
+__device__ __forceinline__ void conv_finish(const ConvTcArgs& a, float4 o, int n, float* orow, const float* rrow) {
+    if (a.bias) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+    }
+    if (rrow) {
+        const float4 rr = *reinterpret_cast<const float4*>(rrow);
+        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+    }
+    o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act);
+    o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
+    *reinterpret_cast<float4*>(orow) = o;
+}
 
 template <int BN, int STAGES>
 struct ConvSmem {
     static constexpr int A_BYTES = 128 * 128;          // one 128 x 64 half tile
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STG_LD = BN + 4;              // split-K staging tile [128][BN + 4] fp32, aliases the stages
+    static_assert(128 * STG_LD * 4 <= STAGES * STAGE_BYTES, "staging tile must fit in the operand stages");
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 128 * (int)sizeof(RowInfo) + (3 * STAGES + 1) * 8 + 16 + 1024;
 };
 
@@ -68,7 +86,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     uint64_t* s_free = b_full + STAGES;
     uint64_t* acc_full = s_free + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-    volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
@@ -182,19 +199,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
         const int m = m0 + wq * 32 + lane;
         const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
         const int cbeg = (warp >> 2) * (BN / 2);
-        auto finish = [&](float4 o, int n, float* orow, const float* rrow) {   // bias + residual + activation + store
-            if (a.bias) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n));
-                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            if (rrow) {
-                const float4 rr = *reinterpret_cast<const float4*>(rrow);
-                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-            }
-            o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act);
-            o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
-            *reinterpret_cast<float4*>(orow) = o;
-        };
 #pragma unroll 1
         for (int c = cbeg; c < cbeg + BN / 2; c += 32) {
             uint32_t r[32];
@@ -205,48 +209,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
-            if (m >= a.M) continue;
             if (a.splits > 1) {
-                float* prow = a.part + ((size_t)blockIdx.z * a.M + m) * a.Cout + n0 + c;
+                // partial tile -> this CTA's staging buffer (the operand stages are dead: every MMA has completed).
+                // Row stride BN + 4 floats: an odd number of 16-byte units, so the 32 rows of a warp do not collide.
+                float* srow = reinterpret_cast<float*>(smem) + (wq * 32 + lane) * SM::STG_LD + c;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
-                    __stcg(reinterpret_cast<float4*>(prow + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
-            } else {
+                    *reinterpret_cast<float4*>(srow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            } else if (m < a.M) {
                 float* orow = a.out + (size_t)m * a.ldout + n0 + c;
                 const float* rrow = a.res ? a.res + (size_t)m * a.ldres + n0 + c : nullptr;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
-                    finish(make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                       __uint_as_float(r[j + 3])), n0 + c + j, orow + j, rrow ? rrow + j : nullptr);
-            }
-        }
-        if (a.splits > 1) {
-            // split-K: the CTA that arrives last on this output tile sums all partial tiles in split order (so the
-            // result does not depend on which CTA that is), applies the epilogue and re-arms the counter.
-            __threadfence();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (tid == 0) {
-                const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-                const int prev = atomicAdd(a.counters + tile, 1);
-                const int last = (prev == a.splits - 1);
-                if (last) a.counters[tile] = 0;
-                *last_flag = last;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (*last_flag && m < a.M) {
-                __threadfence();
-#pragma unroll 1
-                for (int c = cbeg; c < cbeg + BN / 2; c += 4) {
-                    const float* p0 = a.part + (size_t)m * a.Cout + n0 + c;
-                    float4 acc = __ldcg(reinterpret_cast<const float4*>(p0));
-                    for (int z = 1; z < a.splits; ++z) {
-                        const float4 v = __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)z * a.M * a.Cout));
-                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                    }
-                    finish(acc, n0 + c, a.out + (size_t)m * a.ldout + n0 + c,
-                           a.res ? a.res + (size_t)m * a.ldres + n0 + c : nullptr);
-                }
+                    conv_finish(a, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                               __uint_as_float(r[j + 3])), n0 + c + j, orow + j, rrow ? rrow + j : nullptr);
             }
         }
     } else if (warp == 8) {
@@ -293,6 +270,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
             if (nloc > 0) mma_commit(acc_full);
         }
     }
+    if (a.splits > 1) {
+        // split-K reduction across the cluster: CTA z owns rows [z*128/S, (z+1)*128/S) of the tile, reads that slice of
+        // every peer's staging buffer through distributed shared memory in rank order (so the sum is deterministic),
+        // applies the epilogue and writes coalesced rows.  No global-memory partials, no second kernel.
+        __syncwarp();
+        cluster_sync_all();
+        if (warp < 8) {
+            const int S = a.splits, rows = 128 / S, r0 = blockIdx.z * rows;
+            constexpr int C4 = BN / 4;
+            const uint32_t sbase = smem_u32(smem);
+            for (int e = tid; e < rows * C4; e += 256) {
+                const int row = r0 + e / C4, c = (e % C4) * 4;
+                const uint32_t off = sbase + (uint32_t)(row * SM::STG_LD + c) * 4u;
+                float4 acc = dsmem_ld_f4(dsmem_addr(off, 0));
+                for (int z = 1; z < S; ++z) {
+                    const float4 v = dsmem_ld_f4(dsmem_addr(off, (uint32_t)z));
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                const int m = m0 + row;
+                if (m < a.M)
+                    conv_finish(a, acc, n0 + c, a.out + (size_t)m * a.ldout + n0 + c,
+                                a.res ? a.res + (size_t)m * a.ldres + n0 + c : nullptr);
+            }
+        }
+        __syncwarp();
+        cluster_sync_all();      // nobody leaves (and frees its shared memory) while a peer may still read it
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 9) tmem_dealloc<BN>(tmem);
@@ -337,7 +341,7 @@ static int launch_conv_tc(const CUtensorMap& th, const CUtensorMap& tl, const Co
         configured = true;
     }
     dim3 grid(cdiv(a.M, 128), a.Cout / BN, a.splits);
-    launch(conv_tc_kernel<BN, STAGES>, dim3(grid), dim3(320), smem, st, th, tl, a);
+    launch_cluster(conv_tc_kernel<BN, STAGES>, dim3(grid), dim3(320), smem, st, a.splits, th, tl, a);
     return check_launch("aotb_conv2d_nhwc_tc");
 }
 
@@ -345,6 +349,12 @@ static int launch_conv_tc(const CUtensorMap& th, const CUtensorMap& tl, const Co
 }  // namespace aotb
 
 using namespace aotb;
+
+extern "C" int aotb_set_conv_tiling(int mode) {
+    AOTB_REQUIRE(mode == 0 || mode == 1, "aotb_set_conv_tiling: mode must be 0 (wide) or 1 (narrow)");
+    tc::g_conv_tiling = mode;
+    return AOTB_OK;
+}
 
 // wh / wl: pre-split weights [Cout][Kpad] fp16 (K = KH*KW*Cin ordered (ky,kx,ci), zero-padded to a multiple of 64).
 extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* wl, const float* bias, const float* res,
@@ -367,27 +377,27 @@ extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* 
     const int K = ((KH * KW * Cin + 63) / 64) * 64;   // weights are zero-padded to a multiple of 64 along K
     a.nchunks = K / 64;
     a.act = act;
-    // Tile width: the widest BN dividing Cout.  A 128 x BN x 16 MMA reads (4 + BN/32) KB of shared memory per BN/2 math
-    // cycles, i.e. 192 / 128 / 96 B/clk for BN = 64 / 128 / 256 against 128 B/clk of shared-memory bandwidth, and the
-    // fp16x2 split issues three of them per k-step: narrow tiles are smem-bound.  Parallelism for the small maps comes
-    // from split-K instead (>= 2 chunks per split, about one wave of CTAs).
+    // Tile width.  A 128 x BN x 16 MMA reads (4 + BN/32) KB of shared memory per BN/2 math cycles, i.e. 192 / 128 / 96
+    // B/clk for BN = 64 / 128 / 256 against 128 B/clk of shared-memory bandwidth, and the fp16x2 split issues three of
+    // them per k-step: narrow tiles are smem-bound.  Default ("wide"): the widest BN dividing Cout, parallelism for the
+    // small maps from split-K clusters of 2 / 4 / 8 CTAs (>= 2 chunks per CTA, about one wave in total).
     const int mt = cdiv(a.M, 128);
-    const int BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
-    a.splits = 1;
-    a.part = nullptr;
-    a.counters = nullptr;
-    const int ctas = mt * (Cout / BN);
-    constexpr size_t kCounterBytes = 16384;
-    if (workspace && workspace_bytes > kCounterBytes && ctas < 100 && a.nchunks >= 4 && ctas <= 4096) {
-        int sp = 148 / ctas;
-        if (sp > a.nchunks / 2) sp = a.nchunks / 2;
-        if (sp > 16) sp = 16;
-        if (sp > 1 && (size_t)sp * a.M * Cout * sizeof(float) + kCounterBytes <= workspace_bytes) {
-            a.splits = sp;
-            a.counters = (int*)workspace;                                 // zero-initialised by the owner of the workspace
-            a.part = (float*)((char*)workspace + kCounterBytes);
-        }
+    int BN;
+    if (tc::g_conv_tiling == 0) {
+        BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+    } else {          // "narrow": the widest BN that still fills ~a wave on its own, else 64
+        BN = 64;
+        if (Cout % 256 == 0 && mt * (Cout / 256) >= 120) BN = 256;
+        else if (Cout % 128 == 0 && mt * (Cout / 128) >= 120) BN = 128;
     }
+    a.splits = 1;
+    const int ctas = mt * (Cout / BN);
+    if (ctas < 100 && a.nchunks >= 4) {
+        int sp = 8;
+        while (sp > 1 && (ctas * sp > 160 || a.nchunks / sp < 2)) sp >>= 1;
+        a.splits = sp;
+    }
+    (void)workspace; (void)workspace_bytes;      // reserved (the split-K reduction runs over distributed shared memory)
     CUtensorMap th, tl;
     int rc;
     if ((rc = tc::make_tmap_weights(&th, wh, K, Cout, BN)) != AOTB_OK) return rc;

@@ -182,35 +182,35 @@ static int launch_local(const LocalArgs& a, cudaStream_t st) {
 }
 
 
-// ---------------------------------------------------------------------------------------------------
-// Tiled variant for the AOT head shape (d = dv = 32): one CTA = one head x an 8x8 tile of query pixels.
-// The (8+14)^2 K halo is staged once in shared memory with coalesced 128-byte row loads (the per-warp kernel
-// above issues one scattered 16-byte load per lane and tap), scores are computed with taps on lanes, the
-// softmax probabilities of the tile's 64 queries are parked in shared memory, then the same halo buffer is
-// refilled with V and the aggregate runs with channels on lanes.
-// relv_t is relative_emb_v transposed to [H][225][32] so the per-tap row is one coalesced 128-byte read.
+// Tiled kernel for the AOT head shape (d_att = d_v = 32): one CTA per (TY x TX query tile, head), 16 warps.
+// The per-warp kernel above is bound by shared-memory bandwidth (one LDS per FMA).  Here every operand that is
+// reused sits in registers and the other one is a broadcast read:
+//   R pass    thread <-> (tap, half of the queries): its relative_emb_k row stays in 32 registers, q comes from
+//             shared memory as broadcast float4 reads; writes r[tap] into the score tile.
+//   dot pass  thread <-> key position of the 15 x (TX+14) strip under one query row: the key row is read once into
+//             32 registers and dotted with the TX queries of the row (position p is tap p-x of query x), then
+//             added onto r in the score tile ( -1e8 outside the frame, attention.py:355-357).
+//   softmax   warp per query over the padded [15][16] score rows.
+//   aggregate warp <-> 3 neighbouring queries, channels on lanes: the 17 value positions and 15 relative_emb_v
+//             rows of a window row are loaded once and shared by the 3 queries; probabilities come in as float4.
+// The K halo buffer is refilled with V after the dot pass.  relv_t is relative_emb_v transposed to [H][225][32].
 template <int TY, int TX>
 __global__ void __launch_bounds__(512, 1) local_attn_tile_kernel(const LocalArgs p, const float* __restrict__ relv_t) {
     pdl_sync();
-    constexpr int D = 32, HH = TY + 2 * LR, HWD = TX + 2 * LR, NPOS = HH * HWD, LD = 33;
-    constexpr int NT = 512, QPW = TY * TX / (NT / 32);
+    constexpr int D = 32, HH = TY + 2 * LR, HWD = TX + 2 * LR, NPOS = HH * HWD, LD = 36;
+    constexpr int NT = 512, NQ = TY * TX, PLD = LW * 16;
+    static_assert(TX % 3 == 0 && TY * (TX / 3) == NT / 32, "aggregate pass: one warp per 3 queries");
+    static_assert(LW * HWD <= NT && 2 * LTAPS <= NT && NQ % 2 == 0, "pass mappings");
     extern __shared__ __align__(16) float smem[];
-    float* halo = smem;                 // [NPOS][LD]
-    float* wk = halo + NPOS * LD;       // [225][LD]
-    float* bk = wk + LTAPS * LD;        // [225]
+    float* halo = smem;                   // [NPOS][LD]   K, then V
+    float* qs = halo + NPOS * LD;         // [NQ][D]
+    float* prob = qs + NQ * D;            // [NQ][15][16] scores, then probabilities (slot 15 of each row is padding)
+    float* rvs = prob + NQ * PLD;         // [225][D]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_x = (p.w + TX - 1) / TX;
     const int ty0 = (blockIdx.x / tiles_x) * TY, tx0 = (blockIdx.x % tiles_x) * TX;
     const int g = blockIdx.y;
-
-    for (int f = tid; f < LTAPS * 8; f += NT) {
-        const int r = f >> 3, c4 = (f & 7) * 4;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p.relk_w + ((size_t)g * LTAPS + r) * D + c4));
-        float* d = wk + r * LD + c4;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-    }
-    for (int t = tid; t < LTAPS; t += NT) bk[t] = __ldg(p.relk_b + g * LTAPS + t);
 
     auto load_halo = [&](const float* src, int ld) {
         for (int f = tid; f < NPOS * 8; f += NT) {
@@ -220,97 +220,154 @@ __global__ void __launch_bounds__(512, 1) local_attn_tile_kernel(const LocalArgs
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w)
                 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(yy * p.w + xx) * ld + g * D + c4));
-            float* d = halo + pos * LD + c4;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            *reinterpret_cast<float4*>(halo + pos * LD + c4) = v;
         }
     };
+    for (int f = tid; f < NQ * 8; f += NT) {
+        const int ql = f >> 3, c4 = (f & 7) * 4;
+        const int ly = ql / TX, lx = ql - ly * TX;
+        const int y = ty0 + ly, x = tx0 + lx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y < p.h && x < p.w) v = __ldg(reinterpret_cast<const float4*>(p.q + (size_t)(y * p.w + x) * p.ldq + g * D + c4));
+        *reinterpret_cast<float4*>(qs + ql * D + c4) = v;
+    }
+    {
+        const float4* src = reinterpret_cast<const float4*>(relv_t + (size_t)g * LTAPS * D);
+        for (int f = tid; f < LTAPS * 8; f += NT) reinterpret_cast<float4*>(rvs)[f] = __ldg(src + f);
+    }
     load_halo(p.k, p.ldk);
     __syncthreads();
 
-    // ---- phase 1: scores + softmax, taps on lanes; probabilities of all TY*TX queries parked in shared memory
-    float* prob = bk + LTAPS + 7;       // [TY*TX][PLD]
-    constexpr int PLD = 228;
-    const float invT = 1.f / p.T;
-#pragma unroll 1
-    for (int qi = 0; qi < QPW; ++qi) {
-        const int ql = warp * QPW + qi;
-        const int ly = ql / TX, lx = ql - ly * TX;
-        const int y = ty0 + ly, x = tx0 + lx;
-        if (y >= p.h || x >= p.w) continue;      // warp-uniform
-        float qv[D];
-        const float4* qp = reinterpret_cast<const float4*>(p.q + (size_t)(y * p.w + x) * p.ldq + g * D);
+    // ---- R pass: r[tap] = relative_emb_k(q)[tap] on the unscaled q (attention.py:327)
+    if (tid < 2 * LTAPS) {
+        const int half = tid / LTAPS, tap = tid - half * LTAPS;
+        float wk[D];
+        const float4* wp = reinterpret_cast<const float4*>(p.relk_w + ((size_t)g * LTAPS + tap) * D);
 #pragma unroll
         for (int c = 0; c < D / 4; ++c) {
-            const float4 t = __ldg(qp + c);
-            qv[4 * c] = t.x; qv[4 * c + 1] = t.y; qv[4 * c + 2] = t.z; qv[4 * c + 3] = t.w;
+            const float4 t = __ldg(wp + c);
+            wk[4 * c] = t.x; wk[4 * c + 1] = t.y; wk[4 * c + 2] = t.z; wk[4 * c + 3] = t.w;
         }
+        const float bias = __ldg(p.relk_b + g * LTAPS + tap);
+        const int slot = (tap / LW) * 16 + tap % LW;
+#pragma unroll 2
+        for (int qi = 0; qi < NQ / 2; ++qi) {
+            const int ql = half * (NQ / 2) + qi;
+            const float4* q4 = reinterpret_cast<const float4*>(qs + ql * D);
+            float r0 = bias, r1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c) {
+                const float4 t = q4[c];
+                r0 = fmaf(wk[4 * c], t.x, r0); r1 = fmaf(wk[4 * c + 1], t.y, r1);
+                r0 = fmaf(wk[4 * c + 2], t.z, r0); r1 = fmaf(wk[4 * c + 3], t.w, r1);
+            }
+            prob[ql * PLD + slot] = r0 + r1;
+        }
+    }
+    __syncthreads();
+
+    // ---- dot pass: s[tap] = (q . k[pos]) / T + r[tap]  in frame,  r[tap] - 1e8 outside
+    if (tid < LW * HWD) {
+        const int dy = tid / HWD, hx = tid - dy * HWD;
+        const float invT = 1.f / p.T;
+        const int xx = tx0 + hx - LR;
+        const bool xin = (xx >= 0 && xx < p.w);
+#pragma unroll 1
+        for (int ly = 0; ly < TY; ++ly) {
+            const int yy = ty0 + ly + dy - LR;
+            const bool inside = xin && yy >= 0 && yy < p.h;
+            float kv[D];
+            const float4* kp = reinterpret_cast<const float4*>(halo + ((ly + dy) * HWD + hx) * LD);
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c) {
+                const float4 t = kp[c];
+                kv[4 * c] = t.x; kv[4 * c + 1] = t.y; kv[4 * c + 2] = t.z; kv[4 * c + 3] = t.w;
+            }
+#pragma unroll
+            for (int lx = 0; lx < TX; ++lx) {
+                const int dx = hx - lx;
+                const float4* q4 = reinterpret_cast<const float4*>(qs + (ly * TX + lx) * D);
+                float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < D / 4; ++c) {
+                    const float4 t = q4[c];
+                    d0 = fmaf(kv[4 * c], t.x, d0); d1 = fmaf(kv[4 * c + 1], t.y, d1);
+                    d0 = fmaf(kv[4 * c + 2], t.z, d0); d1 = fmaf(kv[4 * c + 3], t.w, d1);
+                }
+                if (dx >= 0 && dx < LW) {
+                    float* sp = prob + (ly * TX + lx) * PLD + dy * 16 + dx;
+                    *sp += inside ? (d0 + d1) * invT : -1e8f;
+                }
+            }
+        }
+    }
+    __syncthreads();          // scores complete; the K halo is dead
+    load_halo(p.v, p.ldv);
+
+    // ---- softmax over the 225 taps of each query (padding slots excluded)
+    for (int ql = warp; ql < NQ; ql += NT / 32) {
+        float* pq = prob + ql * PLD;
         float sc[8];
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int wi = lane + 32 * j;
-            float s1 = -INFINITY;
-            if (wi < LTAPS) {
-                const int dy = wi / LW, dx = wi - dy * LW;       // 0..14
-                const int yy = y + dy - LR, xx = x + dx - LR;
-                const bool inside = (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w);
-                const float* kr = halo + ((ly + dy) * HWD + lx + dx) * LD;
-                const float* wr = wk + wi * LD;
-                float dot = 0.f, rel = bk[wi];
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    dot = fmaf(qv[c], kr[c], dot);
-                    rel = fmaf(wr[c], qv[c], rel);
-                }
-                s1 = inside ? fmaf(dot, invT, rel) : (rel - 1e8f);
-            }
-            sc[j] = s1;
-            mx = fmaxf(mx, s1);
+            const int i = lane + 32 * j;
+            const bool valid = i < PLD && (i & 15) != 15;
+            sc[j] = valid ? pq[i] : -INFINITY;
+            mx = fmaxf(mx, sc[j]);
         }
         mx = warp_max(mx);
         float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            sc[j] = (lane + 32 * j < LTAPS) ? expf(sc[j] - mx) : 0.f;
+            sc[j] = expf(sc[j] - mx);         // exp(-inf) = 0 for the padding slots
             sum += sc[j];
         }
         sum = warp_sum(sum);
         const float inv = 1.f / sum;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (lane + 32 * j < LTAPS) prob[ql * PLD + lane + 32 * j] = sc[j] * inv;
+        for (int j = 0; j < 8; ++j) {
+            const int i = lane + 32 * j;
+            if (i < PLD) pq[i] = sc[j] * inv;
+        }
     }
-    __syncthreads();          // every warp is done with the K halo
-    load_halo(p.v, p.ldv);
     __syncthreads();
 
-    // ---- phase 2: aggregate, channels on lanes
-    const float* rv = relv_t + (size_t)g * LTAPS * D + lane;
+    // ---- aggregate: o[c] = sum_tap p[tap] * (v[pos][c] + relative_emb_v[tap][c]), channels on lanes
+    {
+        const int ly = warp / (TX / 3), lx0 = (warp % (TX / 3)) * 3;
+        float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int qi = 0; qi < QPW; ++qi) {
-        const int ql = warp * QPW + qi;
-        const int ly = ql / TX, lx = ql - ly * TX;
-        const int y = ty0 + ly, x = tx0 + lx;
-        if (y >= p.h || x >= p.w) continue;     // warp-uniform
-        const float* pq = prob + ql * PLD;
-        float acc0 = 0.f, acc1 = 0.f;
         for (int dy = 0; dy < LW; ++dy) {
-            const float* vrow = halo + ((ly + dy) * HWD + lx) * LD + lane;   // zero outside the frame
+            const float* vrow = halo + ((ly + dy) * HWD + lx0) * LD + lane;   // zero outside the frame
+            float vv[LW + 2], rr[LW];
 #pragma unroll
-            for (int dx = 0; dx < LW; ++dx) {
-                const int wi = dy * LW + dx;
-                const float pv = pq[wi];
-                const float vv = vrow[dx * LD] + __ldg(rv + wi * D);
-                if (dx & 1) acc1 = fmaf(pv, vv, acc1); else acc0 = fmaf(pv, vv, acc0);
+            for (int j = 0; j < LW + 2; ++j) vv[j] = vrow[j * LD];
+#pragma unroll
+            for (int dx = 0; dx < LW; ++dx) rr[dx] = rvs[(dy * LW + dx) * D + lane];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float4* pp = reinterpret_cast<const float4*>(prob + (ly * TX + lx0 + i) * PLD + dy * 16);
+                const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2], p3 = pp[3];
+                const float pa[16] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w,
+                                      p2.x, p2.y, p2.z, p2.w, p3.x, p3.y, p3.z, p3.w};
+#pragma unroll
+                for (int dx = 0; dx < LW; ++dx) acc[i] = fmaf(pa[dx], vv[i + dx] + rr[dx], acc[i]);
             }
         }
-        p.out[(size_t)(y * p.w + x) * p.ldo + g * D + lane] = acc0 + acc1;
+        const int y = ty0 + ly;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int x = tx0 + lx0 + i;
+            if (y < p.h && x < p.w) p.out[(size_t)(y * p.w + x) * p.ldo + g * D + lane] = acc[i];
+        }
     }
 }
 
 static int launch_local_tile(const LocalArgs& a, const float* relv_t, cudaStream_t st) {
-    constexpr int TY = 8, TX = 8;
-    const size_t smem = sizeof(float) * (size_t)((TY + 14) * (TX + 14) * 33 + LTAPS * 33 + LTAPS + 8 + TY * TX * 228);
+    // 8 x 6 query tiles: 36 tiles x 8 heads = 288 CTAs on the 31 x 54 map = 1.95 waves of 148 SMs
+    constexpr int TY = 8, TX = 6;
+    const size_t smem = sizeof(float) * (size_t)((TY + 14) * (TX + 14) * 36 + TY * TX * 32 + TY * TX * LW * 16 + LTAPS * 32);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(local_attn_tile_kernel<TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -54,11 +54,10 @@ _TC_WS = {}
 
 
 def _tc_workspace(device):
-    """Per-device split-K scratch for the tensor-core conv: 16 KB of tile arrival counters (must start at zero; the
-    kernel re-arms them) followed by the partial tiles (64 MB covers 16 splits x 1674 x 512 fp32)."""
+    """Per-device scratch handed to the tensor-core conv (reserved by the C-ABI; currently unused by the kernel)."""
     ws = _TC_WS.get(device)
     if ws is None:
-        ws = _TC_WS[device] = torch.zeros(64 << 20, dtype=torch.uint8, device=device)
+        ws = _TC_WS[device] = torch.zeros(1 << 20, dtype=torch.uint8, device=device)
     return ws
 
 

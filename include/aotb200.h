@@ -26,6 +26,10 @@ const char* aotb_last_error_string(void);
 unsigned long long aotb_launch_count(void);
 /* Launch every kernel with programmatic dependent launch (prologues overlap the previous kernel's tail). */
 void aotb_set_pdl(int on);
+/* Tile policy of aotb_conv2d_nhwc_tc: 0 = wide (widest N tile dividing Cout, split-K clusters for small maps; default),
+ * 1 = narrow (N = 64 tiles unless a wider tile fills the GPU on its own).  A/B tuning knob, results are identical
+ * up to fp32 summation order. */
+int aotb_set_conv_tiling(int mode);
 
 /* nn.Conv2d (+ folded FrozenBatchNorm2d, + residual, + activation) as im2col-free implicit GEMM.
  * networks/encoders/resnet.py:34-54,140-157; networks/layers/normalization.py:30-43;
@@ -38,9 +42,9 @@ int aotb_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, con
 /* Same contract as aotb_conv2d_nhwc_f32 (dilation 1) on the tcgen05 tensor cores, fp32-faithful through split-fp16
  * operands: wh / wl are the weights pre-split as hi = fp16(w), lo = fp16(w - hi), laid out [Cout][KH*KW*Cin] (K-major,
  * K ordered (ky,kx,ci), zero-padded to a multiple of 64); activations are split on the fly.
- * Requires Cin % 4 == 0 and Cout % 64 == 0.  `workspace` (optional, caller-owned device memory) enables split-K for
- * few-tile deep-K layers: its first 16 KB are per-tile arrival counters (zero on first use, re-armed by the kernel),
- * the rest holds partial tiles [splits][M][Cout]; the last-arriving CTA of a tile sums them in split order. */
+ * Requires Cin % 4 == 0 and Cout % 64 == 0.  Few-tile deep-K layers run split-K: the 2 / 4 / 8 CTAs of one output
+ * tile form a thread-block cluster and sum their partial tiles over distributed shared memory in rank order
+ * (deterministic).  `workspace` / `workspace_bytes` are reserved (may be NULL / 0). */
 int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* wl, const float* bias, const float* res,
                         float* out, int B, int H, int W, int Cin, int ldin, int Cout, int ldout, int ldres,
                         int KH, int KW, int stride, int pad, int act, void* workspace, size_t workspace_bytes,

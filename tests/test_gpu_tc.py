@@ -142,12 +142,23 @@ def test_conv2d_tc(cfg):
     xg = x.permute(0, 2, 3, 1).contiguous().to(d)
     out = torch.full((B, ref.shape[2], ref.shape[3], Cout), float("nan"), device=d)
     rg = res.permute(0, 2, 3, 1).contiguous().to(d) if use_res else None
-    ops.conv2d_tc(xg, wh, wl, b.to(d), out, res=rg, KH=K, KW=K, stride=s, pad=p, act=act)
-    torch.cuda.synchronize()
-    err = (out.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item()
+    from aot_benchmark_b200._lib import lib
     scale = ref.abs().max().item()
-    # tensor-core fp32 accumulation over K up to 2304 terms: ~5e-6 relative (fp32 CUDA cores: ~1e-6)
-    assert err < 1e-5 * max(scale, 1.0) + 1e-5, f"err {err} scale {scale}"
+    try:
+        for mode in (1, 0):      # narrow tiles, then the default wide tiles + split-K clusters
+            assert lib().aotb_set_conv_tiling(mode) == 0
+            out.fill_(float("nan"))
+            ops.conv2d_tc(xg, wh, wl, b.to(d), out, res=rg, KH=K, KW=K, stride=s, pad=p, act=act)
+            torch.cuda.synchronize()
+            err = (out.permute(0, 3, 1, 2).cpu().double() - ref).abs().max().item()
+            # tensor-core fp32 accumulation over K up to 2304 terms: ~5e-6 relative (fp32 CUDA cores: ~1e-6)
+            assert err < 1e-5 * max(scale, 1.0) + 1e-5, f"tiling {mode}: err {err} scale {scale}"
+            # split-K sums in cluster-rank order: bit-identical from run to run
+            out_b = torch.full_like(out, float("nan"))
+            ops.conv2d_tc(xg, wh, wl, b.to(d), out_b, res=rg, KH=K, KW=K, stride=s, pad=p, act=act)
+            assert torch.equal(out, out_b)
+    finally:
+        lib().aotb_set_conv_tiling(0)
     # and the fp32 CUDA-core kernel on the same problem agrees
     out2 = torch.empty_like(out)
     old = ops.CONV_IMPL
