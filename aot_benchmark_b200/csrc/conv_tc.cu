@@ -42,6 +42,8 @@ struct ConvTcArgs {
     int act;
     int splits;          // split-K: the `splits` CTAs (blockIdx.z) of one output tile form a thread-block cluster; CTA z
                          // handles chunks [z*per, (z+1)*per) and the partial tiles are summed over distributed smem
+    int spin;            // 1: mbarrier waits without the suspend hint
+    long long* prof;     // diagnostic: 8 clock64 stamps per CTA (see aotb_set_conv_tiling), or null
 };
 
 static int g_conv_tiling = 0;      // aotb_set_conv_tiling
@@ -89,6 +91,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+    auto W = [&](uint64_t* bar, uint32_t parity) {
+        if (a.spin) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity);
+    };
+    long long* prof = a.prof ? a.prof + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+    auto stamp = [&](int slot) { if (prof) prof[slot] = clock64(); };
+    if (tid == 0) stamp(0);
     pdl_trigger();      // the next kernel may start its prologue; it waits for this grid before reading our output
 
     if (tid == 0) {
@@ -117,6 +125,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (tid == 0) stamp(1);
     pdl_wait();         // activations / residual below were written by earlier kernels
     const int cpt = (a.Cin % 64 == 0) ? (a.Cin >> 6) : 0;  // 64-wide chunks per filter tap (0: general Cin % 4 path)
     const int per = (a.nchunks + a.splits - 1) / a.splits;
@@ -156,7 +165,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
         const uint32_t soff = rsub * 128 + (((q >> 1) ^ (rsub & 7)) << 4) + ((q & 1) << 3);
         auto store_chunk = [&](int it, const float4* v) {
             const int s = it % STAGES;
-            if (it >= STAGES) mbar_wait(&s_free[s], ((it / STAGES) - 1) & 1);
+            if (it >= STAGES) W(&s_free[s], ((it / STAGES) - 1) & 1);
             uint8_t* Ah = smem + s * SM::STAGE_BYTES + soff;
             uint8_t* Al = Ah + SM::A_BYTES;
 #pragma unroll
@@ -172,6 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
             }
             fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&a_full[s]);
+            if (tid == 0 && it == 0) stamp(2);
         };
         // three chunks of global loads in flight per thread (register ring), so the ~L2 latency of a chunk is
         // covered by the convert+store work of the two chunks before it
@@ -192,9 +202,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
         }
         // ======================= epilogue (warps 0-3: columns [0, BN/2), warps 4-7: [BN/2, BN)) =======================
         if (nloc > 0) {
-            mbar_wait(acc_full, 0);
+            W(acc_full, 0);
             tc_fence_after();
         }
+        if (tid == 0) stamp(5);
         const int wq = warp & 3;
         const int m = m0 + wq * 32 + lane;
         const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
@@ -232,7 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
             tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
             for (int it = 0; it < nloc; ++it) {
                 const int s = it % STAGES;
-                if (it >= STAGES) mbar_wait(&s_free[s], ((it / STAGES) - 1) & 1);
+                if (it >= STAGES) W(&s_free[s], ((it / STAGES) - 1) & 1);
                 uint8_t* Bh = smem + s * SM::STAGE_BYTES + 2 * SM::A_BYTES;
                 mbar_arrive_expect_tx(&b_full[s], 2 * SM::B_BYTES);
                 tma_load_2d(Bh, &tmWh, &b_full[s], (kbeg + it) * 64, n0);
@@ -251,9 +262,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
             for (int kc = 0; kc < nloc; ++kc) {
                 const int s = kc % STAGES;
                 const uint32_t ph = (kc / STAGES) & 1;
-                mbar_wait(&a_full[s], ph);
-                mbar_wait(&b_full[s], ph);
+                W(&a_full[s], ph);
+                W(&b_full[s], ph);
                 tc_fence_after();
+                if (kc == 0) stamp(3);
                 const uint64_t so = (uint64_t)(s * (SM::STAGE_BYTES >> 4));
                 const uint64_t ah = dAh0 + so, al = dAl0 + so, bh = dBh0 + so, bl = dBl0 + so;
                 mma_ss(tmem, ah, bh, IDESC, kc ? 1u : 0u);
@@ -268,8 +280,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
                 mma_commit(&s_free[s]);
             }
             if (nloc > 0) mma_commit(acc_full);
+            stamp(4);
         }
     }
+    if (tid == 0) stamp(6);
     if (a.splits > 1) {
         // split-K reduction across the cluster: CTA z owns rows [z*128/S, (z+1)*128/S) of the tile, reads that slice of
         // every peer's staging buffer through distributed shared memory in rank order (so the sum is deterministic),
@@ -299,6 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    if (tid == 0) stamp(7);
     if (warp == 9) tmem_dealloc<BN>(tmem);
 }
 
@@ -351,7 +366,7 @@ static int launch_conv_tc(const CUtensorMap& th, const CUtensorMap& tl, const Co
 using namespace aotb;
 
 extern "C" int aotb_set_conv_tiling(int mode) {
-    AOTB_REQUIRE(mode == 0 || mode == 1, "aotb_set_conv_tiling: mode must be 0 (wide) or 1 (narrow)");
+    AOTB_REQUIRE(mode >= 0 && mode < 8, "aotb_set_conv_tiling: mode is a 3-bit mask");
     tc::g_conv_tiling = mode;
     return AOTB_OK;
 }
@@ -383,7 +398,7 @@ extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* 
     // small maps from split-K clusters of 2 / 4 / 8 CTAs (>= 2 chunks per CTA, about one wave in total).
     const int mt = cdiv(a.M, 128);
     int BN;
-    if (tc::g_conv_tiling == 0) {
+    if ((tc::g_conv_tiling & 1) == 0) {
         BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
     } else {          // "narrow": the widest BN that still fills ~a wave on its own, else 64
         BN = 64;
@@ -397,7 +412,13 @@ extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* 
         while (sp > 1 && (ctas * sp > 160 || a.nchunks / sp < 2)) sp >>= 1;
         a.splits = sp;
     }
-    (void)workspace; (void)workspace_bytes;      // reserved (the split-K reduction runs over distributed shared memory)
+    a.spin = (tc::g_conv_tiling & 2) ? 1 : 0;
+    a.prof = nullptr;
+    if (tc::g_conv_tiling & 4) {      // diagnostic stamps go to the caller's workspace
+        const size_t need = (size_t)ctas * a.splits * 8 * sizeof(long long);
+        AOTB_REQUIRE(workspace && workspace_bytes >= need, "aotb_conv2d_nhwc_tc: profile mode needs %zu workspace bytes", need);
+        a.prof = (long long*)workspace;
+    }
     CUtensorMap th, tl;
     int rc;
     if ((rc = tc::make_tmap_weights(&th, wh, K, Cout, BN)) != AOTB_OK) return rc;

@@ -26,9 +26,12 @@ const char* aotb_last_error_string(void);
 unsigned long long aotb_launch_count(void);
 /* Launch every kernel with programmatic dependent launch (prologues overlap the previous kernel's tail). */
 void aotb_set_pdl(int on);
-/* Tile policy of aotb_conv2d_nhwc_tc: 0 = wide (widest N tile dividing Cout, split-K clusters for small maps; default),
- * 1 = narrow (N = 64 tiles unless a wider tile fills the GPU on its own).  A/B tuning knob, results are identical
- * up to fp32 summation order. */
+/* Tuning / diagnostic mask of aotb_conv2d_nhwc_tc (default 0); results are identical up to fp32 summation order.
+ *   bit 0: narrow tiles (N = 64 unless a wider tile fills the GPU on its own) instead of the widest N dividing Cout
+ *          with split-K clusters for small maps;
+ *   bit 1: mbarrier waits spin without the suspend hint;
+ *   bit 2: every CTA writes 8 clock64 stamps (start, prologue done, first A stage stored, first stage consumable,
+ *          last MMA issued, accumulator complete, epilogue stored, exit) to `workspace` as long long[ctas][8]. */
 int aotb_set_conv_tiling(int mode);
 
 /* nn.Conv2d (+ folded FrozenBatchNorm2d, + residual, + activation) as im2col-free implicit GEMM.
@@ -44,7 +47,8 @@ int aotb_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, con
  * K ordered (ky,kx,ci), zero-padded to a multiple of 64); activations are split on the fly.
  * Requires Cin % 4 == 0 and Cout % 64 == 0.  Few-tile deep-K layers run split-K: the 2 / 4 / 8 CTAs of one output
  * tile form a thread-block cluster and sum their partial tiles over distributed shared memory in rank order
- * (deterministic).  `workspace` / `workspace_bytes` are reserved (may be NULL / 0). */
+ * (deterministic).  `workspace` / `workspace_bytes` are only used by the diagnostic mode of aotb_set_conv_tiling
+ * (may be NULL / 0 otherwise). */
 int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* wl, const float* bias, const float* res,
                         float* out, int B, int H, int W, int Cin, int ldin, int Cout, int ldout, int ldres,
                         int KH, int KW, int stride, int pad, int act, void* workspace, size_t workspace_bytes,
