@@ -65,6 +65,19 @@ __device__ __forceinline__ void conv_finish(const ConvTcArgs& a, float4 o, int n
     *reinterpret_cast<float4*>(orow) = o;
 }
 
+// Sum of the same staging-buffer float4 over the S CTAs of the cluster, in rank order.  All S remote loads are issued
+// before the first add so their latencies overlap (a load-add-load-add chain costs S round trips: 6 us at S = 8).
+template <int S>
+__device__ __forceinline__ float4 cluster_sum(uint32_t local_saddr) {
+    float4 v[S];
+#pragma unroll
+    for (int z = 0; z < S; ++z) v[z] = dsmem_ld_f4(dsmem_addr(local_saddr, (uint32_t)z));
+    float4 acc = v[0];
+#pragma unroll
+    for (int z = 1; z < S; ++z) { acc.x += v[z].x; acc.y += v[z].y; acc.z += v[z].z; acc.w += v[z].w; }
+    return acc;
+}
+
 template <int BN, int STAGES>
 struct ConvSmem {
     static constexpr int A_BYTES = 128 * 128;          // one 128 x 64 half tile
@@ -207,7 +220,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
         }
         if (tid == 0) stamp(5);
         const int wq = warp & 3;
-        const int m = m0 + wq * 32 + lane;
         const uint32_t trow = tmem + ((uint32_t)(wq * 32) << 16);
         const int cbeg = (warp >> 2) * (BN / 2);
 #pragma unroll 1
@@ -220,22 +232,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
-            if (a.splits > 1) {
-                // partial tile -> this CTA's staging buffer (the operand stages are dead: every MMA has completed).
-                // Row stride BN + 4 floats: an odd number of 16-byte units, so the 32 rows of a warp do not collide.
-                float* srow = reinterpret_cast<float*>(smem) + (wq * 32 + lane) * SM::STG_LD + c;
+            // accumulator tile -> this CTA's staging buffer (the operand stages are dead: every MMA has completed), so
+            // the global stores below run along rows.  Row stride BN + 4 floats: an odd number of 16-byte units, so the
+            // 32 rows of a warp do not collide.  (Storing straight from the TMEM layout -- one row per lane -- costs
+            // 32 half-filled sectors per instruction: 9 us for a 128 x 256 tile against < 1 us this way.)
+            float* srow = reinterpret_cast<float*>(smem) + (wq * 32 + lane) * SM::STG_LD + c;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(srow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            } else if (m < a.M) {
-                float* orow = a.out + (size_t)m * a.ldout + n0 + c;
-                const float* rrow = a.res ? a.res + (size_t)m * a.ldres + n0 + c : nullptr;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    conv_finish(a, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                               __uint_as_float(r[j + 3])), n0 + c + j, orow + j, rrow ? rrow + j : nullptr);
-            }
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(srow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                   __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         }
     } else if (warp == 8) {
         // ======================= weight TMA producer =======================
@@ -284,30 +289,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
         }
     }
     if (tid == 0) stamp(6);
-    if (a.splits > 1) {
-        // split-K reduction across the cluster: CTA z owns rows [z*128/S, (z+1)*128/S) of the tile, reads that slice of
-        // every peer's staging buffer through distributed shared memory in rank order (so the sum is deterministic),
-        // applies the epilogue and writes coalesced rows.  No global-memory partials, no second kernel.
-        __syncwarp();
-        cluster_sync_all();
-        if (warp < 8) {
-            const int S = a.splits, rows = 128 / S, r0 = blockIdx.z * rows;
-            constexpr int C4 = BN / 4;
-            const uint32_t sbase = smem_u32(smem);
-            for (int e = tid; e < rows * C4; e += 256) {
-                const int row = r0 + e / C4, c = (e % C4) * 4;
-                const uint32_t off = sbase + (uint32_t)(row * SM::STG_LD + c) * 4u;
-                float4 acc = dsmem_ld_f4(dsmem_addr(off, 0));
-                for (int z = 1; z < S; ++z) {
-                    const float4 v = dsmem_ld_f4(dsmem_addr(off, (uint32_t)z));
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                }
-                const int m = m0 + row;
-                if (m < a.M)
-                    conv_finish(a, acc, n0 + c, a.out + (size_t)m * a.ldout + n0 + c,
-                                a.res ? a.res + (size_t)m * a.ldres + n0 + c : nullptr);
-            }
+    // Finish: CTA z of a split-K cluster owns rows [z*128/S, (z+1)*128/S) of the tile and reads that slice of every
+    // peer's staging buffer through distributed shared memory, summing in rank order (deterministic); without split-K
+    // (S = 1) it is the CTA's own buffer.  Then bias / residual / activation and coalesced row stores.  No global
+    // partials, no second kernel.
+    __syncwarp();
+    if (a.splits > 1) cluster_sync_all(); else __syncthreads();
+    if (warp < 8) {
+        const int S = a.splits, rows = 128 / S, r0 = (S > 1 ? blockIdx.z : 0) * rows;
+        constexpr int C4 = BN / 4;
+        const uint32_t sbase = smem_u32(smem);
+#pragma unroll 2
+        for (int e = tid; e < rows * C4; e += 256) {
+            const int row = r0 + e / C4, c = (e % C4) * 4;
+            const uint32_t off = sbase + (uint32_t)(row * SM::STG_LD + c) * 4u;
+            float4 acc;
+            if (S == 1) acc = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) + row * SM::STG_LD + c);
+            else if (S == 2) acc = cluster_sum<2>(off);
+            else if (S == 4) acc = cluster_sum<4>(off);
+            else acc = cluster_sum<8>(off);
+            const int m = m0 + row;
+            if (m < a.M)
+                conv_finish(a, acc, n0 + c, a.out + (size_t)m * a.ldout + n0 + c,
+                            a.res ? a.res + (size_t)m * a.ldres + n0 + c : nullptr);
         }
+    }
+    if (a.splits > 1) {
         __syncwarp();
         cluster_sync_all();      // nobody leaves (and frees its shared memory) while a peer may still read it
     }

@@ -172,10 +172,9 @@ __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_saddr, uint32_t ct
 }
 __device__ __forceinline__ float4 dsmem_ld_f4(uint32_t cluster_saddr) {
     float4 v;
-    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"     // volatile: stays after the cluster barrier
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "r"(cluster_saddr)
-                 : "memory");
+                 : "r"(cluster_saddr));
     return v;
 }
 
