@@ -43,39 +43,57 @@ struct ConvTcArgs {
     int splits;          // split-K: the `splits` CTAs (blockIdx.z) of one output tile form a thread-block cluster; CTA z
                          // handles chunks [z*per, (z+1)*per) and the partial tiles are summed over distributed smem
     int spin;            // 1: mbarrier waits without the suspend hint
-    long long* prof;     // diagnostic: 8 clock64 stamps per CTA (see aotb_set_conv_tiling), or null
+    long long* prof;     // diagnostic: 12 clock64 stamps per CTA (see aotb_set_conv_tiling), or null
 };
 
 static int g_conv_tiling = 0;      // aotb_set_conv_tiling
 
 struct RowInfo { int pix_base, iy0, ix0, valid; };
 
-// bias + residual + activation + store of four consecutive output channels starting at n
-__device__ __forceinline__ void conv_finish(const ConvTcArgs& a, float4 o, int n, float* orow, const float* rrow) {
-    if (a.bias) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + n));
-        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-    }
-    if (rrow) {
-        const float4 rr = *reinterpret_cast<const float4*>(rrow);
-        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-    }
-    o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act);
-    o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
-    *reinterpret_cast<float4*>(orow) = o;
-}
-
-// Sum of the same staging-buffer float4 over the S CTAs of the cluster, in rank order.  All S remote loads are issued
-// before the first add so their latencies overlap (a load-add-load-add chain costs S round trips: 6 us at S = 8).
-template <int S>
-__device__ __forceinline__ float4 cluster_sum(uint32_t local_saddr) {
-    float4 v[S];
+// Finish of one output tile by the 256 epilogue threads.  The staging tile is [128][BN + 4] fp32; with split-K the S
+// CTAs of the cluster each own 128 / S rows and sum that slice of every peer's staging buffer in rank order.  A thread
+// keeps one 4-channel column (its bias is loaded once) and walks rows; NB rows are processed per batch with every load
+// of the batch (S remote tiles + residual) issued before the first use -- a load-use-load chain costs one DSMEM / L2
+// round trip per row and was 6 us per tile.
+template <int BN, int S, int NB>
+__device__ __forceinline__ void conv_finish_tile(const ConvTcArgs& a, const uint8_t* smem, int tid, int m0, int n0, int zrank) {
+    constexpr int LD = BN + 4, C4 = BN / 4, RSTEP = 256 / C4, ROWS = 128 / S, ITERS = ROWS / RSTEP;
+    constexpr int B = NB < ITERS ? NB : ITERS;
+    static_assert(ITERS >= 1 && ITERS % B == 0, "finish tiling");
+    const int c = (tid % C4) * 4, n = n0 + c;
+    const int r0 = zrank * ROWS + tid / C4;
+    const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* lbase = reinterpret_cast<const float*>(smem) + r0 * LD + c;
+    const uint32_t sbase = smem_u32(lbase);
+#pragma unroll 1
+    for (int i0 = 0; i0 < ITERS; i0 += B) {
+        float4 v[B][S], rs[B];
 #pragma unroll
-    for (int z = 0; z < S; ++z) v[z] = dsmem_ld_f4(dsmem_addr(local_saddr, (uint32_t)z));
-    float4 acc = v[0];
+        for (int b = 0; b < B; ++b) {
+            const int ro = (i0 + b) * RSTEP;
+            if (S == 1) {
+                v[b][0] = *reinterpret_cast<const float4*>(lbase + ro * LD);
+            } else {
 #pragma unroll
-    for (int z = 1; z < S; ++z) { acc.x += v[z].x; acc.y += v[z].y; acc.z += v[z].z; acc.w += v[z].w; }
-    return acc;
+                for (int z = 0; z < S; ++z) v[b][z] = dsmem_ld_f4(dsmem_addr(sbase + (uint32_t)(ro * LD) * 4u, (uint32_t)z));
+            }
+            const int m = m0 + r0 + ro;
+            rs[b] = (a.res && m < a.M) ? *reinterpret_cast<const float4*>(a.res + (size_t)m * a.ldres + n)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            float4 o = v[b][0];
+#pragma unroll
+            for (int z = 1; z < S; ++z) { o.x += v[b][z].x; o.y += v[b][z].y; o.z += v[b][z].z; o.w += v[b][z].w; }
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            o.x += rs[b].x; o.y += rs[b].y; o.z += rs[b].z; o.w += rs[b].w;
+            o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act);
+            o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
+            const int m = m0 + r0 + (i0 + b) * RSTEP;
+            if (m < a.M) *reinterpret_cast<float4*>(a.out + (size_t)m * a.ldout + n) = o;
+        }
+    }
 }
 
 template <int BN, int STAGES>
@@ -107,7 +125,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     auto W = [&](uint64_t* bar, uint32_t parity) {
         if (a.spin) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity);
     };
-    long long* prof = a.prof ? a.prof + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+    long long* prof = a.prof ? a.prof + 12 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
     auto stamp = [&](int slot) { if (prof) prof[slot] = clock64(); };
     if (tid == 0) stamp(0);
     pdl_trigger();      // the next kernel may start its prologue; it waits for this grid before reading our output
@@ -295,25 +313,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     // partials, no second kernel.
     __syncwarp();
     if (a.splits > 1) cluster_sync_all(); else __syncthreads();
+    if (tid == 0) stamp(8);
     if (warp < 8) {
-        const int S = a.splits, rows = 128 / S, r0 = (S > 1 ? blockIdx.z : 0) * rows;
-        constexpr int C4 = BN / 4;
-        const uint32_t sbase = smem_u32(smem);
-#pragma unroll 2
-        for (int e = tid; e < rows * C4; e += 256) {
-            const int row = r0 + e / C4, c = (e % C4) * 4;
-            const uint32_t off = sbase + (uint32_t)(row * SM::STG_LD + c) * 4u;
-            float4 acc;
-            if (S == 1) acc = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) + row * SM::STG_LD + c);
-            else if (S == 2) acc = cluster_sum<2>(off);
-            else if (S == 4) acc = cluster_sum<4>(off);
-            else acc = cluster_sum<8>(off);
-            const int m = m0 + row;
-            if (m < a.M)
-                conv_finish(a, acc, n0 + c, a.out + (size_t)m * a.ldout + n0 + c,
-                            a.res ? a.res + (size_t)m * a.ldres + n0 + c : nullptr);
-        }
+        const int zr = a.splits > 1 ? (int)blockIdx.z : 0;
+        if (a.splits == 1) conv_finish_tile<BN, 1, 8>(a, smem, tid, m0, n0, zr);
+        else if (a.splits == 2) conv_finish_tile<BN, 2, 4>(a, smem, tid, m0, n0, zr);
+        else if (a.splits == 4) conv_finish_tile<BN, 4, 2>(a, smem, tid, m0, n0, zr);
+        else conv_finish_tile<BN, 8, 2>(a, smem, tid, m0, n0, zr);
     }
+    if (tid == 0) stamp(9);
     if (a.splits > 1) {
         __syncwarp();
         cluster_sync_all();      // nobody leaves (and frees its shared memory) while a peer may still read it
@@ -422,7 +430,7 @@ extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* 
     a.spin = (tc::g_conv_tiling & 2) ? 1 : 0;
     a.prof = nullptr;
     if (tc::g_conv_tiling & 4) {      // diagnostic stamps go to the caller's workspace
-        const size_t need = (size_t)ctas * a.splits * 8 * sizeof(long long);
+        const size_t need = (size_t)ctas * a.splits * 12 * sizeof(long long);
         AOTB_REQUIRE(workspace && workspace_bytes >= need, "aotb_conv2d_nhwc_tc: profile mode needs %zu workspace bytes", need);
         a.prof = (long long*)workspace;
     }

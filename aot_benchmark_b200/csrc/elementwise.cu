@@ -99,6 +99,57 @@ __global__ void dwconv_kernel(const float* __restrict__ in, const float* __restr
     }
 }
 
+// Stride-1, dilation-1 K x K depthwise conv (the 5x5 of the LSTT / GPM feed-forward): one thread = 4 neighbouring
+// output pixels x 4 channels.  The K+3 inputs of a filter row and its K weights are loaded once and shared by the 4
+// outputs (K*(K+3) + K*K loads per 4*K*K taps instead of 2 per tap -- the generic kernel above is L1-bandwidth bound).
+template <int K>
+__global__ void dwconv_row4_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                   const float* __restrict__ bias, float* __restrict__ out, int B, int H, int W, int C,
+                                   int ldin, int ldout, int pad, int act) {
+    pdl_sync();
+    const int C4 = C >> 2, Ho = H + 2 * pad - K + 1, Wo = W + 2 * pad - K + 1, XB = (Wo + 3) >> 2;
+    const size_t total = (size_t)B * Ho * XB * C4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (i % C4) * 4;
+        size_t t = i / C4;
+        const int ox0 = (t % XB) * 4; t /= XB;
+        const int oy = t % Ho;
+        const int b = t / Ho;
+        float4 acc[4];
+        const float4 b4 = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] = b4;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const int iy = oy - pad + ky;
+            if (iy < 0 || iy >= H) continue;
+            float4 v[K + 3], ww[K];
+#pragma unroll
+            for (int j = 0; j < K + 3; ++j) {
+                const int ix = ox0 - pad + j;
+                v[j] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + iy) * W + ix) * ldin + c))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) ww[kx] = __ldg(reinterpret_cast<const float4*>(w + (size_t)(ky * K + kx) * C + c));
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {        // same (ky, kx) order per output as the generic kernel
+                    acc[o].x = fmaf(v[o + kx].x, ww[kx].x, acc[o].x); acc[o].y = fmaf(v[o + kx].y, ww[kx].y, acc[o].y);
+                    acc[o].z = fmaf(v[o + kx].z, ww[kx].z, acc[o].z); acc[o].w = fmaf(v[o + kx].w, ww[kx].w, acc[o].w);
+                }
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            if (ox0 + o >= Wo) break;
+            float4 r = acc[o];
+            r.x = apply_act(r.x, act); r.y = apply_act(r.y, act); r.z = apply_act(r.z, act); r.w = apply_act(r.w, act);
+            *reinterpret_cast<float4*>(out + (((size_t)b * Ho + oy) * Wo + ox0 + o) * ldout + c) = r;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- bilinear resize (NHWC, C%4==0)
 // PyTorch semantics (aten upsample_bilinear2d): align_corners -> src = dst*(in-1)/(out-1);
 // otherwise src = max((dst+0.5)*in/out-0.5, 0).
@@ -221,6 +272,12 @@ extern "C" int aotb_dwconv_nhwc_f32(const float* in, const float* w, const float
     AOTB_REQUIRE(C % 4 == 0 && ldin % 4 == 0 && ldout % 4 == 0, "aotb_dwconv_nhwc_f32: channels must be %%4");
     const int Ho = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
     const int Wo = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+    if (KH == 5 && KW == 5 && stride == 1 && dil == 1) {
+        const size_t tot4 = (size_t)B * Ho * ((Wo + 3) / 4) * (C / 4);
+        launch(dwconv_row4_kernel<5>, dim3(grid_for(tot4, 128)), dim3(128), 0, (cudaStream_t)stream, in, w, bias, out, B, H, W,
+               C, ldin, ldout, pad, act);
+        return check_launch("aotb_dwconv_nhwc_f32");
+    }
     const size_t total = (size_t)B * Ho * Wo * (C / 4);
     launch(dwconv_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, in, w, bias, out, B, H, W, C, ldin, ldout,
                                                                          Ho, Wo, KH, KW, stride, pad, dil, act);

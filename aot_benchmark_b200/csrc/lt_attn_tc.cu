@@ -4,15 +4,20 @@
 // Reference computation: MultiheadAttention.forward(use_linear=False), networks/layers/attention.py:82-117,
 // called at networks/layers/transformer.py:346 (long-term) and :324 (self-attention, Tk = N).
 //
-// Design (one CTA = 256 queries x 1 head x one KV split, 1 CTA / SM, 320 threads):
-//   warp 8      TMA producer: Q tiles once, then a 3-stage ring of K/V tiles (128 keys) via
+// Design (one CTA = 256 queries x 1 head x one KV split, 1 CTA / SM, 576 threads):
+//   warp 16     TMA producer: Q tiles once, then a 3-stage ring of K/V tiles (128 keys) via
 //               cp.async.bulk.tensor + mbarrier complete_tx
-//   warp 9      tcgen05.mma issuer (one elected thread): S_i = Q_i K_j^T into TMEM, later O_i += P_i V_j
-//   warps 0-3   softmax warpgroup 0 (query rows   0..127): one thread = one row; tcgen05.ld S -> row max /
-//   warps 4-7   softmax warpgroup 1 (query rows 128..255)  ex2 / row sum in registers -> P back into TMEM
-//               (aliasing S) as the A operand of the PV MMA; the two groups ping-pong so MUFU and the
-//               tensor pipe overlap (issue order PV_0, S_0', PV_1, S_1').
-//   TMEM        S_0 | S_1 (128 fp32 columns each; P_hi aliases the first 64) | O_0 | O_1 | Plo_0 | Plo_1 (64 each)
+//   warp 17     tcgen05.mma issuer (one elected thread): S_i = Q_i K_j^T into TMEM, later O_i += P_i V_j
+//   warps 0-7   softmax group 0 (query rows   0..127): TWO threads per row (warps w and w+4 share the TMEM lanes of
+//   warps 8-15  softmax group 1 (query rows 128..255)  rows 32(w%4)..+31 and take 64 key columns each): tcgen05.ld S ->
+//               half-row max, exchanged through shared memory -> ex2 / partial row sum in registers -> P back into
+//               TMEM as the A operand of the PV MMA.  Four softmax warps per scheduler (it was one row per thread and
+//               two warps per scheduler: with one group waiting on its MMAs a scheduler had a single warp to issue
+//               from and the MUFU / TMEM latencies were exposed).  The two groups ping-pong so MUFU and the tensor
+//               pipe overlap (issue order PV_0, S_0', PV_1, S_1').
+//   TMEM        S_0 | S_1 (128 fp32 columns each) | O_0 | O_1 | Plo_0 | Plo_1 (64 each).  P_hi of the keys a thread owns
+//               overwrites the first half of that thread's own S columns: keys [0,64) -> columns [0,32),
+//               keys [64,128) -> columns [64,96).
 //
 // Precision ("fp16x2"): every fp32 operand x is carried as hi = fp16(x), lo = fp16(x - hi); rows of the
 // packed operands are [hi(32) | lo(32)] halfs = 128 bytes (the same bytes as fp32, one TMA swizzle atom).
@@ -27,7 +32,7 @@
 namespace aotb {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, STAGES = 3, NTHREADS = 320;
+constexpr int BM = 128, BN = 128, STAGES = 3, NTHREADS = 576, TMA_WARP = 16, MMA_WARP = 17;
 constexpr int TILE_BYTES = BN * 128;  // 128 rows x 128 B
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -79,6 +84,8 @@ struct __align__(8) Barriers {
     uint64_t p_full[2];
     uint64_t o_final[2];
     uint32_t tmem_base;
+    float xmax[2][2][2][BM];    // [tile parity][group][half][row]: half-row maxima
+    float xsum[2][2][BM];       // [group][half][row]: half-row sums (epilogue)
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
@@ -123,10 +130,10 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (tid == 0) {
         mbar_init(&B->q_full, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&B->kv_full[s], 1); mbar_init(&B->kv_free[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&B->s_full[i], 1); mbar_init(&B->p_full[i], BM); mbar_init(&B->o_final[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&B->s_full[i], 1); mbar_init(&B->p_full[i], 2 * BM); mbar_init(&B->o_final[i], 1); }
         fence_mbar_init();
     }
-    if (warp == 9) tmem_alloc<512>(&B->tmem_base);
+    if (warp == MMA_WARP) tmem_alloc<512>(&B->tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -139,7 +146,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     int T = tiles_total - tb;
     T = T < 0 ? 0 : (T > per ? per : T);
 
-    if (warp == 8) {
+    if (warp == TMA_WARP) {
         // ======================= TMA producer =======================
         if (elect_one() && T > 0) {
             tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -154,7 +161,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 tma_load_3d(sV + s * TILE_BYTES, &tmV, &B->kv_full[s], 0, (tb + j) * BN, h);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == MMA_WARP) {
         // ======================= MMA issuer =======================
         if (elect_one() && T > 0) {
             constexpr uint32_t IDESC_S = idesc_f16(128, 128, 0, 0);
@@ -182,7 +189,8 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 const uint32_t d = tmem + 256 + i * 64;
                 const uint32_t p = tmem + i * 128;
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) mma_ts(d, p + 8 * kk, v + 128 * kk, IDESC_O, (kk > 0) ? 1u : acc);
+                for (int kk = 0; kk < 8; ++kk)       // P_hi: keys [0,64) at columns [0,32), keys [64,128) at [64,96)
+                    mma_ts(d, p + 8 * kk + (kk >= 4 ? 32 : 0), v + 128 * kk, IDESC_O, (kk > 0) ? 1u : acc);
                 if (EXACT) {
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) mma_ts(d, tmem + 384 + i * 64 + 8 * kk, v + 128 * kk, IDESC_O, 1);
@@ -211,75 +219,81 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 }
             }
         }
-    } else if (warp < 8) {
-        // ======================= softmax warpgroups =======================
-        const int wg = warp >> 2, wq = warp & 3;
+    } else {
+        // ======================= softmax groups =======================
+        const int wg = warp >> 3, half = (warp >> 2) & 1, wq = warp & 3;
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        const uint32_t tS = tmem + lane_addr + wg * 128;
+        const uint32_t tS = tmem + lane_addr + wg * 128 + half * 64;      // this thread's 64 score columns
         const uint32_t tO = tmem + lane_addr + 256 + wg * 64;
+        const uint32_t tPl = tmem + lane_addr + 384 + wg * 64 + half * 32;
         const int q = q0 + wg * BM + row;
         const bool dump = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && wg == 0;
-        float m_used = -INFINITY, l = 0.f;
+        float m_used = -INFINITY, l0 = 0.f, l1 = 0.f;
 
         for (int j = 0; j < T; ++j) {
             mbar_wait(&B->s_full[wg], j & 1);
             tc_fence_after();
-            const int key0 = (tb + j) * BN;
-            const bool tail = key0 + BN > Tk;
-            // ---- pass 1: row max.  All four tcgen05.ld of the 128-key row are in flight together (one exposed latency);
-            // the values are dropped again so that pass 2 can run in a 64-register window.
+            const int key0 = (tb + j) * BN + half * 64;
+            const bool tail = key0 + 64 > Tk;
+            // ---- pass 1: half-row max (both tcgen05.ld in flight together); the values are dropped again so that
+            // pass 2 runs in a small register window.
             float mt = -INFINITY;
             {
-                uint32_t sr[128];
+                uint32_t sr[64];
                 tmem_ld32(tS + 0, sr);
                 tmem_ld32(tS + 32, sr + 32);
-                tmem_ld32(tS + 64, sr + 64);
-                tmem_ld32(tS + 96, sr + 96);
                 tmem_wait_ld();
                 if (dump && j == 0) {
 #pragma unroll
-                    for (int k = 0; k < 128; ++k) a.dbg[row * 128 + k] = __uint_as_float(sr[k]);
+                    for (int k = 0; k < 64; ++k) a.dbg[row * 128 + half * 64 + k] = __uint_as_float(sr[k]);
                 }
                 if (tail) {                          // warp-uniform: only the last key tile of the bank is ragged
 #pragma unroll
-                    for (int k = 0; k < 128; ++k)
+                    for (int k = 0; k < 64; ++k)
                         if (key0 + k >= Tk) sr[k] = __float_as_uint(-INFINITY);
                 }
+                float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-                for (int k = 0; k < 128; ++k) mt = fmaxf(mt, __uint_as_float(sr[k]));
+                for (int k = 0; k < 64; k += 2) {
+                    m0 = fmaxf(m0, __uint_as_float(sr[k]));
+                    m1 = fmaxf(m1, __uint_as_float(sr[k + 1]));
+                }
+                mt = fmaxf(m0, m1);
             }
+            B->xmax[j & 1][wg][half][row] = mt;
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + wg) : "memory");       // the 8 warps of this group
+            mt = fmaxf(mt, B->xmax[j & 1][wg][half ^ 1][row]);
             const float m_new = fmaxf(m_used, mt);
             const bool grow = (m_new > m_used) && (j > 0);
             if (__any_sync(0xffffffffu, grow)) {
-                // rescale the running output / sum of this warp's rows (O_i is quiescent here: every MMA issued
-                // before S_i(j) has completed, PV_i(j) is not issued until we arrive on p_full)
+                // rescale the running output of this warp's rows -- this thread's 32 of the 64 O' columns -- and its sum
+                // (O_i is quiescent here: every MMA issued before S_i(j) has completed, PV_i(j) is not issued until
+                // all 256 threads of the group arrive on p_full)
                 const float f = grow ? ex2((m_used - m_new) * LOG2E) : 1.f;
                 uint32_t orr[16];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    tmem_ld16(tO + 16 * c, orr);
+                for (int c = 0; c < 2; ++c) {
+                    tmem_ld16(tO + half * 32 + 16 * c, orr);
                     tmem_wait_ld();
 #pragma unroll
                     for (int k = 0; k < 16; ++k) orr[k] = __float_as_uint(__uint_as_float(orr[k]) * f);
-                    tmem_st16(tO + 16 * c, orr);
+                    tmem_st16(tO + half * 32 + 16 * c, orr);
                 }
-                l *= f;
+                l0 *= f; l1 *= f;
             }
             m_used = m_new;
             const float neg = m_used * LOG2E;
-            // ---- pass 2: p = 2^(s*log2e - m*log2e), row sum, fp16 hi / lo split, back into TMEM; 32-key chunks with the
-            // next chunk's tcgen05.ld in flight.  P_hi chunk c lands on columns [16c, 16c+16) of the S region -- always
-            // inside chunks already consumed; P_lo has its own 64-column region.
-            const uint32_t tPl = tmem + lane_addr + 384 + wg * 64;
+            // ---- pass 2: p = 2^(s*log2e - m*log2e), partial row sum, fp16 hi / lo split, back into TMEM; two 32-key
+            // chunks with the second chunk's tcgen05.ld in flight.  P_hi chunk c lands on columns [16c, 16c+16) of this
+            // thread's own S columns -- always inside a chunk it has already consumed.
             uint32_t ca[32], cb[32];
             tmem_ld32(tS + 0, ca);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t* cur = (c & 1) ? cb : ca;
-                uint32_t* nxt = (c & 1) ? ca : cb;
+            for (int c = 0; c < 2; ++c) {
+                uint32_t* cur = c ? cb : ca;
                 tmem_wait_ld();
-                if (c < 3) tmem_ld32(tS + 32 * (c + 1), nxt);
+                if (c == 0) tmem_ld32(tS + 32, cb);
                 if (tail) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k)
@@ -290,7 +304,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 for (int t = 0; t < 16; ++t) {
                     const float p0 = ex2(fmaf(__uint_as_float(cur[2 * t]), LOG2E, -neg));
                     const float p1 = ex2(fmaf(__uint_as_float(cur[2 * t + 1]), LOG2E, -neg));
-                    l += p0 + p1;
+                    l0 += p0; l1 += p1;
                     const __half2 hi = __floats2half2_rn(p0, p1);
                     ph[t] = *reinterpret_cast<const uint32_t*>(&hi);
                     if (EXACT) {
@@ -306,49 +320,55 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             mbar_arrive(&B->p_full[wg]);
         }
 
-        // ---- epilogue
-        float o[32];
+        // ---- epilogue: this thread finishes output channels [16*half, 16*half+16) of its row
+        float l = l0 + l1;
+        B->xsum[wg][half][row] = l;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + wg) : "memory");
+        l = B->xsum[wg][0][row] + B->xsum[wg][1][row];          // same order in both threads of the row
+        float o[16];
         if (T > 0) {
             mbar_wait(&B->o_final[wg], 0);
             tc_fence_after();
-            uint32_t o0[32], o1[32];
-            tmem_ld32(tO, o0);
-            tmem_ld32(tO + 32, o1);
+            uint32_t o0[16], o1[16];
+            tmem_ld16(tO + half * 16, o0);
+            tmem_ld16(tO + 32 + half * 16, o1);
             tmem_wait_ld();
             if (dump) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    a.dbg[128 * 128 + row * 64 + k] = __uint_as_float(o0[k]);
-                    a.dbg[128 * 128 + row * 64 + 32 + k] = __uint_as_float(o1[k]);
+                for (int k = 0; k < 16; ++k) {
+                    a.dbg[128 * 128 + row * 64 + half * 16 + k] = __uint_as_float(o0[k]);
+                    a.dbg[128 * 128 + row * 64 + 32 + half * 16 + k] = __uint_as_float(o1[k]);
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(o0[k]) + __uint_as_float(o1[k]);
+            for (int k = 0; k < 16; ++k) o[k] = __uint_as_float(o0[k]) + __uint_as_float(o1[k]);
         } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) o[k] = 0.f;
+            for (int k = 0; k < 16; ++k) o[k] = 0.f;
         }
         if (q < a.N) {
             if (a.splits == 1) {
                 const float inv = 1.f / l;
-                float* dst = a.O + (size_t)q * a.ldo + h * 32;
+                float* dst = a.O + (size_t)q * a.ldo + h * 32 + half * 16;
 #pragma unroll
-                for (int k = 0; k < 32; k += 4)
+                for (int k = 0; k < 16; k += 4)
                     *reinterpret_cast<float4*>(dst + k) = make_float4(o[k] * inv, o[k + 1] * inv, o[k + 2] * inv, o[k + 3] * inv);
             } else {
-                float* dst = a.Opart + ((size_t)z * a.N + q) * (a.H * 32) + h * 32;
+                float* dst = a.Opart + ((size_t)z * a.N + q) * (a.H * 32) + h * 32 + half * 16;
 #pragma unroll
-                for (int k = 0; k < 32; k += 4)
+                for (int k = 0; k < 16; k += 4)
                     *reinterpret_cast<float4*>(dst + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
-                a.Mpart[((size_t)z * a.H + h) * a.N + q] = m_used;
-                a.Lpart[((size_t)z * a.H + h) * a.N + q] = l;
+                if (half == 0) {
+                    a.Mpart[((size_t)z * a.H + h) * a.N + q] = m_used;
+                    a.Lpart[((size_t)z * a.H + h) * a.N + q] = l;
+                }
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc<512>(tmem);
+    if (warp == MMA_WARP) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------ operand packing

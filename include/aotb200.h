@@ -30,8 +30,9 @@ void aotb_set_pdl(int on);
  *   bit 0: narrow tiles (N = 64 unless a wider tile fills the GPU on its own) instead of the widest N dividing Cout
  *          with split-K clusters for small maps;
  *   bit 1: mbarrier waits spin without the suspend hint;
- *   bit 2: every CTA writes 8 clock64 stamps (start, prologue done, first A stage stored, first stage consumable,
- *          last MMA issued, accumulator complete, epilogue stored, exit) to `workspace` as long long[ctas][8]. */
+ *   bit 2: every CTA writes clock64 stamps (0 start, 1 prologue done, 2 first A stage stored, 3 first stage
+ *          consumable, 4 last MMA issued, 5 accumulator complete, 6 tile staged, 7 exit, 8 tile visible to the
+ *          finish (cluster barrier), 9 finish stored, 10-11 unused) to `workspace` as long long[ctas][12]. */
 int aotb_set_conv_tiling(int mode);
 
 /* nn.Conv2d (+ folded FrozenBatchNorm2d, + residual, + activation) as im2col-free implicit GEMM.

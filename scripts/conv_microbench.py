@@ -32,7 +32,8 @@ SHAPES = [  # name, H, W, Cin, Cout, K, stride, pad
     ("lstt linear 1024->256", 1674, 1, 1024, 256, 1, 1, 0),
 ]
 REP = 20
-NAMES = ["prologue", "A0 stored", "stage0 ready", "last MMA issued", "acc complete", "epilogue stored", "exit"]
+NAMES = ["prologue", "A0 stored", "stage0 ready", "last MMA issued", "acc complete", "staged", "exit", "finish start",
+         "finish stored"]
 
 
 def main():
@@ -74,8 +75,8 @@ def main():
             ws.zero_()
             ops.conv2d_tc(x, wh, wl, b, out, KH=K, KW=K, stride=s, pad=p, act=1)
             torch.cuda.synchronize()
-            st8 = ws.view(torch.int64)[: 8 * 4096].view(-1, 8).cpu()
-            st8 = st8[st8[:, 7] != 0]
+            st8 = ws.view(torch.int64)[: 12 * 4096].view(-1, 12).cpu()
+            st8 = st8[st8[:, 7] != 0][:, :10]
             rel = (st8[:, 1:] - st8[:, :1]).double() / 1965.0      # cycles -> us at 1965 MHz
             rel = torch.where(st8[:, 1:] != 0, rel, torch.full_like(rel, float("nan")))
             med = torch.nanmedian(rel, dim=0).values.tolist()
