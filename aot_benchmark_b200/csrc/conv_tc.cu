@@ -381,7 +381,7 @@ static int launch_conv_tc(const CUtensorMap& th, const CUtensorMap& tl, const Co
 using namespace aotb;
 
 extern "C" int aotb_set_conv_tiling(int mode) {
-    AOTB_REQUIRE(mode >= 0 && mode < 8, "aotb_set_conv_tiling: mode is a 3-bit mask");
+    AOTB_REQUIRE(mode >= 0 && mode < (1 << 12), "aotb_set_conv_tiling: mode is a 12-bit mask");
     tc::g_conv_tiling = mode;
     return AOTB_OK;
 }
@@ -420,9 +420,18 @@ extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* 
         if (Cout % 256 == 0 && mt * (Cout / 256) >= 120) BN = 256;
         else if (Cout % 128 == 0 && mt * (Cout / 128) >= 120) BN = 128;
     }
+    const int force_bn = (tc::g_conv_tiling >> 4) & 15, force_s = (tc::g_conv_tiling >> 8) & 15;
+    if (force_bn) {
+        BN = 32 << force_bn;
+        AOTB_REQUIRE((BN == 64 || BN == 128 || BN == 256) && Cout % BN == 0, "aotb_conv2d_nhwc_tc: forced tile %d invalid", BN);
+    }
     a.splits = 1;
     const int ctas = mt * (Cout / BN);
-    if (ctas < 100 && a.nchunks >= 4) {
+    if (force_s) {
+        AOTB_REQUIRE((force_s == 1 || force_s == 2 || force_s == 4 || force_s == 8) && force_s <= a.nchunks,
+                     "aotb_conv2d_nhwc_tc: forced split %d invalid", force_s);
+        a.splits = force_s;
+    } else if (ctas < 100 && a.nchunks >= 4) {
         int sp = 8;
         while (sp > 1 && (ctas * sp > 160 || a.nchunks / sp < 2)) sp >>= 1;
         a.splits = sp;

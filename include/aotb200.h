@@ -32,7 +32,9 @@ void aotb_set_pdl(int on);
  *   bit 1: mbarrier waits spin without the suspend hint;
  *   bit 2: every CTA writes clock64 stamps (0 start, 1 prologue done, 2 first A stage stored, 3 first stage
  *          consumable, 4 last MMA issued, 5 accumulator complete, 6 tile staged, 7 exit, 8 tile visible to the
- *          finish (cluster barrier), 9 finish stored, 10-11 unused) to `workspace` as long long[ctas][12]. */
+ *          finish (cluster barrier), 9 finish stored, 10-11 unused) to `workspace` as long long[ctas][12];
+ *   bits 4-7: force the N tile (1 = 64, 2 = 128, 3 = 256; 0 = policy); bits 8-11: force the split-K factor
+ *          (1, 2, 4, 8; 0 = policy).  Forced values that do not divide the problem are an argument error. */
 int aotb_set_conv_tiling(int mode);
 
 /* nn.Conv2d (+ folded FrozenBatchNorm2d, + residual, + activation) as im2col-free implicit GEMM.
