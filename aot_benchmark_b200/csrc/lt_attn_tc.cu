@@ -8,16 +8,16 @@
 //   warp 16     TMA producer: Q tiles once, then a 3-stage ring of K/V tiles (128 keys) via
 //               cp.async.bulk.tensor + mbarrier complete_tx
 //   warp 17     tcgen05.mma issuer (one elected thread): S_i = Q_i K_j^T into TMEM, later O_i += P_i V_j
-//   warps 0-7   softmax group 0 (query rows   0..127): TWO threads per row (warps w and w+4 share the TMEM lanes of
-//   warps 8-15  softmax group 1 (query rows 128..255)  rows 32(w%4)..+31 and take 64 key columns each): tcgen05.ld S ->
-//               half-row max, exchanged through shared memory -> ex2 / partial row sum in registers -> P back into
-//               TMEM as the A operand of the PV MMA.  Four softmax warps per scheduler (it was one row per thread and
-//               two warps per scheduler: with one group waiting on its MMAs a scheduler had a single warp to issue
-//               from and the MUFU / TMEM latencies were exposed).  The two groups ping-pong so MUFU and the tensor
-//               pipe overlap (issue order PV_0, S_0', PV_1, S_1').
-//   TMEM        S_0 | S_1 (128 fp32 columns each) | O_0 | O_1 | Plo_0 | Plo_1 (64 each).  P_hi of the keys a thread owns
-//               overwrites the first half of that thread's own S columns: keys [0,64) -> columns [0,32),
-//               keys [64,128) -> columns [64,96).
+//   warps 0-15  softmax: all 16 warps work on ONE 128 x 128 score tile at a time, alternating between S_0 (query rows
+//               0..127) and S_1 (rows 128..255).  Warp w owns TMEM lanes 32(w%4)..+31 and key columns 32(w/4)..+31, i.e.
+//               four threads share a row: tcgen05.ld of its 32 scores ONCE -> quarter-row max, exchanged through shared
+//               memory -> ex2 / partial row sum -> P (fp16 hi / lo) back into TMEM as the A operand of the PV MMA.
+//               TMEM reads run at 64 B/clk/SM, so a 128 x 128 fp32 tile costs 1024 cycles per pass: the earlier
+//               layouts (1 or 2 threads per row) could not keep a row in registers and read every tile twice
+//               (max pass + exp pass), which capped the kernel at ~2 x 2048 cycles per key tile.  While the warps
+//               are on S_i the tensor pipe runs PV_(1-i) and the next S_(1-i) (issue order PV_0, S_0', PV_1, S_1').
+//   TMEM        S_0 | S_1 (128 fp32 columns each) | O_0 | O_1 | Plo_0 | Plo_1 (64 each).  P_hi of the 32 keys a thread
+//               owns overwrites the first 16 of its own 32 S columns: keys [32t, 32t+32) -> columns [32t, 32t+16).
 //
 // Precision ("fp16x2"): every fp32 operand x is carried as hi = fp16(x), lo = fp16(x - hi); rows of the
 // packed operands are [hi(32) | lo(32)] halfs = 128 bytes (the same bytes as fp32, one TMA swizzle atom).
@@ -84,8 +84,8 @@ struct __align__(8) Barriers {
     uint64_t p_full[2];
     uint64_t o_final[2];
     uint32_t tmem_base;
-    float xmax[2][2][2][BM];    // [tile parity][group][half][row]: half-row maxima
-    float xsum[2][2][BM];       // [group][half][row]: half-row sums (epilogue)
+    float xmax[2][4][BM];       // [tile parity][column quarter][row]: quarter-row maxima
+    float xsum[2][4][BM];       // [tile][column quarter][row]: quarter-row sums (epilogue)
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
@@ -103,6 +103,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
 }
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
@@ -130,7 +136,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (tid == 0) {
         mbar_init(&B->q_full, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&B->kv_full[s], 1); mbar_init(&B->kv_free[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&B->s_full[i], 1); mbar_init(&B->p_full[i], 2 * BM); mbar_init(&B->o_final[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&B->s_full[i], 1); mbar_init(&B->p_full[i], 4 * BM); mbar_init(&B->o_final[i], 1); }
         fence_mbar_init();
     }
     if (warp == MMA_WARP) tmem_alloc<512>(&B->tmem_base);
@@ -189,8 +195,8 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 const uint32_t d = tmem + 256 + i * 64;
                 const uint32_t p = tmem + i * 128;
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk)       // P_hi: keys [0,64) at columns [0,32), keys [64,128) at [64,96)
-                    mma_ts(d, p + 8 * kk + (kk >= 4 ? 32 : 0), v + 128 * kk, IDESC_O, (kk > 0) ? 1u : acc);
+                for (int kk = 0; kk < 8; ++kk)       // P_hi of keys [32t, 32t+32) sits at columns [32t, 32t+16)
+                    mma_ts(d, p + 32 * (kk >> 1) + 8 * (kk & 1), v + 128 * kk, IDESC_O, (kk > 0) ? 1u : acc);
                 if (EXACT) {
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) mma_ts(d, tmem + 384 + i * 64 + 8 * kk, v + 128 * kk, IDESC_O, 1);
@@ -220,91 +226,70 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
         }
     } else {
-        // ======================= softmax groups =======================
-        const int wg = warp >> 3, half = (warp >> 2) & 1, wq = warp & 3;
+        // ======================= softmax (16 warps, one score tile at a time) =======================
+        const int qt = warp >> 2, wq = warp & 3;           // column quarter, TMEM lane quadrant
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        const uint32_t tS = tmem + lane_addr + wg * 128 + half * 64;      // this thread's 64 score columns
-        const uint32_t tO = tmem + lane_addr + 256 + wg * 64;
-        const uint32_t tPl = tmem + lane_addr + 384 + wg * 64 + half * 32;
-        const int q = q0 + wg * BM + row;
-        const bool dump = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && wg == 0;
-        float m_used = -INFINITY, l0 = 0.f, l1 = 0.f;
+        float m_used[2] = {-INFINITY, -INFINITY}, l0[2] = {0.f, 0.f}, l1[2] = {0.f, 0.f};
 
         for (int j = 0; j < T; ++j) {
-            mbar_wait(&B->s_full[wg], j & 1);
-            tc_fence_after();
-            const int key0 = (tb + j) * BN + half * 64;
-            const bool tail = key0 + 64 > Tk;
-            // ---- pass 1: half-row max (both tcgen05.ld in flight together); the values are dropped again so that
-            // pass 2 runs in a small register window.
-            float mt = -INFINITY;
-            {
-                uint32_t sr[64];
-                tmem_ld32(tS + 0, sr);
-                tmem_ld32(tS + 32, sr + 32);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const uint32_t tS = tmem + lane_addr + i * 128 + qt * 32;      // this thread's 32 score columns
+                const uint32_t tO = tmem + lane_addr + 256 + i * 64 + qt * 16;  // its 16 of the 64 O' columns
+                const uint32_t tPl = tmem + lane_addr + 384 + i * 64 + qt * 16;
+                const bool dump = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i == 0;
+                mbar_wait(&B->s_full[i], j & 1);
+                tc_fence_after();
+                const int key0 = (tb + j) * BN + qt * 32;
+                uint32_t sr[32];
+                tmem_ld32(tS, sr);
                 tmem_wait_ld();
                 if (dump && j == 0) {
 #pragma unroll
-                    for (int k = 0; k < 64; ++k) a.dbg[row * 128 + half * 64 + k] = __uint_as_float(sr[k]);
+                    for (int k = 0; k < 32; ++k) a.dbg[row * 128 + qt * 32 + k] = __uint_as_float(sr[k]);
                 }
-                if (tail) {                          // warp-uniform: only the last key tile of the bank is ragged
+                if (key0 + 32 > Tk) {                    // warp-uniform: only the last key tile of the bank is ragged
 #pragma unroll
-                    for (int k = 0; k < 64; ++k)
+                    for (int k = 0; k < 32; ++k)
                         if (key0 + k >= Tk) sr[k] = __float_as_uint(-INFINITY);
                 }
-                float m0 = -INFINITY, m1 = -INFINITY;
+                float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-                for (int k = 0; k < 64; k += 2) {
-                    m0 = fmaxf(m0, __uint_as_float(sr[k]));
-                    m1 = fmaxf(m1, __uint_as_float(sr[k + 1]));
+                for (int k = 0; k < 32; k += 2) {
+                    mx0 = fmaxf(mx0, __uint_as_float(sr[k]));
+                    mx1 = fmaxf(mx1, __uint_as_float(sr[k + 1]));
                 }
-                mt = fmaxf(m0, m1);
-            }
-            B->xmax[j & 1][wg][half][row] = mt;
-            asm volatile("bar.sync %0, 256;" ::"r"(1 + wg) : "memory");       // the 8 warps of this group
-            mt = fmaxf(mt, B->xmax[j & 1][wg][half ^ 1][row]);
-            const float m_new = fmaxf(m_used, mt);
-            const bool grow = (m_new > m_used) && (j > 0);
-            if (__any_sync(0xffffffffu, grow)) {
-                // rescale the running output of this warp's rows -- this thread's 32 of the 64 O' columns -- and its sum
-                // (O_i is quiescent here: every MMA issued before S_i(j) has completed, PV_i(j) is not issued until
-                // all 256 threads of the group arrive on p_full)
-                const float f = grow ? ex2((m_used - m_new) * LOG2E) : 1.f;
-                uint32_t orr[16];
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    tmem_ld16(tO + half * 32 + 16 * c, orr);
+                const int par = i;                        // tiles alternate 0,1,0,1: the tile index is its own parity
+                B->xmax[par][qt][row] = fmaxf(mx0, mx1);
+                asm volatile("bar.sync 1, 512;" ::: "memory");                    // the 16 softmax warps
+                const float mt = fmaxf(fmaxf(B->xmax[par][0][row], B->xmax[par][1][row]),
+                                       fmaxf(B->xmax[par][2][row], B->xmax[par][3][row]));
+                const float m_new = fmaxf(m_used[i], mt);
+                const bool grow = (m_new > m_used[i]) && (j > 0);
+                if (__any_sync(0xffffffffu, grow)) {
+                    // rescale the running output of this warp's rows -- this thread's 16 of the 64 O' columns -- and
+                    // its partial sum (O_i is quiescent here: every MMA issued before S_i(j) has completed, PV_i(j)
+                    // is not issued until all 512 threads arrive on p_full)
+                    const float f = grow ? ex2((m_used[i] - m_new) * LOG2E) : 1.f;
+                    uint32_t orr[16];
+                    tmem_ld16(tO, orr);
                     tmem_wait_ld();
 #pragma unroll
                     for (int k = 0; k < 16; ++k) orr[k] = __float_as_uint(__uint_as_float(orr[k]) * f);
-                    tmem_st16(tO + half * 32 + 16 * c, orr);
+                    tmem_st16(tO, orr);
+                    l0[i] *= f; l1[i] *= f;
                 }
-                l0 *= f; l1 *= f;
-            }
-            m_used = m_new;
-            const float neg = m_used * LOG2E;
-            // ---- pass 2: p = 2^(s*log2e - m*log2e), partial row sum, fp16 hi / lo split, back into TMEM; two 32-key
-            // chunks with the second chunk's tcgen05.ld in flight.  P_hi chunk c lands on columns [16c, 16c+16) of this
-            // thread's own S columns -- always inside a chunk it has already consumed.
-            uint32_t ca[32], cb[32];
-            tmem_ld32(tS + 0, ca);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t* cur = c ? cb : ca;
-                tmem_wait_ld();
-                if (c == 0) tmem_ld32(tS + 32, cb);
-                if (tail) {
-#pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        if (key0 + 32 * c + k >= Tk) cur[k] = __float_as_uint(-INFINITY);
-                }
+                m_used[i] = m_new;
+                const float neg = m_new * LOG2E;
+                // p = 2^(s*log2e - m*log2e), partial row sum, fp16 hi / lo split, back into TMEM
                 uint32_t ph[16], pl[16];
+                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
-                    const float p0 = ex2(fmaf(__uint_as_float(cur[2 * t]), LOG2E, -neg));
-                    const float p1 = ex2(fmaf(__uint_as_float(cur[2 * t + 1]), LOG2E, -neg));
-                    l0 += p0; l1 += p1;
+                    const float p0 = ex2(fmaf(__uint_as_float(sr[2 * t]), LOG2E, -neg));
+                    const float p1 = ex2(fmaf(__uint_as_float(sr[2 * t + 1]), LOG2E, -neg));
+                    s0 += p0; s1 += p1;
                     const __half2 hi = __floats2half2_rn(p0, p1);
                     ph[t] = *reinterpret_cast<const uint32_t*>(&hi);
                     if (EXACT) {
@@ -312,55 +297,60 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         pl[t] = *reinterpret_cast<const uint32_t*>(&lo);
                     }
                 }
-                tmem_st16(tS + 16 * c, ph);
-                if (EXACT) tmem_st16(tPl + 16 * c, pl);
+                l0[i] += s0; l1[i] += s1;
+                tmem_st16(tS, ph);
+                if (EXACT) tmem_st16(tPl, pl);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&B->p_full[i]);
             }
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(&B->p_full[wg]);
         }
 
-        // ---- epilogue: this thread finishes output channels [16*half, 16*half+16) of its row
-        float l = l0 + l1;
-        B->xsum[wg][half][row] = l;
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + wg) : "memory");
-        l = B->xsum[wg][0][row] + B->xsum[wg][1][row];          // same order in both threads of the row
-        float o[16];
-        if (T > 0) {
-            mbar_wait(&B->o_final[wg], 0);
-            tc_fence_after();
-            uint32_t o0[16], o1[16];
-            tmem_ld16(tO + half * 16, o0);
-            tmem_ld16(tO + 32 + half * 16, o1);
-            tmem_wait_ld();
-            if (dump) {
+        // ---- epilogue: per tile, this thread finishes output channels [8*qt, 8*qt+8) of its row
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    a.dbg[128 * 128 + row * 64 + half * 16 + k] = __uint_as_float(o0[k]);
-                    a.dbg[128 * 128 + row * 64 + 32 + half * 16 + k] = __uint_as_float(o1[k]);
+        for (int i = 0; i < 2; ++i) B->xsum[i][qt][row] = l0[i] + l1[i];
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float l = (B->xsum[i][0][row] + B->xsum[i][1][row]) + (B->xsum[i][2][row] + B->xsum[i][3][row]);
+            const uint32_t tO = tmem + lane_addr + 256 + i * 64;
+            const bool dump = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i == 0;
+            const int q = q0 + i * BM + row;
+            float o[8];
+            if (T > 0) {
+                mbar_wait(&B->o_final[i], 0);
+                tc_fence_after();
+                uint32_t o0[8], o1[8];
+                tmem_ld8(tO + qt * 8, o0);
+                tmem_ld8(tO + 32 + qt * 8, o1);
+                tmem_wait_ld();
+                if (dump) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        a.dbg[128 * 128 + row * 64 + qt * 8 + k] = __uint_as_float(o0[k]);
+                        a.dbg[128 * 128 + row * 64 + 32 + qt * 8 + k] = __uint_as_float(o1[k]);
+                    }
                 }
-            }
 #pragma unroll
-            for (int k = 0; k < 16; ++k) o[k] = __uint_as_float(o0[k]) + __uint_as_float(o1[k]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) o[k] = 0.f;
-        }
-        if (q < a.N) {
-            if (a.splits == 1) {
-                const float inv = 1.f / l;
-                float* dst = a.O + (size_t)q * a.ldo + h * 32 + half * 16;
-#pragma unroll
-                for (int k = 0; k < 16; k += 4)
-                    *reinterpret_cast<float4*>(dst + k) = make_float4(o[k] * inv, o[k + 1] * inv, o[k + 2] * inv, o[k + 3] * inv);
+                for (int k = 0; k < 8; ++k) o[k] = __uint_as_float(o0[k]) + __uint_as_float(o1[k]);
             } else {
-                float* dst = a.Opart + ((size_t)z * a.N + q) * (a.H * 32) + h * 32 + half * 16;
 #pragma unroll
-                for (int k = 0; k < 16; k += 4)
-                    *reinterpret_cast<float4*>(dst + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
-                if (half == 0) {
-                    a.Mpart[((size_t)z * a.H + h) * a.N + q] = m_used;
-                    a.Lpart[((size_t)z * a.H + h) * a.N + q] = l;
+                for (int k = 0; k < 8; ++k) o[k] = 0.f;
+            }
+            if (q < a.N) {
+                if (a.splits == 1) {
+                    const float inv = 1.f / l;
+                    float* dst = a.O + (size_t)q * a.ldo + h * 32 + qt * 8;
+                    *reinterpret_cast<float4*>(dst) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
+                } else {
+                    float* dst = a.Opart + ((size_t)z * a.N + q) * (a.H * 32) + h * 32 + qt * 8;
+                    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                    if (qt == 0) {
+                        a.Mpart[((size_t)z * a.H + h) * a.N + q] = m_used[i];
+                        a.Lpart[((size_t)z * a.H + h) * a.N + q] = l;
+                    }
                 }
             }
         }
