@@ -407,34 +407,54 @@ extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* 
     const int K = ((KH * KW * Cin + 63) / 64) * 64;   // weights are zero-padded to a multiple of 64 along K
     a.nchunks = K / 64;
     a.act = act;
-    // Tile width.  A 128 x BN x 16 MMA reads (4 + BN/32) KB of shared memory per BN/2 math cycles, i.e. 192 / 128 / 96
-    // B/clk for BN = 64 / 128 / 256 against 128 B/clk of shared-memory bandwidth, and the fp16x2 split issues three of
-    // them per k-step: narrow tiles are smem-bound.  Default ("wide"): the widest BN dividing Cout, parallelism for the
-    // small maps from split-K clusters of 2 / 4 / 8 CTAs (>= 2 chunks per CTA, about one wave in total).
+    // Tile policy: pick the N tile (64 / 128 / 256 dividing Cout) and the split-K cluster size (1 / 2 / 4 / 8) that
+    // minimise a cost model fitted to profiles/r01_trip14_conv_sweep.json (B200, graph-replayed launches):
+    //     T = waves * (ramp + chunks_per_cta * t_chunk[BN] + t_finish[BN]) + (S > 1 ? t_cluster : 0)
+    //   t_chunk : one 64-deep K chunk = 12 MMAs.  A 128 x BN x 16 MMA reads (4 + BN/32) KB of shared memory per BN/2
+    //             math cycles -- 192 / 128 / 96 B/clk for BN = 64 / 128 / 256 against 128 B/clk of smem bandwidth --
+    //             so narrow tiles are smem-bound (0.63 us for a quarter of the work a BN = 256 chunk does in 0.80 us);
+    //   t_finish: staging + (DSMEM reduction) + row stores of a 128 x BN fp32 tile; proportional to the tile bytes at
+    //             ~20-26 GB/s per SM whether it is written straight out or summed over the cluster (DSMEM ~21 B/clk);
+    //   ramp    : prologue + first activation chunk in shared memory, paid once per wave of CTAs.
+    // bit 0 of the tuning mask ("narrow") restores the pre-model heuristic for A/B runs.
     const int mt = cdiv(a.M, 128);
-    int BN;
+    int BN = 64, best_s = 1;
     if ((tc::g_conv_tiling & 1) == 0) {
-        BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
-    } else {          // "narrow": the widest BN that still fills ~a wave on its own, else 64
-        BN = 64;
+        float best = 1e30f;
+        const int bns[3] = {256, 128, 64};
+        const float t_chunk[3] = {0.80f, 0.66f, 0.63f}, t_fin[3] = {6.5f, 3.6f, 2.1f};
+        for (int bi = 0; bi < 3; ++bi) {
+            if (Cout % bns[bi]) continue;
+            for (int sp = 1; sp <= 8; sp <<= 1) {
+                if (sp > a.nchunks) break;
+                const int ctas = mt * (Cout / bns[bi]) * sp;
+                const int slots = sp == 8 ? 128 : (sp == 4 ? 132 : 148);        // co-resident CTAs with clusters of sp
+                if (sp > 1 && ctas > slots) continue;                         // split-K only to fill a partial wave
+                const int waves = cdiv(ctas, slots);
+                const float t = waves * (2.0f + cdiv(a.nchunks, sp) * t_chunk[bi] + t_fin[bi]) + (sp > 1 ? 0.3f : 0.f);
+                if (t < best) { best = t; BN = bns[bi]; best_s = sp; }
+            }
+        }
+    } else {          // "narrow": the widest BN that still fills ~a wave on its own, else 64; split-K to ~one wave
         if (Cout % 256 == 0 && mt * (Cout / 256) >= 120) BN = 256;
         else if (Cout % 128 == 0 && mt * (Cout / 128) >= 120) BN = 128;
+        const int ctas = mt * (Cout / BN);
+        if (ctas < 100 && a.nchunks >= 4) {
+            best_s = 8;
+            while (best_s > 1 && (ctas * best_s > 160 || a.nchunks / best_s < 2)) best_s >>= 1;
+        }
     }
     const int force_bn = (tc::g_conv_tiling >> 4) & 15, force_s = (tc::g_conv_tiling >> 8) & 15;
     if (force_bn) {
         BN = 32 << force_bn;
         AOTB_REQUIRE((BN == 64 || BN == 128 || BN == 256) && Cout % BN == 0, "aotb_conv2d_nhwc_tc: forced tile %d invalid", BN);
     }
-    a.splits = 1;
+    a.splits = force_bn ? 1 : best_s;
     const int ctas = mt * (Cout / BN);
     if (force_s) {
         AOTB_REQUIRE((force_s == 1 || force_s == 2 || force_s == 4 || force_s == 8) && force_s <= a.nchunks,
                      "aotb_conv2d_nhwc_tc: forced split %d invalid", force_s);
         a.splits = force_s;
-    } else if (ctas < 100 && a.nchunks >= 4) {
-        int sp = 8;
-        while (sp > 1 && (ctas * sp > 160 || a.nchunks / sp < 2)) sp >>= 1;
-        a.splits = sp;
     }
     a.spin = (tc::g_conv_tiling & 2) ? 1 : 0;
     a.prof = nullptr;

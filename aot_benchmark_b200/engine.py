@@ -47,8 +47,8 @@ LT_KERNEL_NAME = _LT_NAMES.get(LT_IMPL, LT_IMPL)
 USE_GRAPHS = _os.environ.get("AOTB_GRAPHS", "1") == "1"
 # programmatic dependent launch: kernel N+1's prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps
 # kernel N's tail; every kernel waits (griddepcontrol.wait) before reading its inputs
-USE_PDL = _os.environ.get("AOTB_PDL", "0") == "1"
-CONV_TILING = _os.environ.get("AOTB_CONV_TILING", "wide")    # "wide" | "narrow": tile policy of the tensor-core conv
+USE_PDL = _os.environ.get("AOTB_PDL", "1") == "1"     # programmatic dependent launch: +2 % (profiles/r01_trip14)
+CONV_TILING = _os.environ.get("AOTB_CONV_TILING", "model")   # "model" (fitted cost model) | "narrow" (old heuristic)
 
 
 def _apply_pdl():

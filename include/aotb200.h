@@ -27,8 +27,8 @@ unsigned long long aotb_launch_count(void);
 /* Launch every kernel with programmatic dependent launch (prologues overlap the previous kernel's tail). */
 void aotb_set_pdl(int on);
 /* Tuning / diagnostic mask of aotb_conv2d_nhwc_tc (default 0); results are identical up to fp32 summation order.
- *   bit 0: narrow tiles (N = 64 unless a wider tile fills the GPU on its own) instead of the widest N dividing Cout
- *          with split-K clusters for small maps;
+ *   bit 0: the pre-cost-model heuristic (N = 64 tiles unless a wider tile fills the GPU on its own) instead of the
+ *          fitted cost model over N tile x split-K cluster size;
  *   bit 1: mbarrier waits spin without the suspend hint;
  *   bit 2: every CTA writes clock64 stamps (0 start, 1 prologue done, 2 first A stage stored, 3 first stage
  *          consumable, 4 last MMA issued, 5 accumulator complete, 6 tile staged, 7 exit, 8 tile visible to the
