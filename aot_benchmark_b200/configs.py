@@ -22,6 +22,9 @@ _MODELS = {
     "deaotl": ("deaot", "mobilenetv2", [24, 32, 96, 1280], 3, True, 5),
     # configs/models/r50_deaotl.py
     "r50_deaotl": ("deaot", "resnet50", [256, 512, 1024, 1024], 3, True, 5),
+    # configs/models/swinb_aotl.py:9-18, swinb_deaotl.py:9-18
+    "swinb_aotl": ("aot", "swin_base", [128, 256, 512, 512], 3, False, 5),
+    "swinb_deaotl": ("deaot", "swin_base", [128, 256, 512, 512], 3, False, 5),
 }
 
 

@@ -165,6 +165,9 @@ class _Encoder:
         P = self.plan
         if img.dim() != 4 or img.shape[0] != 1 or img.shape[1] != 3:
             raise ValueError("expected an image tensor [1,3,H,W]")
+        if P.encoder_name == "swin_base" and (img.shape[2] % 4 or img.shape[3] % 4):
+            # PatchEmbed zero-pads right/bottom to a multiple of the 4x4 patch (swin_transformer.py:476-481)
+            img = torch.nn.functional.pad(img, (0, -img.shape[3] % 4, 0, -img.shape[2] % 4))
         H, W = img.shape[2], img.shape[3]
         if getattr(self, "_gkey", None) != (id(P), H, W):
             self.graphs = GraphCache()
@@ -181,6 +184,8 @@ class _Encoder:
         st = _cur_stream()
         if P.encoder_name == "resnet50":
             feats = self._resnet(x, st)
+        elif P.encoder_name == "swin_base":
+            feats = self._swin(x, st)
         else:
             feats = self._mobilenet(x, st)
         f16 = feats[-1]
@@ -214,6 +219,46 @@ class _Encoder:
                 ops.conv2d(t2, b.c3.w, b.c3.b, out, res=res, act=A_RELU, stream=st)
                 cur, h, w = out, ho, wo
             feats.append(cur)
+        return feats
+
+    def _swin(self, x4, st):
+        """SwinTransformer.forward (swin_transformer.py:684-716) for 'swin_base': tokens stay one [H*W, C] matrix per
+        stage (= the NHWC map), every Linear is a tensor-core GEMM with the residual / GELU fused in its finish, the
+        window partition / shift / padding / mask live inside window_attn_kernel, and the per-stage output norms
+        write the NHWC feature maps the decoder reads."""
+        e = self.plan.enc
+        H, W, C = x4.shape[1] // 4, x4.shape[2] // 4, e.embed
+        pe = self._buf("pe", (1, H, W, C))
+        ops.conv2d(x4, e.patch.w, e.patch.b, pe, KH=4, KW=4, stride=4, pad=0, stream=st)          # PatchEmbed :473-489
+        x = self._buf("s0x", (H * W, C))
+        ops.layernorm(pe.view(H * W, C), e.patch_norm[0], e.patch_norm[1], x, stream=st)
+        feats = []
+        for si, stg in enumerate(e.stages):
+            N = H * W
+            ln = self._buf(f"s{si}ln", (N, C))
+            qkv = self._buf(f"s{si}qkv", (N, 3 * C))
+            att = self._buf(f"s{si}att", (N, C))
+            hid = self._buf(f"s{si}hid", (N, 4 * C))
+            for b in stg.blocks:                                                            # SwinTransformerBlock :257-323
+                ops.layernorm(x, b.norm1[0], b.norm1[1], ln, stream=st)
+                ops.linear(ln, b.qkv_w, b.qkv_b, qkv, stream=st)
+                ops.window_attention(qkv, b.qkv_b, b.relb, att, H, W, stg.heads, b.shift, window=e.window, stream=st)
+                ops.linear(att, b.proj_w, b.proj_b, x, res=x, stream=st)                    # x = shortcut + proj(attn)
+                ops.layernorm(x, b.norm2[0], b.norm2[1], ln, stream=st)
+                ops.linear(ln, b.fc1_w, b.fc1_b, hid, act=A_GELU, stream=st)
+                ops.linear(hid, b.fc2_w, b.fc2_b, x, res=x, stream=st)                      # x = x + mlp(norm2(x))
+            f = self._buf(f"s{si}f", (1, H, W, C))
+            ops.layernorm(x, stg.norm[0], stg.norm[1], f.view(N, C), stream=st)             # norm{i} on the stage output
+            feats.append(f)
+            if stg.down is not None:                                                        # PatchMerging :339-365
+                H2, W2 = (H + 1) // 2, (W + 1) // 2
+                mg = self._buf(f"s{si}mg", (H2 * W2, 4 * C))
+                ops.patch_merge(x, mg, H, W, stream=st)
+                mln = self._buf(f"s{si}mln", (H2 * W2, 4 * C))
+                ops.layernorm(mg, stg.down.norm[0], stg.down.norm[1], mln, stream=st)
+                x = self._buf(f"s{si + 1}x", (H2 * W2, 2 * C))
+                ops.linear(mln, stg.down.w, stg.down.b, x, stream=st)
+                H, W, C = H2, W2, 2 * C
         return feats
 
     def _mobilenet(self, x, st):

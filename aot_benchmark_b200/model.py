@@ -144,12 +144,70 @@ def _mobilenetv2():
     return enc
 
 
+# build.py:11-22 ('swin_base'): the 4th stage is dropped at construction (swin_transformer.py:566)
+SWIN_BASE = {"embed": 128, "depths": (2, 2, 18), "heads": (4, 8, 16), "window": 7, "patch": 4}
+
+
+def swin_relative_position_index(ws):
+    # swin_transformer.py:131-147
+    ys, xs = torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij")
+    y, x = ys.reshape(-1), xs.reshape(-1)
+    return (y[:, None] - y[None, :] + ws - 1) * (2 * ws - 1) + (x[:, None] - x[None, :] + ws - 1)
+
+
+def _swin_base():
+    """Parameter tree of SwinTransformer(embed_dim=128, depths=[2,2,18,2], num_heads=[4,8,16,32]) with the
+    reference's names (swin_transformer.py:571-640): patch_embed.{proj,norm}, layers.<i>.blocks.<j>.{norm1,
+    attn.{relative_position_bias_table,relative_position_index,qkv,proj},norm2,mlp.{fc1,fc2}},
+    layers.<i>.downsample.{reduction,norm}, norm<i>."""
+    S = SWIN_BASE
+    ws = S["window"]
+    enc = ParamNode()
+    enc.patch_embed = ParamNode()
+    enc.patch_embed.proj = Conv(3, S["embed"], S["patch"])
+    enc.patch_embed.norm = Norm(S["embed"])
+    layers = []
+    for i, (depth, heads) in enumerate(zip(S["depths"], S["heads"])):
+        dim = S["embed"] * 2 ** i
+        layer = ParamNode()
+        blocks = []
+        for _ in range(depth):
+            b = ParamNode()
+            b.norm1 = Norm(dim)
+            b.attn = ParamNode()
+            b.attn.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws - 1) ** 2, heads))
+            nn.init.trunc_normal_(b.attn.relative_position_bias_table, std=0.02)    # :155
+            b.attn.register_buffer("relative_position_index", swin_relative_position_index(ws))
+            b.attn.qkv = Linear(dim, 3 * dim)
+            b.attn.proj = Linear(dim, dim)
+            b.norm2 = Norm(dim)
+            b.mlp = ParamNode()
+            b.mlp.fc1 = Linear(dim, 4 * dim)
+            b.mlp.fc2 = Linear(4 * dim, dim)
+            blocks.append(b)
+        layer.blocks = nn.ModuleList(blocks)
+        if i < len(S["depths"]) - 1:
+            layer.downsample = ParamNode()
+            red = ParamNode()
+            red.weight = nn.Parameter(torch.empty(2 * dim, 4 * dim))               # Linear(4C, 2C, bias=False) :333
+            nn.init.kaiming_uniform_(red.weight, a=math.sqrt(5))
+            layer.downsample.reduction = red
+            layer.downsample.norm = Norm(4 * dim)
+        layers.append(layer)
+    enc.layers = nn.ModuleList(layers)
+    for i in range(len(S["depths"])):
+        setattr(enc, f"norm{i}", Norm(S["embed"] * 2 ** i))
+    return enc
+
+
 def build_encoder_params(name):
     if name == "resnet50":
         return _resnet50()
     if name == "mobilenetv2":
         return _mobilenetv2()
-    raise NotImplementedError(f"encoder '{name}' has no sm_100a path yet (resnet50, mobilenetv2 do)")
+    if name == "swin_base":
+        return _swin_base()
+    raise NotImplementedError(f"encoder '{name}' has no sm_100a path yet (resnet50, mobilenetv2, swin_base do)")
 
 
 # ---------------------------------------------------------------- transformer blocks

@@ -192,6 +192,28 @@ def layernorm(x, gamma, beta, out, add=None, out2=None, stream=None):
     return out
 
 
+def window_attention(qkv, qkv_bias, rel_bias, out, H, W, heads, shift, window=7, stream=None):
+    """Swin (S)W-MSA core: qkv [H*W, 3C], rel_bias [heads, 49, 49], out [H*W, C]."""
+    _chk(qkv, qkv_bias, rel_bias, out)
+    C = out.shape[1]
+    if qkv.shape[0] != H * W or qkv.shape[1] != 3 * C or out.shape[0] != H * W or not rel_bias.is_contiguous():
+        raise AotbError("window_attention: qkv must be [H*W, 3C], out [H*W, C], rel_bias contiguous")
+    check(lib().aotb_window_attention_f32(_p(qkv), qkv.stride(0), _p(qkv_bias), _p(rel_bias), _p(out), out.stride(0),
+                                          H, W, C, heads, window, shift, _st(stream)), "aotb_window_attention_f32")
+    return out
+
+
+def patch_merge(x, out, H, W, stream=None):
+    """x [H*W, C] -> out [ceil(H/2)*ceil(W/2), 4C] (PatchMerging gather)."""
+    _chk(x, out)
+    C = x.shape[1]
+    if x.shape[0] != H * W or out.shape[0] != ((H + 1) // 2) * ((W + 1) // 2) or out.shape[1] != 4 * C:
+        raise AotbError("patch_merge: shape mismatch")
+    check(lib().aotb_patch_merge_f32(_p(x), x.stride(0), _p(out), out.stride(0), H, W, C, _st(stream)),
+          "aotb_patch_merge_f32")
+    return out
+
+
 def groupnorm_workspace(B, G, device):
     n = lib().aotb_groupnorm_workspace_bytes(B, G)
     return torch.empty(n // 8, dtype=torch.float64, device=device)

@@ -17,7 +17,7 @@ from types import SimpleNamespace as NS
 
 import torch
 
-from .model import mobilenetv2_plan
+from .model import SWIN_BASE, mobilenetv2_plan, swin_relative_position_index
 
 
 def _signature(model):
@@ -40,9 +40,7 @@ class Plan:
         cfg = model.cfg
         self.cfg = cfg
         dev = next(model.parameters()).device
-        if dev.type != "cuda":
-            raise RuntimeError("aot_benchmark_b200 runs on CUDA devices only (no CPU path): move the model to "
-                               "a GPU before building an engine")
+        self._require_cuda(dev)
         self.device = dev
         sd = {k: v.detach() for k, v in model.state_dict().items()}
         self.sd = sd
@@ -59,6 +57,12 @@ class Plan:
         self.layers = [self._gpm_layer(i) if self.deaot else self._lstt_layer(i) for i in range(self.L)]
         self._decoder()
         self._idbank()
+
+    @staticmethod
+    def _require_cuda(dev):
+        if dev.type != "cuda":
+            raise RuntimeError("aot_benchmark_b200 runs on CUDA devices only (no CPU path): move the model to "
+                               "a GPU before building an engine")
 
     def _reg(self, w, cin=None):
         """Register split-fp16 [Cout, K] copies of a GEMM-shaped fp32 weight [K, Cout] for the tensor-core conv
@@ -153,8 +157,46 @@ class Plan:
                 e.blocks.append(b)
             e.last = self._conv_bn(p + "features.18.0", p + "features.18.1")
             self.enc = e
+        elif name == "swin_base":
+            self.enc = self._swin(p)
         else:
             raise NotImplementedError(f"encoder '{name}' has no sm_100a path")
+
+    def _swin(self, p):
+        """Swin-B (build.py:11-22) weights: every Linear as [in, out] (registered for the tensor-core GEMM), the 4x4/4
+        patch embedding as a conv over the NHWC4 image (fp32 CUDA-core path: K = 64), and per block the dense
+        [heads, 49, 49] relative-position bias = table[index] (swin_transformer.py:176-183), gathered once here
+        instead of once per block per frame."""
+        sd = self.sd
+        S = SWIN_BASE
+        ws = S["window"]
+        pw = sd[p + "patch_embed.proj.weight"]
+        pw = torch.nn.functional.pad(pw, (0, 0, 0, 0, 0, 4 - pw.shape[1]))        # zero 4th input channel (NHWC4 image)
+        e = NS(embed=S["embed"], window=ws, patch=NS(w=self._conv_w(pw), b=self._f(sd[p + "patch_embed.proj.bias"])),
+               patch_norm=self._norm(p + "patch_embed.norm"), stages=[])
+        idx = swin_relative_position_index(ws).reshape(-1).to(self.device)
+        for i, (depth, heads) in enumerate(zip(S["depths"], S["heads"])):
+            dim = S["embed"] * 2 ** i
+            stg = NS(dim=dim, heads=heads, blocks=[], down=None, norm=self._norm(f"{p}norm{i}"))
+            for j in range(depth):
+                q = f"{p}layers.{i}.blocks.{j}."
+                b = NS(shift=0 if j % 2 == 0 else ws // 2)
+                b.norm1 = self._norm(q + "norm1")
+                b.qkv_w, b.qkv_b = self._lin(q + "attn.qkv")
+                table = sd[q + "attn.relative_position_bias_table"]                 # [(2ws-1)^2, heads]
+                b.relb = self._f(table[idx].view(ws * ws, ws * ws, heads).permute(2, 0, 1))
+                b.proj_w, b.proj_b = self._lin(q + "attn.proj")
+                b.norm2 = self._norm(q + "norm2")
+                b.fc1_w, b.fc1_b = self._lin(q + "mlp.fc1")
+                b.fc2_w, b.fc2_b = self._lin(q + "mlp.fc2")
+                stg.blocks.append(b)
+            q = f"{p}layers.{i}.downsample."
+            if (q + "reduction.weight") in sd:
+                w = self._reg(self._f(sd[q + "reduction.weight"].t()))
+                stg.down = NS(norm=self._norm(q + "norm"), w=w,
+                              b=torch.zeros(w.shape[1], dtype=torch.float32, device=self.device))   # bias=False :333
+            e.stages.append(stg)
+        return e
 
     # ------------------------------------------------------------------ AOT block
     def _lstt_layer(self, i):

@@ -91,6 +91,21 @@ int aotb_eltwise_f32(int op, const float* a, int lda, const float* b, int ldb, f
 int aotb_layernorm_f32(const float* x, int ldx, const float* gamma, const float* beta, const float* add,
                        int ldadd, float* out, int ldo, float* out2, int ldo2, int rows, int C, void* stream);
 
+/* Swin (shifted-)window multi-head self-attention core, batch 1 (BASELINE config 4 encoder):
+ * WindowAttention.forward networks/encoders/swin/swin_transformer.py:158-196 fused with the zero padding, cyclic
+ * shift, window partition / reverse and crop of SwinTransformerBlock.forward :273-316 and the shifted-window mask of
+ * BasicLayer.forward :416-438.  qkv [H*W][ldqkv] = the qkv Linear applied to the UN-padded norm1 output, columns
+ * [q(C) | k(C) | v(C)], head h = columns h*32..h*32+31 of each; qkv_bias [3C] stands in for padded positions (the
+ * reference pads after norm1, so a padded token's q/k/v are the bias); rel_bias [heads][49][49] =
+ * relative_position_bias_table[relative_position_index] permuted (:176-183); out [H*W][ldo] = softmax(q k^T / sqrt(32)
+ * + rel_bias + mask) v per head, heads concatenated, before `proj`.  window must be 7, C == heads * 32. */
+int aotb_window_attention_f32(const float* qkv, int ldqkv, const float* qkv_bias, const float* rel_bias, float* out,
+                              int ldo, int H, int W, int C, int heads, int window, int shift, void* stream);
+
+/* PatchMerging gather (swin_transformer.py:339-360): x [H*W][ldx] (C channels) -> out [ceil(H/2)*ceil(W/2)][ldo] with
+ * 4C channels ordered [(0,0) | (1,0) | (0,1) | (1,1)] of each 2x2 block, zeros outside H x W. */
+int aotb_patch_merge_f32(const float* x, int ldx, float* out, int ldo, int H, int W, int C, void* stream);
+
 /* nn.GroupNorm(G, C) over [B][P pixels][C] + activation: networks/layers/basic.py:6-12,18,30-32,75-85. */
 size_t aotb_groupnorm_workspace_bytes(int B, int G);
 int aotb_groupnorm_nhwc_f32(const float* x, int ldx, const float* gamma, const float* beta, float* out, int ldo,

@@ -51,6 +51,8 @@ class OracleConfig:
         "deaott": ("deaot", "mobilenetv2", [24, 32, 96, 1280], 1, True, 9999),  # configs/models/deaott.py
         "deaotl": ("deaot", "mobilenetv2", [24, 32, 96, 1280], 3, True, 5),     # configs/models/deaotl.py
         "r50_deaotl": ("deaot", "resnet50", [256, 512, 1024, 1024], 3, True, 5),  # configs/models/r50_deaotl.py
+        "swinb_aotl": ("aot", "swin_base", [128, 256, 512, 512], 3, False, 5),   # configs/models/swinb_aotl.py:9-18
+        "swinb_deaotl": ("deaot", "swin_base", [128, 256, 512, 512], 3, False, 5),  # configs/models/swinb_deaotl.py
     }
 
     def __init__(self, model: str = "r50_aotl"):
@@ -193,12 +195,107 @@ def mobilenetv2_forward(W: Dict[str, Tensor], img: Tensor, p: str = "encoder.") 
     return feats
 
 
+# Swin-B as build.py:11-22 instantiates it: embed 128, depths [2,2,18,(2)], heads [4,8,16,(32)], window 7,
+# ape=False, patch_norm=True, out_indices (0,1,2); the 4th stage is never built (swin_transformer.py:566).
+SWIN_BASE = {"embed": 128, "depths": (2, 2, 18), "heads": (4, 8, 16), "window": 7, "patch": 4}
+
+
+def swin_rel_index(ws: int) -> Tensor:
+    """swin_transformer.py:131-147: index into the (2ws-1)^2 bias table for every (query, key) pair."""
+    ys, xs = torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij")
+    y, x = ys.reshape(-1), xs.reshape(-1)
+    return (y[:, None] - y[None, :] + ws - 1) * (2 * ws - 1) + (x[:, None] - x[None, :] + ws - 1)
+
+
+def swin_shift_mask(Hp: int, Wp: int, ws: int, shift: int, dtype) -> Tensor:
+    """swin_transformer.py:416-438: region ids of the cyclically shifted padded map -> additive mask
+    [nW, ws*ws, ws*ws] with -100 between tokens of different regions."""
+    def band(n):
+        r = torch.zeros(n, dtype=torch.long)
+        r[n - ws:n - shift] = 1
+        r[n - shift:] = 2
+        return r
+    reg = band(Hp)[:, None] * 3 + band(Wp)[None, :]
+    reg = reg.view(Hp // ws, ws, Wp // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
+    diff = reg[:, None, :] != reg[:, :, None]
+    return torch.where(diff, torch.tensor(-100.0, dtype=dtype), torch.tensor(0.0, dtype=dtype))
+
+
+def swin_block(W: Dict[str, Tensor], p: str, x: Tensor, H: int, Wd: int, heads: int, ws: int, shift: int) -> Tensor:
+    """SwinTransformerBlock.forward swin_transformer.py:257-323 + WindowAttention.forward :158-196.
+    x [H*Wd, C] (batch 1).  Zero padding is applied AFTER norm1 (:273-278), so padded tokens carry the
+    qkv bias and take part in the softmax of their window."""
+    C = x.shape[1]
+    d = C // heads
+    y = _ln(x, W, p + "norm1").view(H, Wd, C)
+    pb, pr = (ws - H % ws) % ws, (ws - Wd % ws) % ws
+    y = F.pad(y, (0, 0, 0, pr, 0, pb))
+    Hp, Wp = H + pb, Wd + pr
+    if shift > 0:
+        y = torch.roll(y, shifts=(-shift, -shift), dims=(0, 1))
+    nwy, nwx = Hp // ws, Wp // ws
+    win = y.view(nwy, ws, nwx, ws, C).permute(0, 2, 1, 3, 4).reshape(nwy * nwx, ws * ws, C)
+    qkv = _lin(win, W, p + "attn.qkv").view(nwy * nwx, ws * ws, 3, heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0] * (d ** -0.5), qkv[1], qkv[2]
+    att = q @ k.transpose(-2, -1)                                              # [nW, heads, 49, 49]
+    table = W[p + "attn.relative_position_bias_table"]                          # [(2ws-1)^2, heads]
+    bias = table[swin_rel_index(ws).reshape(-1)].view(ws * ws, ws * ws, heads).permute(2, 0, 1)
+    att = att + bias.unsqueeze(0)
+    if shift > 0:
+        att = att + swin_shift_mask(Hp, Wp, ws, shift, att.dtype).unsqueeze(1)
+    att = torch.softmax(att, dim=-1)
+    o = (att @ v).transpose(1, 2).reshape(nwy * nwx, ws * ws, C)
+    o = _lin(o, W, p + "attn.proj")
+    o = o.view(nwy, nwx, ws, ws, C).permute(0, 2, 1, 3, 4).reshape(Hp, Wp, C)
+    if shift > 0:
+        o = torch.roll(o, shifts=(shift, shift), dims=(0, 1))
+    x = x + o[:H, :Wd].reshape(H * Wd, C)                                      # drop_path is identity in eval
+    m = _lin(F.gelu(_lin(_ln(x, W, p + "norm2"), W, p + "mlp.fc1")), W, p + "mlp.fc2")   # Mlp :41-63, exact GELU
+    return x + m
+
+
+def swin_patch_merge(W: Dict[str, Tensor], p: str, x: Tensor, H: int, Wd: int) -> Tensor:
+    """PatchMerging.forward swin_transformer.py:339-365: 2x2 neighbours concatenated in the order
+    (0,0), (1,0), (0,1), (1,1), LayerNorm(4C), bias-free Linear 4C -> 2C."""
+    C = x.shape[1]
+    y = F.pad(x.view(H, Wd, C), (0, 0, 0, Wd % 2, 0, H % 2))
+    y = torch.cat([y[0::2, 0::2], y[1::2, 0::2], y[0::2, 1::2], y[1::2, 1::2]], dim=-1)
+    y = _ln(y.reshape(-1, 4 * C), W, p + "norm")
+    return F.linear(y, W[p + "reduction.weight"])
+
+
+def swin_forward(W: Dict[str, Tensor], img: Tensor, p: str = "encoder.") -> List[Tensor]:
+    """SwinTransformer.forward swin_transformer.py:684-716 (+ PatchEmbed :473-489, BasicLayer :404-452) for
+    'swin_base' (build.py:11-22).  Returns [4x(128), 8x(256), 16x(512), 16x(512)] NCHW (last one repeated, :714)."""
+    S = SWIN_BASE
+    ps, ws = S["patch"], S["window"]
+    _, _, Hi, Wi = img.shape
+    img = F.pad(img, (0, (ps - Wi % ps) % ps, 0, (ps - Hi % ps) % ps))
+    x = F.conv2d(img, W[p + "patch_embed.proj.weight"], W[p + "patch_embed.proj.bias"], ps)
+    H, Wd = x.shape[2], x.shape[3]
+    x = x.flatten(2).transpose(1, 2)[0]                                        # [H*Wd, C]
+    x = _ln(x, W, p + "patch_embed.norm")
+    outs = []
+    for i, (depth, heads) in enumerate(zip(S["depths"], S["heads"])):
+        for j in range(depth):
+            x = swin_block(W, f"{p}layers.{i}.blocks.{j}.", x, H, Wd, heads, ws, 0 if j % 2 == 0 else ws // 2)
+        C = x.shape[1]
+        outs.append(_ln(x, W, f"{p}norm{i}").view(1, H, Wd, C).permute(0, 3, 1, 2).contiguous())
+        if i < len(S["depths"]) - 1:
+            x = swin_patch_merge(W, f"{p}layers.{i}.downsample.", x, H, Wd)
+            H, Wd = (H + 1) // 2, (Wd + 1) // 2
+    outs.append(outs[-1])
+    return outs
+
+
 def encode_image(W: Dict[str, Tensor], cfg, img: Tensor) -> List[Tensor]:
     # aot.py:81-84
     if cfg.MODEL_ENCODER == "resnet50":
         xs = resnet50_forward(W, img)
     elif cfg.MODEL_ENCODER == "mobilenetv2":
         xs = mobilenetv2_forward(W, img)
+    elif cfg.MODEL_ENCODER == "swin_base":
+        xs = swin_forward(W, img)
     else:
         raise NotImplementedError(cfg.MODEL_ENCODER)
     xs[-1] = F.conv2d(xs[-1], W["encoder_projector.weight"], W["encoder_projector.bias"])

@@ -50,6 +50,10 @@ VIDEO_CASES = {
     "r50_aotl_small": ("r50_aotl", 161, 241, 150, 230, 7, 10, 2, "calibrated"),
     "r50_deaotl_small": ("r50_deaotl", 161, 241, 150, 230, 7, 10, 2, "calibrated"),
     "deaott_small": ("deaott", 129, 177, 129, 177, 5, 4, 2, "calibrated"),
+    # Swin-B encoder (BASELINE configs[3]); align_corners=False models take multiples of 16 (video_transforms.py:649-655).
+    # 144x208 -> 36x52 / 18x26 / 9x13 maps: window padding and shifted-window masks at every stage
+    "swinb_aotl_small": ("swinb_aotl", 144, 208, 130, 200, 5, 6, 2, "calibrated"),
+    "swinb_deaotl_small": ("swinb_deaotl", 112, 176, 112, 176, 4, 3, 2, "calibrated"),
 }
 
 

@@ -21,7 +21,7 @@ import torch
 
 # fixed calibration constants (measured once in the build container through the oracle and
 # frozen here so weights do not depend on the machine): projector-output std under raw init
-_PROJ_STD = {"resnet50": 9.0, "mobilenetv2": 0.016}
+_PROJ_STD = {"resnet50": 9.0, "mobilenetv2": 0.016, "swin_base": 1.15}
 
 
 def build_state_dict(model_name: str, seed: int = 0, flavour: str = "calibrated",
@@ -44,6 +44,15 @@ def build_state_dict(model_name: str, seed: int = 0, flavour: str = "calibrated"
             sd[base + "running_mean"] = 0.1 * torch.randn(n, generator=g)
             sd[base + "weight"] = 0.9 + 0.2 * torch.rand(n, generator=g)
             sd[base + "bias"] = 0.05 * torch.randn(n, generator=g)
+    if cfg.MODEL_ENCODER == "swin_base":
+        # default nn.Linear init leaves window attention nearly uniform and the relative-position bias (std 0.02)
+        # invisible: sharpen q and enlarge the bias table so the bias / shifted-window-mask paths carry signal
+        for k in list(sd.keys()):
+            if k.endswith("attn.qkv.weight") or k.endswith("attn.qkv.bias"):
+                c = sd[k].shape[0] // 3
+                sd[k][:c] *= 6.0
+            elif k.endswith("relative_position_bias_table"):
+                sd[k] = sd[k] * 50.0
     s = 1.0 / _PROJ_STD[cfg.MODEL_ENCODER]
     sd["encoder_projector.weight"] = sd["encoder_projector.weight"] * s
     sd["encoder_projector.bias"] = sd["encoder_projector.bias"] * s

@@ -9,7 +9,8 @@ import torch.nn.functional as F
 from oracle import aot_oracle as O
 from oracle import weights as OW
 
-VIDEO = ["aott_256", "aott_raw_257", "r50_aotl_small", "r50_deaotl_small", "deaott_small"]
+VIDEO = ["aott_256", "aott_raw_257", "r50_aotl_small", "r50_deaotl_small", "deaott_small", "swinb_aotl_small",
+         "swinb_deaotl_small"]
 
 
 @pytest.fixture(scope="module")
@@ -124,7 +125,7 @@ T.MultiheadLocalAttentionV3 = A.MultiheadLocalAttentionV2
 from configs.default import DefaultEngineConfig
 from networks.models import build_vos_model as ref_build
 from aot_benchmark_b200 import build_vos_model, EngineConfig
-for m in ["aott", "r50_aotl", "deaott", "r50_deaotl"]:
+for m in ["aott", "r50_aotl", "deaott", "r50_deaotl", "swinb_aotl", "swinb_deaotl"]:
     rc = DefaultEngineConfig("x", m); mc = EngineConfig("x", m)
     a = {k: tuple(v.shape) for k, v in ref_build(rc.MODEL_VOS, rc).state_dict().items()}
     b = {k: tuple(v.shape) for k, v in build_vos_model(mc.MODEL_VOS, mc).state_dict().items()}
