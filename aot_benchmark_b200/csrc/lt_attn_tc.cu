@@ -117,7 +117,20 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                  : "memory");
 }
 
-template <bool EXACT>
+// tcgen05.wait::ld that also names the registers an earlier, still in-flight tcgen05.ld writes: the "+r" ties make every
+// later use of them depend on this statement, so the compiler cannot hoist arithmetic on the prefetched scores above
+// the wait (tcgen05.ld results are not scoreboarded; they are defined only after wait::ld).
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+template <bool EXACT, bool PIPE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const LtArgs a) {
@@ -232,6 +245,96 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
         float m_used[2] = {-INFINITY, -INFINITY}, l0[2] = {0.f, 0.f}, l1[2] = {0.f, 0.f};
 
+        if constexpr (PIPE) {
+            // Software-pipelined variant: the (asynchronous) tcgen05.ld of the NEXT score tile -- the other query tile,
+            // whose S MMAs were issued one step ahead -- is started before the ex2 pass of the current tile and
+            // completed after it, so the TMEM read port (64 B/clk: 1024 clk per 128x128 tile) works in the shadow of
+            // the MUFU pass (16 ex2/clk: 1024 clk per tile) instead of in series with it.  Scores alternate between
+            // the register sets srA (query tile 0) and srB (query tile 1); P is produced 16 keys at a time to keep both
+            // sets plus the packed halves inside the 112-register budget of a 576-thread CTA.
+            uint32_t srA[32], srB[32];
+            auto tile = [&](uint32_t (&sr)[32], uint32_t (&srn)[32], const int i, const int j, const bool has_next,
+                            const uint32_t next_parity) {
+                const uint32_t tS = tmem + lane_addr + i * 128 + qt * 32;
+                const uint32_t tO = tmem + lane_addr + 256 + i * 64 + qt * 16;
+                const uint32_t tPl = tmem + lane_addr + 384 + i * 64 + qt * 16;
+                const int key0 = (tb + j) * BN + qt * 32;
+                if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i == 0 && j == 0) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) a.dbg[row * 128 + qt * 32 + k] = __uint_as_float(sr[k]);
+                }
+                if (key0 + 32 > Tk) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (key0 + k >= Tk) sr[k] = __float_as_uint(-INFINITY);
+                }
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < 32; k += 2) {
+                    mx0 = fmaxf(mx0, __uint_as_float(sr[k]));
+                    mx1 = fmaxf(mx1, __uint_as_float(sr[k + 1]));
+                }
+                B->xmax[i][qt][row] = fmaxf(mx0, mx1);
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                const float mt = fmaxf(fmaxf(B->xmax[i][0][row], B->xmax[i][1][row]),
+                                       fmaxf(B->xmax[i][2][row], B->xmax[i][3][row]));
+                const float m_new = fmaxf(m_used[i], mt);
+                const bool grow = (m_new > m_used[i]) && (j > 0);
+                if (__any_sync(0xffffffffu, grow)) {
+                    const float f = grow ? ex2((m_used[i] - m_new) * LOG2E) : 1.f;
+                    uint32_t orr[16];
+                    tmem_ld16(tO, orr);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) orr[k] = __float_as_uint(__uint_as_float(orr[k]) * f);
+                    tmem_st16(tO, orr);
+                    l0[i] *= f; l1[i] *= f;
+                }
+                m_used[i] = m_new;
+                const float neg = m_new * LOG2E;
+                const uint32_t tSn = tmem + lane_addr + (1 - i) * 128 + qt * 32;
+                if (has_next) {                 // start reading the other query tile's scores (its MMAs were issued earlier)
+                    mbar_wait(&B->s_full[1 - i], next_parity);
+                    tc_fence_after();
+                    tmem_ld16(tSn, srn);        // first half now; second half once sr[0..15] are dead (register budget)
+                }
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    if (hf == 1 && has_next) tmem_ld16(tSn + 16, srn + 16);
+                    uint32_t ph[8], pl[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const float p0 = ex2(fmaf(__uint_as_float(sr[16 * hf + 2 * t]), LOG2E, -neg));
+                        const float p1 = ex2(fmaf(__uint_as_float(sr[16 * hf + 2 * t + 1]), LOG2E, -neg));
+                        s0 += p0; s1 += p1;
+                        const __half2 hi = __floats2half2_rn(p0, p1);
+                        ph[t] = *reinterpret_cast<const uint32_t*>(&hi);
+                        if (EXACT) {
+                            const __half2 lo = __floats2half2_rn(p0 - __low2float(hi), p1 - __high2float(hi));
+                            pl[t] = *reinterpret_cast<const uint32_t*>(&lo);
+                        }
+                    }
+                    tmem_st8(tS + 8 * hf, ph);          // keys [32 qt + 16 hf, +16) -> S columns [32 qt + 8 hf, +8)
+                    if (EXACT) tmem_st8(tPl + 8 * hf, pl);
+                }
+                l0[i] += s0; l1[i] += s1;
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&B->p_full[i]);
+                if (has_next) tmem_wait_ld32(srn);
+            };
+            if (T > 0) {
+                mbar_wait(&B->s_full[0], 0);
+                tc_fence_after();
+                tmem_ld32(tmem + lane_addr + qt * 32, srA);
+                tmem_wait_ld32(srA);
+            }
+            for (int j = 0; j < T; ++j) {
+                tile(srA, srB, 0, j, true, (uint32_t)(j & 1));
+                tile(srB, srA, 1, j, j + 1 < T, (uint32_t)((j + 1) & 1));
+            }
+        } else {
         for (int j = 0; j < T; ++j) {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -305,6 +408,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 mbar_arrive(&B->p_full[i]);
             }
         }
+        }   // !PIPE
 
         // ---- epilogue: per tile, this thread finishes output channels [8*qt, 8*qt+8) of its row
 #pragma unroll
@@ -429,9 +533,13 @@ extern "C" int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp,
     const size_t smem = aotb_lt_attn_tc_smem_bytes();
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::lt_attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc::lt_attn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(tc::lt_attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(tc::lt_attn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc::lt_attn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc::lt_attn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("aotb_lt_attn_tc_f16x2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return AOTB_ERR_CUDA;
@@ -440,9 +548,15 @@ extern "C" int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp,
     }
     tc::LtArgs a;
     a.N = N; a.Tk = Tk; a.Tk_dev = Tk_dev; a.H = H; a.O = O; a.ldo = ldo;
-    a.Opart = Opart; a.Mpart = Mpart; a.Lpart = Lpart; a.splits = splits; a.exact = exact; a.dbg = dbg;
+    a.Opart = Opart; a.Mpart = Mpart; a.Lpart = Lpart; a.splits = splits; a.exact = exact & 1; a.dbg = dbg;
     dim3 grid(cdiv(N, 2 * tc::BM), H, splits);
-    if (exact) launch(tc::lt_attn_tc_kernel<true>, dim3(grid), dim3(tc::NTHREADS), smem, (cudaStream_t)stream, tq, tk, tv, a);
-    else launch(tc::lt_attn_tc_kernel<false>, dim3(grid), dim3(tc::NTHREADS), smem, (cudaStream_t)stream, tq, tk, tv, a);
+    const dim3 block(tc::NTHREADS);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (exact & 3) {      // bit 0: fp16x2 "exact" operands; bit 1: software-pipelined TMEM reads
+        case 3: launch(tc::lt_attn_tc_kernel<true, true>, dim3(grid), block, smem, st, tq, tk, tv, a); break;
+        case 2: launch(tc::lt_attn_tc_kernel<false, true>, dim3(grid), block, smem, st, tq, tk, tv, a); break;
+        case 1: launch(tc::lt_attn_tc_kernel<true, false>, dim3(grid), block, smem, st, tq, tk, tv, a); break;
+        default: launch(tc::lt_attn_tc_kernel<false, false>, dim3(grid), block, smem, st, tq, tk, tv, a);
+    }
     return check_launch("aotb_lt_attn_tc_f16x2");
 }

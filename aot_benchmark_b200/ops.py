@@ -340,10 +340,17 @@ def tc_pack_rows(src, dst, row_off=0, div=1.0, row_off_dev=None, stream=None):
     return dst
 
 
+# software-pipelined softmax of the tensor-core attention kernel (TMEM read of the next score tile under the ex2 pass
+# of the current one): same arithmetic and results as the serial variant
+LT_PIPE = os.environ.get("AOTB_LT_PIPE", "0") == "1"
+
+
 def lt_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True, part=None, dbg=None, stream=None,
-                    merge=True):
+                    merge=True, pipe=None):
     """Qp [H, Nq_cap, 64], Kp/Vp [H, kv_cap, 64] packed fp16x2; O [N, H*32] fp32.
-    With splits > 1, `part` = (Opart [S,N,H*32], Mpart [S,H,N], Lpart [S,H,N]) and O receives the merge."""
+    With splits > 1, `part` = (Opart [S,N,H*32], Mpart [S,H,N], Lpart [S,H,N]) and O receives the merge.
+    `pipe` (default: AOTB_LT_PIPE) selects the software-pipelined softmax variant."""
+    mode = (1 if exact else 0) | (2 if (LT_PIPE if pipe is None else pipe) else 0)
     H, nq_cap, _ = Qp.shape
     kv_cap = Kp.shape[1]
     if splits > 1:
@@ -353,7 +360,7 @@ def lt_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True
     check(lib().aotb_lt_attn_tc_f16x2(Qp.data_ptr(), nq_cap, Kp.data_ptr(), Vp.data_ptr(), kv_cap, N, int(Tk),
                                       Tk_dev.data_ptr() if Tk_dev is not None else None, H,
                                       _p(O) if splits == 1 else None, O.stride(0) if O is not None else 0,
-                                      _p(Op), _p(Mp), _p(Lp), splits, 1 if exact else 0, _p(dbg), _st(stream)),
+                                      _p(Op), _p(Mp), _p(Lp), splits, mode, _p(dbg), _st(stream)),
           "aotb_lt_attn_tc_f16x2")
     if splits > 1 and merge:
         attn_merge(Op, Mp, Lp, O, H, 32, stream=stream)

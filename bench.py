@@ -37,6 +37,14 @@ import torch.nn.functional as F  # noqa: E402
 H_IN, W_IN, H_OUT, W_OUT, OBJS = 481, 849, 480, 854, 10   # what MultiRestrictSize makes of 480x854
 
 
+def set_workload(model_name):
+    """Network input size per model family: align_corners models get (k*16+1) sizes -- 481x849 for 480p --
+    and the Swin models (align_corners=False, BASELINE configs[3]) multiples of 16 at 1.3 x 480p = 592x1040."""
+    global H_IN, W_IN
+    if model_name.startswith("swinb"):
+        H_IN, W_IN = 592, 1040
+
+
 def _peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -225,7 +233,7 @@ def run_ours(args):
         "metric": "frames/sec (480p, 10 obj)", "value": round(fps, 3), "unit": "frames/s", "n_gpus": world,
         "steps": K, "warmup": Wm, "ms_per_step": round(ms_value / K, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} inference, synthetic 480p clip (net input {H_IN}x{W_IN}, output "
+        "config": {"workload": f"{args.model} inference, synthetic {'1.3x480p' if H_IN > 481 else '480p'} clip (net input {H_IN}x{W_IN}, output "
                                f"{H_OUT}x{W_OUT}), {OBJS} objects, 1 reference + {K} propagated frames, long-term gap "
                                f"{cfg.TEST_LONG_TERM_MEM_GAP}, batch 1/GPU, one clip per GPU",
                    "weights": "seeded random init (no checkpoints offline)",
@@ -241,12 +249,12 @@ def run_ours(args):
                      "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": traffic_note,
                      "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({how})",
                      "launches": len(eng_probe), "avg_launch_us": round(1e3 * lt_ms / max(len(eng_probe), 1), 2),
-                     "algorithmic": "FLOPs = 4*N*Tk*C per launch (N=1674, C=256, Tk=1674*m)" if cfg.MODEL_VOS == "aot"
-                     else "FLOPs = 2*N*Tk*(128+1024) per launch (N=1674, Tk=1674*m)",
+                     "algorithmic": f"FLOPs = 4*N*Tk*C per launch (N={e0().enc_hw}, C=256, Tk={e0().enc_hw}*m)"
+                     if cfg.MODEL_VOS == "aot" else f"FLOPs = 2*N*Tk*(128+1024) per launch (N={e0().enc_hw}, Tk={e0().enc_hw}*m)",
                      "timing": "CUDA events around every launch in an eager (graph-free) probe pass of the same clip"},
         "clocks": clocks,
     }
-    out["cpu_baseline"] = cpu_baseline(args.model, threads=os.cpu_count())
+    out["cpu_baseline"] = None if args.skip_cpu_baseline else cpu_baseline(args.model, threads=os.cpu_count())
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -351,7 +359,7 @@ def run_reference(args):
         "impl": "reference", "metric": "frames/sec (480p, 10 obj)", "value": round(fps, 4), "unit": "frames/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(1e3 / fps, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} inference, synthetic 480p clip (net input {H_IN}x{W_IN}, output "
+        "config": {"workload": f"{args.model} inference, synthetic {'1.3x480p' if H_IN > 481 else '480p'} clip (net input {H_IN}x{W_IN}, output "
                                f"{H_OUT}x{W_OUT}), {OBJS} objects, 1 reference + {K} propagated frames, long-term gap "
                                f"{cfg.TEST_LONG_TERM_MEM_GAP}, batch 1",
                    "weights": "seeded random init"},
@@ -368,7 +376,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="r50_aotl")
+    ap.add_argument("--skip-cpu-baseline", action="store_true",
+                    help="development only: omit the cpu_baseline leg (the driver's default run keeps it)")
     args = ap.parse_args()
+    set_workload(args.model)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -105,6 +105,48 @@ def test_lt_attention_tc_matches_simt_and_splits():
     assert (O4 - ref).abs().max().item() < 1e-4
 
 
+def _pipe_enabled():
+    import os
+    from aot_benchmark_b200 import ops
+    return ops.LT_PIPE or os.environ.get("AOTB_TEST_PIPE", "0") == "1"
+
+
+@pytest.mark.parametrize("N,Tk,splits,exact", [(128, 128, 1, True), (300, 700, 1, True), (1674, 5022 + 77, 1, True),
+                                               (1674, 1674 * 7, 5, True), (200, 300, 8, True), (300, 700, 1, False),
+                                               (1674, 1674 * 3 + 5, 3, False)])
+def test_lt_attention_tc_pipelined_softmax_is_bit_identical(N, Tk, splits, exact):
+    """The software-pipelined softmax (TMEM prefetch of the next score tile) performs the same operations in the same
+    order per thread as the serial variant: outputs (and split partials) must be bit-identical."""
+    if not _pipe_enabled():
+        pytest.skip("pipelined variant not enabled (AOTB_LT_PIPE=1 or AOTB_TEST_PIPE=1)")
+    from aot_benchmark_b200 import ops
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(N * 7 + Tk)
+    Q = (torch.randn(N, 256, generator=g) * 3).to(d)
+    K = torch.randn(Tk, 256, generator=g).to(d)
+    V = torch.randn(Tk, 256, generator=g).to(d)
+    ncap = ((N + 255) // 256) * 256
+    kcap = ((Tk + 127) // 128) * 128 + 128
+    Qp, Kp, Vp = _pack(Q, ncap, math.sqrt(32.0)), _pack(K, kcap), _pack(V, kcap)
+    outs = []
+    for pipe in (False, True):
+        part = None
+        if splits > 1:
+            part = (torch.zeros(splits, N, 256, device=d), torch.zeros(splits, H, N, device=d),
+                    torch.zeros(splits, H, N, device=d))
+        O = torch.full((N, 256), float("nan"), device=d)
+        ops.lt_attention_tc(Qp, Kp, Vp, N, Tk, O=O, splits=splits, exact=exact, part=part, pipe=pipe)
+        torch.cuda.synchronize()
+        outs.append((O, part))
+    assert torch.isfinite(outs[1][0]).all()
+    assert torch.equal(outs[0][0], outs[1][0])
+    if splits > 1:
+        for a, b in zip(outs[0][1], outs[1][1]):
+            assert torch.equal(a, b)
+    ref = _ref(Q, K, V)
+    assert (outs[1][0].cpu().double() - ref).abs().max().item() < (2e-4 if exact else 5e-2)
+
+
 def _pack_w(w):  # [Cout,Cin,KH,KW] -> fp32 [K, Cout] (k = (ky,kx,ci))
     co, ci, kh, kw = w.shape
     return w.permute(2, 3, 1, 0).reshape(kh * kw * ci, co).contiguous()

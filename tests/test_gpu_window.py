@@ -56,7 +56,7 @@ def test_window_attention_kernel(H, W, heads, shift):
     ops.window_attention(qkv, qkv_b.cuda(), relb, out, H, W, heads, shift)
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()                      # every un-padded token is written exactly once
-    assert (out.cpu() - want).abs().max().item() < 2e-5 * max(1.0, want.abs().max().item())
+    assert (out.cpu() - want).abs().max().item() < 1e-4 * max(1.0, want.abs().max().item())
 
 
 def test_window_attention_rejects_other_geometries():
