@@ -84,8 +84,11 @@ struct __align__(8) Barriers {
     uint64_t p_full[2];
     uint64_t o_final[2];
     uint32_t tmem_base;
-    float xmax[2][4][BM];       // [tile parity][column quarter][row]: quarter-row maxima
-    float xsum[2][4][BM];       // [tile][column quarter][row]: quarter-row sums (epilogue)
+    // partial row maxima / sums exchanged between the threads that share a query row:
+    //   one-tile layout  (4 threads per row): xmax[tile parity * 4 + column quarter], xsum[tile * 4 + column quarter]
+    //   two-group layout (2 threads per row): xmax[((j & 1) * 2 + group) * 2 + half], xsum[group * 2 + half]
+    float xmax[8][BM];
+    float xsum[8][BM];
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
@@ -117,20 +120,7 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                  : "memory");
 }
 
-// tcgen05.wait::ld that also names the registers an earlier, still in-flight tcgen05.ld writes: the "+r" ties make every
-// later use of them depend on this statement, so the compiler cannot hoist arithmetic on the prefetched scores above
-// the wait (tcgen05.ld results are not scoreboarded; they are defined only after wait::ld).
-__device__ __forceinline__ void tmem_wait_ld32(uint32_t* r) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
-}
-
-template <bool EXACT, bool PIPE>
+template <bool EXACT, bool GROUPS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const LtArgs a) {
@@ -149,7 +139,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (tid == 0) {
         mbar_init(&B->q_full, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&B->kv_full[s], 1); mbar_init(&B->kv_free[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&B->s_full[i], 1); mbar_init(&B->p_full[i], 4 * BM); mbar_init(&B->o_final[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&B->s_full[i], 1); mbar_init(&B->p_full[i], GROUPS ? 2 * BM : 4 * BM); mbar_init(&B->o_final[i], 1); }
         fence_mbar_init();
     }
     if (warp == MMA_WARP) tmem_alloc<512>(&B->tmem_base);
@@ -208,8 +198,12 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 const uint32_t d = tmem + 256 + i * 64;
                 const uint32_t p = tmem + i * 128;
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk)       // P_hi of keys [32t, 32t+32) sits at columns [32t, 32t+16)
-                    mma_ts(d, p + 32 * (kk >> 1) + 8 * (kk & 1), v + 128 * kk, IDESC_O, (kk > 0) ? 1u : acc);
+                for (int kk = 0; kk < 8; ++kk) {
+                    // one-tile layout : P_hi of keys [32t, 32t+32) sits at columns [32t, 32t+16)
+                    // two-group layout: P_hi of keys [0,64) at columns [0,32), keys [64,128) at [64,96)
+                    const uint32_t pc = GROUPS ? 8 * kk + (kk >= 4 ? 32 : 0) : 32 * (kk >> 1) + 8 * (kk & 1);
+                    mma_ts(d, p + pc, v + 128 * kk, IDESC_O, (kk > 0) ? 1u : acc);
+                }
                 if (EXACT) {
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) mma_ts(d, tmem + 384 + i * 64 + 8 * kk, v + 128 * kk, IDESC_O, 1);
@@ -238,6 +232,141 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 }
             }
         }
+    } else if constexpr (GROUPS) {
+        // ======================= softmax, two-group layout =======================
+        // Warps 0-7 own query tile 0 (S_0, O_0), warps 8-15 query tile 1; inside a group warp w owns TMEM lanes
+        // 32(w%4)..+31 and the key half (w/4)%2, i.e. two threads share a row and each keeps its 64 scores of a tile in
+        // registers: ONE tcgen05.ld pass per tile (the earlier two-group kernel re-read every tile for the exp pass).
+        // The groups run out of phase -- S_1 is issued ~900 cycles after S_0 -- so while one group is on the TMEM read
+        // port (64 B/clk: 1024 clk per 128x128 tile) the other is on the MUFU pipe (16 ex2/clk: 1024 clk per tile)
+        // instead of all 16 warps queuing on the same resource in lockstep.
+        const int wg = warp >> 3, half = (warp >> 2) & 1, wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const uint32_t tS = tmem + lane_addr + wg * 128 + half * 64;      // this thread's 64 score columns
+        const uint32_t tO = tmem + lane_addr + 256 + wg * 64;
+        const uint32_t tPl = tmem + lane_addr + 384 + wg * 64 + half * 32;
+        const int q = q0 + wg * BM + row;
+        const bool dump = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && wg == 0;
+        float m_used = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+        for (int j = 0; j < T; ++j) {
+            mbar_wait(&B->s_full[wg], j & 1);
+            tc_fence_after();
+            const int key0 = (tb + j) * BN + half * 64;
+            uint32_t sr[64];
+            tmem_ld32(tS + 0, sr);
+            tmem_ld32(tS + 32, sr + 32);
+            tmem_wait_ld();
+            if (dump && j == 0) {
+#pragma unroll
+                for (int k = 0; k < 64; ++k) a.dbg[row * 128 + half * 64 + k] = __uint_as_float(sr[k]);
+            }
+            if (key0 + 64 > Tk) {                    // warp-uniform: only the last key tile of the bank is ragged
+#pragma unroll
+                for (int k = 0; k < 64; ++k)
+                    if (key0 + k >= Tk) sr[k] = __float_as_uint(-INFINITY);
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 64; k += 2) {
+                mx0 = fmaxf(mx0, __uint_as_float(sr[k]));
+                mx1 = fmaxf(mx1, __uint_as_float(sr[k + 1]));
+            }
+            float mt = fmaxf(mx0, mx1);
+            const int xb = ((j & 1) * 2 + wg) * 2;
+            B->xmax[xb + half][row] = mt;
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + wg) : "memory");       // the 8 warps of this group
+            mt = fmaxf(mt, B->xmax[xb + (half ^ 1)][row]);
+            const float m_new = fmaxf(m_used, mt);
+            const bool grow = (m_new > m_used) && (j > 0);
+            if (__any_sync(0xffffffffu, grow)) {
+                // rescale the running output of this warp's rows -- this thread's 32 of the 64 O' columns -- and its sum
+                // (O_i is quiescent here: every MMA issued before S_i(j) has completed, PV_i(j) is not issued until
+                // all 256 threads of the group arrive on p_full)
+                const float f = grow ? ex2((m_used - m_new) * LOG2E) : 1.f;
+                uint32_t orr[16];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    tmem_ld16(tO + half * 32 + 16 * c, orr);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) orr[k] = __float_as_uint(__uint_as_float(orr[k]) * f);
+                    tmem_st16(tO + half * 32 + 16 * c, orr);
+                }
+                l0 *= f; l1 *= f;
+            }
+            m_used = m_new;
+            const float neg = m_used * LOG2E;
+            // p = 2^(s*log2e - m*log2e), partial row sum, fp16 hi / lo split, back into TMEM 16 keys at a time.  P_hi of
+            // chunk c lands on columns [8c, 8c+8) of this thread's own S columns (all 64 scores are in registers).
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const float p0 = ex2(fmaf(__uint_as_float(sr[16 * c + 2 * t]), LOG2E, -neg));
+                    const float p1 = ex2(fmaf(__uint_as_float(sr[16 * c + 2 * t + 1]), LOG2E, -neg));
+                    l0 += p0; l1 += p1;
+                    const __half2 hi = __floats2half2_rn(p0, p1);
+                    ph[t] = *reinterpret_cast<const uint32_t*>(&hi);
+                    if (EXACT) {
+                        const __half2 lo = __floats2half2_rn(p0 - __low2float(hi), p1 - __high2float(hi));
+                        pl[t] = *reinterpret_cast<const uint32_t*>(&lo);
+                    }
+                }
+                tmem_st8(tS + 8 * c, ph);
+                if (EXACT) tmem_st8(tPl + 8 * c, pl);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&B->p_full[wg]);
+        }
+
+        // ---- epilogue: this thread finishes output channels [16*half, 16*half+16) of its row
+        float l = l0 + l1;
+        B->xsum[wg * 2 + half][row] = l;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + wg) : "memory");
+        l = B->xsum[wg * 2 + 0][row] + B->xsum[wg * 2 + 1][row];          // same order in both threads of the row
+        float o[16];
+        if (T > 0) {
+            mbar_wait(&B->o_final[wg], 0);
+            tc_fence_after();
+            uint32_t o0[16], o1[16];
+            tmem_ld16(tO + half * 16, o0);
+            tmem_ld16(tO + 32 + half * 16, o1);
+            tmem_wait_ld();
+            if (dump) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    a.dbg[128 * 128 + row * 64 + half * 16 + k] = __uint_as_float(o0[k]);
+                    a.dbg[128 * 128 + row * 64 + 32 + half * 16 + k] = __uint_as_float(o1[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = __uint_as_float(o0[k]) + __uint_as_float(o1[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = 0.f;
+        }
+        if (q < a.N) {
+            if (a.splits == 1) {
+                const float inv = 1.f / l;
+                float* dst = a.O + (size_t)q * a.ldo + h * 32 + half * 16;
+#pragma unroll
+                for (int k = 0; k < 16; k += 4)
+                    *reinterpret_cast<float4*>(dst + k) = make_float4(o[k] * inv, o[k + 1] * inv, o[k + 2] * inv, o[k + 3] * inv);
+            } else {
+                float* dst = a.Opart + ((size_t)z * a.N + q) * (a.H * 32) + h * 32 + half * 16;
+#pragma unroll
+                for (int k = 0; k < 16; k += 4)
+                    *reinterpret_cast<float4*>(dst + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+                if (half == 0) {
+                    a.Mpart[((size_t)z * a.H + h) * a.N + q] = m_used;
+                    a.Lpart[((size_t)z * a.H + h) * a.N + q] = l;
+                }
+            }
+        }
     } else {
         // ======================= softmax (16 warps, one score tile at a time) =======================
         const int qt = warp >> 2, wq = warp & 3;           // column quarter, TMEM lane quadrant
@@ -245,96 +374,6 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
         float m_used[2] = {-INFINITY, -INFINITY}, l0[2] = {0.f, 0.f}, l1[2] = {0.f, 0.f};
 
-        if constexpr (PIPE) {
-            // Software-pipelined variant: the (asynchronous) tcgen05.ld of the NEXT score tile -- the other query tile,
-            // whose S MMAs were issued one step ahead -- is started before the ex2 pass of the current tile and
-            // completed after it, so the TMEM read port (64 B/clk: 1024 clk per 128x128 tile) works in the shadow of
-            // the MUFU pass (16 ex2/clk: 1024 clk per tile) instead of in series with it.  Scores alternate between
-            // the register sets srA (query tile 0) and srB (query tile 1); P is produced 16 keys at a time to keep both
-            // sets plus the packed halves inside the 112-register budget of a 576-thread CTA.
-            uint32_t srA[32], srB[32];
-            auto tile = [&](uint32_t (&sr)[32], uint32_t (&srn)[32], const int i, const int j, const bool has_next,
-                            const uint32_t next_parity) {
-                const uint32_t tS = tmem + lane_addr + i * 128 + qt * 32;
-                const uint32_t tO = tmem + lane_addr + 256 + i * 64 + qt * 16;
-                const uint32_t tPl = tmem + lane_addr + 384 + i * 64 + qt * 16;
-                const int key0 = (tb + j) * BN + qt * 32;
-                if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i == 0 && j == 0) {
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) a.dbg[row * 128 + qt * 32 + k] = __uint_as_float(sr[k]);
-                }
-                if (key0 + 32 > Tk) {
-#pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        if (key0 + k >= Tk) sr[k] = __float_as_uint(-INFINITY);
-                }
-                float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-                for (int k = 0; k < 32; k += 2) {
-                    mx0 = fmaxf(mx0, __uint_as_float(sr[k]));
-                    mx1 = fmaxf(mx1, __uint_as_float(sr[k + 1]));
-                }
-                B->xmax[i][qt][row] = fmaxf(mx0, mx1);
-                asm volatile("bar.sync 1, 512;" ::: "memory");
-                const float mt = fmaxf(fmaxf(B->xmax[i][0][row], B->xmax[i][1][row]),
-                                       fmaxf(B->xmax[i][2][row], B->xmax[i][3][row]));
-                const float m_new = fmaxf(m_used[i], mt);
-                const bool grow = (m_new > m_used[i]) && (j > 0);
-                if (__any_sync(0xffffffffu, grow)) {
-                    const float f = grow ? ex2((m_used[i] - m_new) * LOG2E) : 1.f;
-                    uint32_t orr[16];
-                    tmem_ld16(tO, orr);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) orr[k] = __float_as_uint(__uint_as_float(orr[k]) * f);
-                    tmem_st16(tO, orr);
-                    l0[i] *= f; l1[i] *= f;
-                }
-                m_used[i] = m_new;
-                const float neg = m_new * LOG2E;
-                const uint32_t tSn = tmem + lane_addr + (1 - i) * 128 + qt * 32;
-                if (has_next) {                 // start reading the other query tile's scores (its MMAs were issued earlier)
-                    mbar_wait(&B->s_full[1 - i], next_parity);
-                    tc_fence_after();
-                    tmem_ld16(tSn, srn);        // first half now; second half once sr[0..15] are dead (register budget)
-                }
-                float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    if (hf == 1 && has_next) tmem_ld16(tSn + 16, srn + 16);
-                    uint32_t ph[8], pl[8];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const float p0 = ex2(fmaf(__uint_as_float(sr[16 * hf + 2 * t]), LOG2E, -neg));
-                        const float p1 = ex2(fmaf(__uint_as_float(sr[16 * hf + 2 * t + 1]), LOG2E, -neg));
-                        s0 += p0; s1 += p1;
-                        const __half2 hi = __floats2half2_rn(p0, p1);
-                        ph[t] = *reinterpret_cast<const uint32_t*>(&hi);
-                        if (EXACT) {
-                            const __half2 lo = __floats2half2_rn(p0 - __low2float(hi), p1 - __high2float(hi));
-                            pl[t] = *reinterpret_cast<const uint32_t*>(&lo);
-                        }
-                    }
-                    tmem_st8(tS + 8 * hf, ph);          // keys [32 qt + 16 hf, +16) -> S columns [32 qt + 8 hf, +8)
-                    if (EXACT) tmem_st8(tPl + 8 * hf, pl);
-                }
-                l0[i] += s0; l1[i] += s1;
-                tmem_wait_st();
-                tc_fence_before();
-                mbar_arrive(&B->p_full[i]);
-                if (has_next) tmem_wait_ld32(srn);
-            };
-            if (T > 0) {
-                mbar_wait(&B->s_full[0], 0);
-                tc_fence_after();
-                tmem_ld32(tmem + lane_addr + qt * 32, srA);
-                tmem_wait_ld32(srA);
-            }
-            for (int j = 0; j < T; ++j) {
-                tile(srA, srB, 0, j, true, (uint32_t)(j & 1));
-                tile(srB, srA, 1, j, j + 1 < T, (uint32_t)((j + 1) & 1));
-            }
-        } else {
         for (int j = 0; j < T; ++j) {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -364,10 +403,10 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     mx1 = fmaxf(mx1, __uint_as_float(sr[k + 1]));
                 }
                 const int par = i;                        // tiles alternate 0,1,0,1: the tile index is its own parity
-                B->xmax[par][qt][row] = fmaxf(mx0, mx1);
+                B->xmax[par * 4 + qt][row] = fmaxf(mx0, mx1);
                 asm volatile("bar.sync 1, 512;" ::: "memory");                    // the 16 softmax warps
-                const float mt = fmaxf(fmaxf(B->xmax[par][0][row], B->xmax[par][1][row]),
-                                       fmaxf(B->xmax[par][2][row], B->xmax[par][3][row]));
+                const float mt = fmaxf(fmaxf(B->xmax[par * 4 + 0][row], B->xmax[par * 4 + 1][row]),
+                                       fmaxf(B->xmax[par * 4 + 2][row], B->xmax[par * 4 + 3][row]));
                 const float m_new = fmaxf(m_used[i], mt);
                 const bool grow = (m_new > m_used[i]) && (j > 0);
                 if (__any_sync(0xffffffffu, grow)) {
@@ -408,15 +447,14 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 mbar_arrive(&B->p_full[i]);
             }
         }
-        }   // !PIPE
 
         // ---- epilogue: per tile, this thread finishes output channels [8*qt, 8*qt+8) of its row
 #pragma unroll
-        for (int i = 0; i < 2; ++i) B->xsum[i][qt][row] = l0[i] + l1[i];
+        for (int i = 0; i < 2; ++i) B->xsum[i * 4 + qt][row] = l0[i] + l1[i];
         asm volatile("bar.sync 1, 512;" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const float l = (B->xsum[i][0][row] + B->xsum[i][1][row]) + (B->xsum[i][2][row] + B->xsum[i][3][row]);
+            const float l = (B->xsum[i * 4 + 0][row] + B->xsum[i * 4 + 1][row]) + (B->xsum[i * 4 + 2][row] + B->xsum[i * 4 + 3][row]);
             const uint32_t tO = tmem + lane_addr + 256 + i * 64;
             const bool dump = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i == 0;
             const int q = q0 + i * BM + row;
@@ -552,7 +590,7 @@ extern "C" int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp,
     dim3 grid(cdiv(N, 2 * tc::BM), H, splits);
     const dim3 block(tc::NTHREADS);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (exact & 3) {      // bit 0: fp16x2 "exact" operands; bit 1: software-pipelined TMEM reads
+    switch (exact & 3) {      // bit 0: fp16x2 "exact" operands; bit 1: two-group softmax layout
         case 3: launch(tc::lt_attn_tc_kernel<true, true>, dim3(grid), block, smem, st, tq, tk, tv, a); break;
         case 2: launch(tc::lt_attn_tc_kernel<false, true>, dim3(grid), block, smem, st, tq, tk, tv, a); break;
         case 1: launch(tc::lt_attn_tc_kernel<true, false>, dim3(grid), block, smem, st, tq, tk, tv, a); break;

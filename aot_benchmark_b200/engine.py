@@ -39,7 +39,7 @@ LOCAL_IMPL = _os.environ.get("AOTB_LOCAL_IMPL", "tile")      # "tile" (halo in s
 _LT_NAMES = {"simt": "attn_f32_kernel<32,32> (fp32 SIMT flash attention)",
              "tc_exact": "lt_attn_tc_kernel (tcgen05 fp16x2 exact: 6+16 MMAs/tile)",
              "tc_fast": "lt_attn_tc_kernel (tcgen05 fp16 fast: 2+8 MMAs/tile)"}
-LT_KERNEL_NAME = _LT_NAMES.get(LT_IMPL, LT_IMPL) + (", software-pipelined softmax" if (ops.LT_PIPE and LT_IMPL.startswith("tc")) else "")
+LT_KERNEL_NAME = _LT_NAMES.get(LT_IMPL, LT_IMPL) + (f", softmax layout '{ops.LT_VARIANT}'" if LT_IMPL.startswith("tc") else "")
 
 
 # Whole-call CUDA graphs (encoder / LSTT / decoder / memory update are each captured once per video geometry and

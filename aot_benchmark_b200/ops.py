@@ -340,17 +340,21 @@ def tc_pack_rows(src, dst, row_off=0, div=1.0, row_off_dev=None, stream=None):
     return dst
 
 
-# software-pipelined softmax of the tensor-core attention kernel (TMEM read of the next score tile under the ex2 pass
-# of the current one): same arithmetic and results as the serial variant
-LT_PIPE = os.environ.get("AOTB_LT_PIPE", "0") == "1"
+# softmax layout of the tensor-core attention kernel:
+#   "tile"   all 16 softmax warps on one 128x128 score tile at a time (4 threads per row)
+#   "groups" two groups of 8 warps, one per query tile, running out of phase (2 threads per row, 64 scores in registers)
+LT_VARIANT = os.environ.get("AOTB_LT_VARIANT", "tile")
 
 
 def lt_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True, part=None, dbg=None, stream=None,
-                    merge=True, pipe=None):
+                    merge=True, variant=None):
     """Qp [H, Nq_cap, 64], Kp/Vp [H, kv_cap, 64] packed fp16x2; O [N, H*32] fp32.
     With splits > 1, `part` = (Opart [S,N,H*32], Mpart [S,H,N], Lpart [S,H,N]) and O receives the merge.
-    `pipe` (default: AOTB_LT_PIPE) selects the software-pipelined softmax variant."""
-    mode = (1 if exact else 0) | (2 if (LT_PIPE if pipe is None else pipe) else 0)
+    `variant` (default: AOTB_LT_VARIANT) selects the softmax layout, "tile" or "groups"."""
+    v = LT_VARIANT if variant is None else variant
+    if v not in ("tile", "groups"):
+        raise AotbError(f"unknown long-term attention variant '{v}' (tile | groups)")
+    mode = (1 if exact else 0) | (2 if v == "groups" else 0)
     H, nq_cap, _ = Qp.shape
     kv_cap = Kp.shape[1]
     if splits > 1:

@@ -162,9 +162,11 @@ int aotb_nearest_resize_f32(const float* in, float* out, int H, int W, int Ho, i
  *                            (div = T for Q, attention.py:82; 1 for K and V).  Buffers must be zero-filled
  *                            beyond the live rows.
  *   aotb_lt_attn_tc_f16x2  : exact bit 0 set -> S = QhKh + QlKh + QhKl, O = (Ph + Pl)[Vh|Vl] (fp32-faithful);
- *                            clear -> S = QhKh, O = Ph[Vh|Vl].  exact bit 1 selects the software-pipelined
- *                            softmax (the TMEM read of the next score tile overlaps the ex2 pass of the current
- *                            one; same arithmetic, same results).  splits > 1 writes split-KV partials
+ *                            clear -> S = QhKh, O = Ph[Vh|Vl].  exact bit 1 selects the softmax layout: clear = all
+ *                            16 softmax warps on one 128x128 score tile at a time (4 threads per query row); set =
+ *                            two groups of 8 warps, one per query tile, out of phase (2 threads per row, one TMEM
+ *                            read per tile).  Same arithmetic; row sums are associated differently (~1e-7 relative).
+ *                            splits > 1 writes split-KV partials
  *                            for aotb_attn_merge_f32.  dbg (optional) receives S and O' of CTA 0. */
 int aotb_tc_pack_rows_f16x2(const float* src, int ld, void* dst, int cap, int rows, int H, int row_off,
                             const int* row_off_dev, float div, void* stream);

@@ -775,6 +775,115 @@ class OracleEngine:
 
 
 # --------------------------------------------------------------------------------------
+# multi-engine facade  (AOTInferEngine aot_engine.py:485-635; DeAOTInferEngine deaot_engine.py:59-94 differs
+# only in the sub-engine class it instantiates)
+# --------------------------------------------------------------------------------------
+class OracleInferEngine:
+    """ceil(obj/10) OracleEngines sharing one image encoding; masks are split into per-engine id ranges
+    (:515-545) and the per-engine logits are merged by soft_logit_aggregation (:565-582)."""
+
+    def __init__(self, weights: Dict[str, Tensor], cfg, long_term_mem_gap: Optional[int] = None,
+                 short_term_mem_skip: int = 1, dtype=torch.float32):
+        self.weights, self.cfg, self.dtype = weights, cfg, dtype
+        self.long_term_mem_gap = cfg.TEST_LONG_TERM_MEM_GAP if long_term_mem_gap is None else long_term_mem_gap
+        self.short_term_mem_skip = short_term_mem_skip
+        self.max_aot_obj_num = cfg.MODEL_MAX_OBJ_NUM
+        self.restart_engine()
+
+    def restart_engine(self):                                           # :510-513
+        self.aot_engines: List[OracleEngine] = []
+        self.obj_nums = None
+
+    def separate_mask(self, mask: Tensor, obj_nums: int):               # :515-545 (label-map branch)
+        if len(self.aot_engines) == 1:
+            return [mask], [obj_nums]
+        M = self.max_aot_obj_num
+        nums = [M] * len(self.aot_engines)
+        if obj_nums % M > 0:
+            nums[-1] = obj_nums % M
+        masks = []
+        for idx in range(len(self.aot_engines)):
+            lo, hi = idx * M + 1, (idx + 1) * M
+            fg = ((mask >= lo) & (mask <= hi)).to(mask.dtype)
+            masks.append((fg * mask - lo + 1) * fg)
+        return masks, nums
+
+    def soft_logit_aggregation(self, all_logits: List[Tensor]) -> Tensor:   # :565-582
+        if len(all_logits) == 1:
+            return all_logits[0]
+        M = self.max_aot_obj_num
+        probs = [torch.softmax(l, dim=1) for l in all_logits]
+        bg = torch.prod(torch.cat([p[:, 0:1] for p in probs], dim=1), dim=1, keepdim=True)
+        merged = torch.cat([bg] + [p[:, 1:1 + M] for p in probs], dim=1).clamp(1e-5, 1 - 1e-5)
+        return torch.logit(merged)
+
+    def add_reference_frame(self, img: Tensor, mask: Tensor, obj_nums, frame_step: int = -1):   # :584-609
+        if isinstance(obj_nums, list):
+            obj_nums = obj_nums[0]
+        self.obj_nums = obj_nums
+        need = max(math.ceil(obj_nums / self.max_aot_obj_num), 1)
+        while need > len(self.aot_engines):
+            self.aot_engines.append(OracleEngine(self.weights, self.cfg, self.long_term_mem_gap,
+                                                 self.short_term_mem_skip, self.dtype))
+        masks, nums = self.separate_mask(mask, obj_nums)
+        for eng, m, n in zip(self.aot_engines, masks, nums):
+            # the reference encodes the image once and hands the embeddings on (:600-607); the oracle engines
+            # simply re-encode (same values)
+            eng.add_reference_frame(img, m, [n], frame_step)
+        self.input_size_2d = self.aot_engines[0].input_size_2d
+        self.enc_size_2d = self.aot_engines[0].enc_size_2d
+
+    def match_propogate_one_frame(self, img: Tensor):                    # :611-616
+        for eng in self.aot_engines:
+            eng.match_propogate_one_frame(img)
+
+    def decode_current_logits(self, output_size=None) -> Tensor:         # :618-623
+        return self.soft_logit_aggregation([e.decode_current_logits(output_size) for e in self.aot_engines])
+
+    def update_memory(self, curr_mask: Tensor, skip_long_term_update: bool = False):   # :625-630
+        masks, _ = self.separate_mask(curr_mask, self.obj_nums)
+        for eng, m in zip(self.aot_engines, masks):
+            eng.update_memory(m, skip_long_term_update)
+
+
+def run_video_events(engine, frames: Sequence[Tensor], first_mask: Tensor, obj_num: int,
+                     output_size: Tuple[int, int], new_objects: Optional[Dict[int, Tensor]] = None,
+                     forced_masks: Optional[Sequence[Tensor]] = None):
+    """Evaluator.evaluating (evaluator.py:302-446, no TTA) including objects that first appear at a later frame
+    (:338-340, :362-370, :380-402): at such a frame the predicted label is overwritten where the new annotation is
+    non-zero, the frame is added as a reference frame with the enlarged object count, decoded again and written to
+    memory.  `new_objects` maps frame index -> label map [1,1,H_out,W_out] holding ONLY the new ids.
+    Returns (list of merged output-size logits, list of label maps fed back to the engine)."""
+    new_objects = new_objects or {}
+    engine.restart_engine()
+    engine.add_reference_frame(frames[0], first_mask, obj_nums=[obj_num], frame_step=0)
+    logits, labels = [], []
+    for t in range(1, len(frames)):
+        engine.match_propogate_one_frame(frames[t])
+        logit = engine.decode_current_logits(output_size)
+        label = torch.argmax(torch.softmax(logit, dim=1), dim=1, keepdim=True).to(logit.dtype)
+        if forced_masks is not None:
+            label = forced_masks[t - 1].to(label.device, label.dtype)
+        new = new_objects.get(t)
+        if new is not None:
+            new = new.to(label.device, label.dtype)
+            if forced_masks is None:
+                keep = (new == 0).to(label.dtype)
+                label = label * keep + new * (1 - keep)
+            obj_num = max(obj_num, int(new.max().item()))
+            fb = F.interpolate(label, size=tuple(engine.input_size_2d), mode="nearest")
+            engine.add_reference_frame(frames[t], fb, obj_nums=[obj_num], frame_step=t)
+            logit = engine.decode_current_logits(output_size)
+            engine.update_memory(fb)
+        else:
+            fb = F.interpolate(label, size=tuple(engine.input_size_2d), mode="nearest")
+            engine.update_memory(fb)
+        logits.append(logit.detach().clone())
+        labels.append(label.detach().clone())
+    return logits, labels
+
+
+# --------------------------------------------------------------------------------------
 # the evaluator's per-frame span (evaluator.py:325-446), single engine, no TTA
 # --------------------------------------------------------------------------------------
 def run_video(engine, frames: Sequence[Tensor], first_mask: Tensor, obj_num: int,

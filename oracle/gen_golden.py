@@ -94,6 +94,41 @@ def video_case(name, out_dir):
     }, os.path.join(out_dir, f"video_{name}.pt"))
 
 
+def events_case(out_dir, name="aott_multi14_events"):
+    """> 10 objects and objects that first appear mid-video, through the reference's AOTInferEngine exactly as
+    Evaluator.evaluating drives it (evaluator.py:302-446): 8 objects at frame 0, ids 9..14 annotated at frame 2 (a second
+    sub-engine is created there, aot_engine.py:588-594), merged logits from soft_logit_aggregation (:565-582)."""
+    model_name, H, W, oh, ow, T, gap = "aott", 97, 129, 64, 80, 6, 2
+    torch.manual_seed(0)
+    sd = OW.build_state_dict(model_name, seed=0, flavour="calibrated")
+    rcfg = DefaultEngineConfig("golden", model_name)
+    ref_model = ref_build_model(rcfg.MODEL_VOS, rcfg).eval()
+    ref_model.load_state_dict(sd, strict=True)
+    engine = ref_build_engine(rcfg.MODEL_ENGINE, phase="eval", aot_model=ref_model, gpu_id=-1,
+                              long_term_mem_gap=gap, short_term_mem_skip=1)
+    engine.eval()
+    frames, full = O.synthetic_video(T, H, W, 14, seed=4321)
+    first = torch.where(full <= 8, full, torch.zeros_like(full))
+    new = F.interpolate(torch.where(full > 8, full, torch.zeros_like(full)), size=(oh, ow), mode="nearest")
+    with torch.no_grad():
+        ref_lo, ref_labels = O.run_video_events(engine, frames, first, 8, (oh, ow), new_objects={2: new})
+        oe = O.OracleInferEngine(sd, O.OracleConfig(model_name), long_term_mem_gap=gap)
+        o_lo, _ = O.run_video_events(oe, frames, first, 8, (oh, ow), new_objects={2: new}, forced_masks=ref_labels)
+    assert [t.shape[1] for t in ref_lo] == [11, 21, 21, 21, 21], [t.shape for t in ref_lo]
+    # channels above the live object count hold -1e10-derived values: compare the live ones
+    live = [9, 15, 15, 15, 15]
+    max_d = max((a[:, :n] - b[:, :n]).abs().max().item() for a, b, n in zip(ref_lo, o_lo, live))
+    print(f"[{name}] oracle vs reference: max|dlogit|={max_d:.3e} engines={len(engine.aot_engines)} "
+          f"labels used={sorted(set(int(v) for l in ref_labels for v in l.unique().tolist()))}")
+    torch.save({
+        "model": model_name, "H": H, "W": W, "out_size": (oh, ow), "frames": T, "gap": gap, "seed": 0,
+        "video_seed": 4321, "first_objs": 8, "event_frame": 2, "live_channels": live,
+        "weights_checksum": OW.checksum(sd), "new_label": new.to(torch.uint8),
+        "ref_logits": [t[:, :n].to(torch.float32).clone() for t, n in zip(ref_lo, live)],
+        "ref_labels": [t.to(torch.uint8) for t in ref_labels], "oracle_pin_max_dlogit": max_d,
+    }, os.path.join(out_dir, f"events_{name}.pt"))
+
+
 def op_cases(out_dir):
     """Per-op vectors straight from the reference's attention modules (K1, K2, K1', K2')."""
     g = torch.Generator().manual_seed(77)
@@ -177,6 +212,8 @@ def main():
     for name in VIDEO_CASES:
         if a.only in (None, name):
             video_case(name, a.out)
+    if a.only in (None, "events"):
+        events_case(a.out)
 
 
 if __name__ == "__main__":

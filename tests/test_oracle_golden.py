@@ -98,6 +98,28 @@ def test_video_vs_reference_golden(name, golden_dir):
     assert mism <= 1e-4 * total  # fp32 summation-order ties only
 
 
+def _events_inputs(g):
+    frames, full = O.synthetic_video(g["frames"], g["H"], g["W"], 14, seed=g["video_seed"])
+    first = torch.where(full <= g["first_objs"], full, torch.zeros_like(full))
+    return frames, first, {g["event_frame"]: g["new_label"].float()}
+
+
+def test_multi_engine_and_new_objects_vs_reference_golden(golden_dir):
+    """AOTInferEngine with 14 objects (2 sub-engines, soft_logit_aggregation) where ids 9..14 first appear at frame 2
+    (second reference frame mid-video, evaluator.py:362-402): reference outputs (stored) vs the oracle."""
+    g = torch.load(os.path.join(golden_dir, "events_aott_multi14_events.pt"))
+    sd = OW.build_state_dict(g["model"], seed=g["seed"])
+    assert OW.checksum(sd) == g["weights_checksum"]
+    frames, first, new = _events_inputs(g)
+    eng = O.OracleInferEngine(sd, O.OracleConfig(g["model"]), long_term_mem_gap=g["gap"])
+    with torch.no_grad():
+        lo, labels = O.run_video_events(eng, frames, first, g["first_objs"], tuple(g["out_size"]), new_objects=new,
+                                        forced_masks=[l.float() for l in g["ref_labels"]])
+    assert len(eng.aot_engines) == 2
+    for a, b, n in zip(lo, g["ref_logits"], g["live_channels"]):
+        assert (a[:, :n] - b).abs().max().item() < 1e-4
+
+
 def test_float64_oracle_close_to_float32():
     """The fp64 truth used to size tolerances must agree with the fp32 restatement."""
     sd = OW.build_state_dict("aott", seed=1)
