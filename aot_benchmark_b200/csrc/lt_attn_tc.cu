@@ -73,6 +73,7 @@ struct LtArgs {
     float* Lpart;
     int splits;
     int exact;
+    int spin;    // 1: critical-path mbarrier waits poll (no suspend-time hint) instead of sleeping
     float* dbg;  // optional: CTA (0,0,0) dumps S_0(tile 0) [128][128] then O'_0 [128][64]
 };
 
@@ -118,6 +119,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                  "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
+}
+
+// critical-path wait: with `spin` the thread polls try_wait (hardware default time limit) instead of the NANOSLEEP-backed
+// suspend-hint loop, whose wake-up latency sits on the softmax -> MMA -> softmax dependency chain of every key tile
+__device__ __forceinline__ void mbar_wait_cp(uint64_t* bar, uint32_t parity, int spin) {
+    if (spin) mbar_wait_spin(bar, parity);
+    else mbar_wait(bar, parity);
 }
 
 template <bool EXACT, bool GROUPS>
@@ -217,13 +225,13 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             for (int j = 0; j < T; ++j) {
                 const int s = j % STAGES;
                 for (int i = 0; i < 2; ++i) {
-                    mbar_wait(&B->p_full[i], j & 1);
+                    mbar_wait_cp(&B->p_full[i], j & 1, a.spin);
                     tc_fence_after();
                     issue_PV(i, s, j > 0 ? 1u : 0u);
                     if (i == 1) mma_commit(&B->kv_free[s]);
                     if (j + 1 < T) {
                         const int s2 = (j + 1) % STAGES;
-                        if (i == 0) { mbar_wait(&B->kv_full[s2], ((j + 1) / STAGES) & 1); tc_fence_after(); }
+                        if (i == 0) { mbar_wait_cp(&B->kv_full[s2], ((j + 1) / STAGES) & 1, a.spin); tc_fence_after(); }
                         issue_S(i, s2);
                         mma_commit(&B->s_full[i]);
                     } else {
@@ -251,7 +259,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         float m_used = -INFINITY, l0 = 0.f, l1 = 0.f;
 
         for (int j = 0; j < T; ++j) {
-            mbar_wait(&B->s_full[wg], j & 1);
+            mbar_wait_cp(&B->s_full[wg], j & 1, a.spin);
             tc_fence_after();
             const int key0 = (tb + j) * BN + half * 64;
             uint32_t sr[64];
@@ -381,7 +389,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 const uint32_t tO = tmem + lane_addr + 256 + i * 64 + qt * 16;  // its 16 of the 64 O' columns
                 const uint32_t tPl = tmem + lane_addr + 384 + i * 64 + qt * 16;
                 const bool dump = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i == 0;
-                mbar_wait(&B->s_full[i], j & 1);
+                mbar_wait_cp(&B->s_full[i], j & 1, a.spin);
                 tc_fence_after();
                 const int key0 = (tb + j) * BN + qt * 32;
                 uint32_t sr[32];
@@ -586,7 +594,7 @@ extern "C" int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp,
     }
     tc::LtArgs a;
     a.N = N; a.Tk = Tk; a.Tk_dev = Tk_dev; a.H = H; a.O = O; a.ldo = ldo;
-    a.Opart = Opart; a.Mpart = Mpart; a.Lpart = Lpart; a.splits = splits; a.exact = exact & 1; a.dbg = dbg;
+    a.Opart = Opart; a.Mpart = Mpart; a.Lpart = Lpart; a.splits = splits; a.exact = exact & 1; a.spin = (exact >> 2) & 1; a.dbg = dbg;
     dim3 grid(cdiv(N, 2 * tc::BM), H, splits);
     const dim3 block(tc::NTHREADS);
     cudaStream_t st = (cudaStream_t)stream;

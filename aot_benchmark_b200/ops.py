@@ -344,6 +344,8 @@ def tc_pack_rows(src, dst, row_off=0, div=1.0, row_off_dev=None, stream=None):
 #   "tile"   all 16 softmax warps on one 128x128 score tile at a time (4 threads per row)
 #   "groups" two groups of 8 warps, one per query tile, running out of phase (2 threads per row, 64 scores in registers)
 LT_VARIANT = os.environ.get("AOTB_LT_VARIANT", "tile")
+# 1: the mbarrier waits on the softmax -> MMA -> softmax chain poll instead of sleeping with a suspend-time hint
+LT_SPIN = os.environ.get("AOTB_LT_SPIN", "0") == "1"
 
 
 def lt_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True, part=None, dbg=None, stream=None,
@@ -354,7 +356,7 @@ def lt_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True
     v = LT_VARIANT if variant is None else variant
     if v not in ("tile", "groups"):
         raise AotbError(f"unknown long-term attention variant '{v}' (tile | groups)")
-    mode = (1 if exact else 0) | (2 if v == "groups" else 0)
+    mode = (1 if exact else 0) | (2 if v == "groups" else 0) | (4 if LT_SPIN else 0)
     H, nq_cap, _ = Qp.shape
     kv_cap = Kp.shape[1]
     if splits > 1:

@@ -166,7 +166,8 @@ int aotb_nearest_resize_f32(const float* in, float* out, int H, int W, int Ho, i
  *                            16 softmax warps on one 128x128 score tile at a time (4 threads per query row); set =
  *                            two groups of 8 warps, one per query tile, out of phase (2 threads per row, one TMEM
  *                            read per tile).  Same arithmetic; row sums are associated differently (~1e-7 relative).
- *                            splits > 1 writes split-KV partials
+ *                            exact bit 2: the mbarrier waits between the softmax warps and the MMA issuer poll instead
+ *                            of sleeping (latency experiment; results unchanged).  splits > 1 writes split-KV partials
  *                            for aotb_attn_merge_f32.  dbg (optional) receives S and O' of CTA 0. */
 int aotb_tc_pack_rows_f16x2(const float* src, int ld, void* dst, int cap, int rows, int H, int row_off,
                             const int* row_off_dev, float div, void* stream);
