@@ -511,6 +511,307 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (warp == MMA_WARP) tmem_dealloc<512>(tmem);
 }
 
+// ------------------------------------------------------------------ "ahead" layout: scores one tile ahead of the softmax
+// Same arithmetic as lt_attn_tc_kernel<EXACT, false>, different TMEM plan and issue order (round-1 trips 16-18 showed
+// that the tile time of every two-buffer layout is the serial chain TMEM read -> max exchange -> ex2 pass, because the
+// next score tile does not exist yet while the current one is processed: S_i aliases P_i, so S_i(j+1) queues behind
+// PV_i(j)).  Here:
+//   TMEM   S_0 | S_1 | S_2 (128 fp32 columns each) | O_0 | O_1 (64 each) = 512 columns.  Score tile n = 2j + i (key tile
+//          j, query tile i) lives in buffer n % 3.  P_hi AND P_lo of the 32 keys a thread owns overwrite its own 32
+//          score columns (hi: columns [32t, 32t+16), lo: [32t+16, 32t+32)), which frees the former Plo_0 | Plo_1.
+//   MMA    S(0), S(1), S(2) up front; then for every n: wait P(n) -> PV(n) -> S(n+3) (same buffer, in pipe order).
+//          While the softmax warps are on tile n, S(n+1) has long completed (it was issued behind PV(n-2)).
+//   softmax 16 warps, 4 threads per row as in the default layout, but the tcgen05.ld of tile n+1 is issued before the
+//          ex2 pass of tile n and completed after it (two register sets; P is produced 16 keys at a time to stay inside
+//          the 96-register budget), so the TMEM read port works under the MUFU pass instead of in series with it.
+//   O_i    PV(n) accumulates into O_(n % 2).  S(n) is no longer ordered behind PV(n-2), so the (rare) rescale of O_i
+//          waits for o_done[i] (committed after every PV) instead of relying on s_full.
+//   smem   Q 2 tiles + 4-stage K/V ring (S runs up to 1.5 key tiles ahead of PV) = 160 KB.
+constexpr int STAGES3 = 4;
+
+struct __align__(8) Barriers3 {
+    uint64_t q_full;
+    uint64_t kv_full[STAGES3];
+    uint64_t kv_free[STAGES3];
+    uint64_t s_full[3];     // S(n) complete in buffer n % 3; use k = n / 3 of a buffer completes phase k
+    uint64_t p_full[3];     // 512 arrivals: P(n) written over S(n)
+    uint64_t o_done[2];     // PV(n) complete, n % 2 == i; the j-th PV of query tile i completes phase j
+    uint32_t tmem_base;
+    float xmax[8][BM];      // [(n & 1) * 4 + column quarter][row]
+    float xsum[8][BM];      // [query tile * 4 + column quarter][row]
+};
+
+// tcgen05.wait::ld that also names the registers a still in-flight tcgen05.ld writes: the "+r" ties make every later use
+// of them depend on this statement, so the compiler cannot hoist arithmetic on the prefetched scores above the wait.
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+lt_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const LtArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;                                  // 2 tiles
+    uint8_t* sK = sQ + 2 * TILE_BYTES;                   // STAGES3 tiles
+    uint8_t* sV = sK + STAGES3 * TILE_BYTES;             // STAGES3 tiles
+    Barriers3* B = reinterpret_cast<Barriers3*>(sV + STAGES3 * TILE_BYTES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * (2 * BM), h = blockIdx.y, z = blockIdx.z;
+    pdl_trigger();
+
+    if (tid == 0) {
+        mbar_init(&B->q_full, 1);
+        for (int s = 0; s < STAGES3; ++s) { mbar_init(&B->kv_full[s], 1); mbar_init(&B->kv_free[s], 1); }
+        for (int b = 0; b < 3; ++b) { mbar_init(&B->s_full[b], 1); mbar_init(&B->p_full[b], 4 * BM); }
+        for (int i = 0; i < 2; ++i) mbar_init(&B->o_done[i], 1);
+        fence_mbar_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc<512>(&B->tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = B->tmem_base;
+    pdl_wait();
+    const int Tk = a.Tk_dev ? *a.Tk_dev : a.Tk;
+    const int tiles_total = (Tk + BN - 1) / BN;
+    const int per = (tiles_total + a.splits - 1) / a.splits;
+    const int tb = z * per;
+    int T = tiles_total - tb;
+    T = T < 0 ? 0 : (T > per ? per : T);
+    const int nT = 2 * T;                                 // score tiles of this CTA: n = 2 j + i
+
+    if (warp == TMA_WARP) {
+        if (elect_one() && T > 0) {
+            tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+            mbar_arrive_expect_tx(&B->q_full, 2 * TILE_BYTES);
+            tma_load_3d(sQ, &tmQ, &B->q_full, 0, q0, h);
+            tma_load_3d(sQ + TILE_BYTES, &tmQ, &B->q_full, 0, q0 + BM, h);
+            for (int j = 0; j < T; ++j) {
+                const int s = j % STAGES3;
+                if (j >= STAGES3) mbar_wait(&B->kv_free[s], ((j / STAGES3) - 1) & 1);
+                mbar_arrive_expect_tx(&B->kv_full[s], 2 * TILE_BYTES);
+                tma_load_3d(sK + s * TILE_BYTES, &tmK, &B->kv_full[s], 0, (tb + j) * BN, h);
+                tma_load_3d(sV + s * TILE_BYTES, &tmV, &B->kv_full[s], 0, (tb + j) * BN, h);
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        if (elect_one() && T > 0) {
+            constexpr uint32_t IDESC_S = idesc_f16(128, 128, 0, 0);
+            constexpr uint32_t IDESC_O = idesc_f16(128, 64, 0, 1);
+            const uint64_t dQ0 = smem_desc_sw128(smem_u32(sQ)), dQ1 = smem_desc_sw128(smem_u32(sQ) + TILE_BYTES);
+            const uint64_t dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
+            int kv_ready = -1;                              // highest key tile whose K/V have been waited for
+            auto issue_S = [&](int n) {
+                const int i = n & 1, j = n >> 1, s = j % STAGES3;
+                if (j > kv_ready) {
+                    mbar_wait_cp(&B->kv_full[s], (j / STAGES3) & 1, a.spin);
+                    tc_fence_after();
+                    kv_ready = j;
+                }
+                const uint64_t q = i ? dQ1 : dQ0;
+                const uint64_t k = dK + (uint64_t)(s * (TILE_BYTES >> 4));
+                const uint32_t d = tmem + (n % 3) * 128;
+                mma_ss(d, q, k, IDESC_S, 0);
+                mma_ss(d, q + 2, k + 2, IDESC_S, 1);
+                if (EXACT) {
+                    mma_ss(d, q + 4, k, IDESC_S, 1);          // Ql Kh
+                    mma_ss(d, q + 6, k + 2, IDESC_S, 1);
+                    mma_ss(d, q, k + 4, IDESC_S, 1);          // Qh Kl
+                    mma_ss(d, q + 2, k + 6, IDESC_S, 1);
+                }
+                mma_commit(&B->s_full[n % 3]);
+            };
+            auto issue_PV = [&](int n) {
+                const int i = n & 1, j = n >> 1, s = j % STAGES3;
+                const uint64_t v = dV + (uint64_t)(s * (TILE_BYTES >> 4));
+                const uint32_t d = tmem + 384 + i * 64;
+                const uint32_t p = tmem + (n % 3) * 128;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)      // P_hi of keys [16 kk, +16) at columns 32 (kk / 2) + 8 (kk % 2)
+                    mma_ts(d, p + 32 * (kk >> 1) + 8 * (kk & 1), v + 128 * kk, IDESC_O, (kk > 0 || j > 0) ? 1u : 0u);
+                if (EXACT) {
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)  // P_lo 16 columns further up in the same thread's score columns
+                        mma_ts(d, p + 32 * (kk >> 1) + 16 + 8 * (kk & 1), v + 128 * kk, IDESC_O, 1);
+                }
+                mma_commit(&B->o_done[i]);
+                if (i == 1) mma_commit(&B->kv_free[s]);
+            };
+            mbar_wait(&B->q_full, 0);
+            tc_fence_after();
+            for (int n = 0; n < 3 && n < nT; ++n) issue_S(n);
+            for (int n = 0; n < nT; ++n) {
+                mbar_wait_cp(&B->p_full[n % 3], (n / 3) & 1, a.spin);
+                tc_fence_after();
+                issue_PV(n);
+                if (n + 3 < nT) issue_S(n + 3);
+            }
+        }
+    } else {
+        const int qt = warp >> 2, wq = warp & 3;           // column quarter, TMEM lane quadrant
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        float m_used[2] = {-INFINITY, -INFINITY}, l0[2] = {0.f, 0.f}, l1[2] = {0.f, 0.f};
+        uint32_t srA[32], srB[32];
+        // one score tile: `sr` holds this thread's 32 scores of tile n, `srn` receives those of tile n + 1
+        // b / bn: score buffers of tile n and n + 1 (n % 3 kept as a rotating counter); next_par: phase parity of S(n + 1)
+        auto tile = [&](uint32_t (&sr)[32], uint32_t (&srn)[32], const int i, const int j, const int b, const int bn,
+                        const bool has_next, const uint32_t next_par) {
+            const uint32_t tS = tmem + lane_addr + b * 128 + qt * 32;
+            const uint32_t tO = tmem + lane_addr + 384 + i * 64 + qt * 16;
+            const int key0 = (tb + j) * BN + qt * 32;
+            if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i == 0 && j == 0) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) a.dbg[row * 128 + qt * 32 + k] = __uint_as_float(sr[k]);
+            }
+            if (key0 + 32 > Tk) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (key0 + k >= Tk) sr[k] = __float_as_uint(-INFINITY);
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) {
+                mx0 = fmaxf(mx0, __uint_as_float(sr[k]));
+                mx1 = fmaxf(mx1, __uint_as_float(sr[k + 1]));
+            }
+            B->xmax[i * 4 + qt][row] = fmaxf(mx0, mx1);
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            const float mt = fmaxf(fmaxf(B->xmax[i * 4 + 0][row], B->xmax[i * 4 + 1][row]),
+                                   fmaxf(B->xmax[i * 4 + 2][row], B->xmax[i * 4 + 3][row]));
+            const float m_new = fmaxf(m_used[i], mt);
+            const bool grow = (m_new > m_used[i]) && (j > 0);
+            if (__any_sync(0xffffffffu, grow)) {
+                // O_i must be quiescent: PV(n - 2) complete (o_done), PV(n) not issued before all threads arrive on p_full
+                mbar_wait(&B->o_done[i], (uint32_t)((j - 1) & 1));
+                tc_fence_after();
+                const float f = grow ? ex2((m_used[i] - m_new) * LOG2E) : 1.f;
+                uint32_t orr[16];
+                tmem_ld16(tO, orr);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 16; ++k) orr[k] = __float_as_uint(__uint_as_float(orr[k]) * f);
+                tmem_st16(tO, orr);
+                l0[i] *= f; l1[i] *= f;
+            }
+            m_used[i] = m_new;
+            const float neg = m_new * LOG2E;
+            const uint32_t tSn = tmem + lane_addr + bn * 128 + qt * 32;
+            if (has_next) {                 // S(n + 1) was issued behind PV(n - 2): complete long ago in steady state
+                mbar_wait_cp(&B->s_full[bn], next_par, a.spin);
+                tc_fence_after();
+                tmem_ld16(tSn, srn);        // first half now; second half once sr[0..15] are dead (register budget)
+            }
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                if (hf == 1 && has_next) tmem_ld16(tSn + 16, srn + 16);
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const float p0 = ex2(fmaf(__uint_as_float(sr[16 * hf + 2 * t]), LOG2E, -neg));
+                    const float p1 = ex2(fmaf(__uint_as_float(sr[16 * hf + 2 * t + 1]), LOG2E, -neg));
+                    s0 += p0; s1 += p1;
+                    const __half2 hi = __floats2half2_rn(p0, p1);
+                    ph[t] = *reinterpret_cast<const uint32_t*>(&hi);
+                    if (EXACT) {
+                        const __half2 lo = __floats2half2_rn(p0 - __low2float(hi), p1 - __high2float(hi));
+                        pl[t] = *reinterpret_cast<const uint32_t*>(&lo);
+                    }
+                }
+                tmem_st8(tS + 8 * hf, ph);               // keys [32 qt + 16 hf, +16) -> columns [32 qt + 8 hf, +8)
+                if (EXACT) tmem_st8(tS + 16 + 8 * hf, pl);
+            }
+            l0[i] += s0; l1[i] += s1;
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&B->p_full[b]);
+            if (has_next) tmem_wait_ld32(srn);
+        };
+        if (T > 0) {
+            mbar_wait(&B->s_full[0], 0);
+            tc_fence_after();
+            tmem_ld32(tmem + lane_addr + qt * 32, srA);
+            tmem_wait_ld32(srA);
+        }
+        // buffer b of tile n and the parity of its s_full phase rotate with n: bit b of `par` = uses of buffer b so far (mod 2)
+        int b = 0;
+        uint32_t par = 1u;                                  // the prologue consumed phase 0 of s_full[0]
+        for (int j = 0; j < T; ++j) {
+            int bn = b == 2 ? 0 : b + 1;
+            tile(srA, srB, 0, j, b, bn, true, (par >> bn) & 1u);
+            par ^= 1u << bn;
+            b = bn;
+            bn = b == 2 ? 0 : b + 1;
+            tile(srB, srA, 1, j, b, bn, j + 1 < T, (par >> bn) & 1u);
+            par ^= 1u << bn;                                // (harmless after the last tile)
+            b = bn;
+        }
+
+        // ---- epilogue: per query tile, this thread finishes output channels [8*qt, 8*qt+8) of its row
+#pragma unroll
+        for (int i = 0; i < 2; ++i) B->xsum[i * 4 + qt][row] = l0[i] + l1[i];
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float l = (B->xsum[i * 4 + 0][row] + B->xsum[i * 4 + 1][row]) + (B->xsum[i * 4 + 2][row] + B->xsum[i * 4 + 3][row]);
+            const uint32_t tO = tmem + lane_addr + 384 + i * 64;
+            const bool dump = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i == 0;
+            const int q = q0 + i * BM + row;
+            float o[8];
+            if (T > 0) {
+                mbar_wait(&B->o_done[i], (uint32_t)((T - 1) & 1));       // the last PV into O_i
+                tc_fence_after();
+                uint32_t o0[8], o1[8];
+                tmem_ld8(tO + qt * 8, o0);
+                tmem_ld8(tO + 32 + qt * 8, o1);
+                tmem_wait_ld();
+                if (dump) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        a.dbg[128 * 128 + row * 64 + qt * 8 + k] = __uint_as_float(o0[k]);
+                        a.dbg[128 * 128 + row * 64 + 32 + qt * 8 + k] = __uint_as_float(o1[k]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = __uint_as_float(o0[k]) + __uint_as_float(o1[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = 0.f;
+            }
+            if (q < a.N) {
+                if (a.splits == 1) {
+                    const float inv = 1.f / l;
+                    float* dst = a.O + (size_t)q * a.ldo + h * 32 + qt * 8;
+                    *reinterpret_cast<float4*>(dst) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
+                } else {
+                    float* dst = a.Opart + ((size_t)z * a.N + q) * (a.H * 32) + h * 32 + qt * 8;
+                    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                    if (qt == 0) {
+                        a.Mpart[((size_t)z * a.H + h) * a.N + q] = m_used[i];
+                        a.Lpart[((size_t)z * a.H + h) * a.N + q] = l;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc<512>(tmem);
+}
+
 // ------------------------------------------------------------------ operand packing
 // src fp32 [rows][ld] (head h at columns h*32) -> dst halfs [H][cap][64] at row offset: [hi(32) | lo(32)]
 __global__ void pack_rows64_kernel(const float* __restrict__ src, int ld, __half* __restrict__ dst, int cap, int rows,
@@ -559,6 +860,8 @@ extern "C" size_t aotb_lt_attn_tc_smem_bytes(void) {
     return (size_t)(2 + 2 * tc::STAGES) * tc::TILE_BYTES + sizeof(tc::Barriers) + 1024;
 }
 
+static size_t lt3_smem_bytes() { return (size_t)(2 + 2 * tc::STAGES3) * tc::TILE_BYTES + sizeof(tc::Barriers3) + 1024; }
+
 // Qp [H][Nq_cap][64], Kp/Vp [H][kv_cap][64] packed fp16x2 operands (zero-filled beyond the live rows);
 // O [N][ldo] fp32 (head h at columns h*32).  splits > 1 writes un-normalised partials
 // (Opart [splits][N][H*32], Mpart/Lpart [splits][H][N]) for aotb_attn_merge_f32.
@@ -586,6 +889,10 @@ extern "C" int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp,
             e = cudaFuncSetAttribute(tc::lt_attn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(tc::lt_attn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc::lt_attn_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lt3_smem_bytes());
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc::lt_attn_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lt3_smem_bytes());
         if (e != cudaSuccess) {
             set_error("aotb_lt_attn_tc_f16x2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return AOTB_ERR_CUDA;
@@ -598,6 +905,11 @@ extern "C" int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp,
     dim3 grid(cdiv(N, 2 * tc::BM), H, splits);
     const dim3 block(tc::NTHREADS);
     cudaStream_t st = (cudaStream_t)stream;
+    if (exact & 8) {          // bit 3: "ahead" layout (three score buffers, TMEM read under the ex2 pass)
+        if (exact & 1) launch(tc::lt_attn_tc3_kernel<true>, dim3(grid), block, lt3_smem_bytes(), st, tq, tk, tv, a);
+        else launch(tc::lt_attn_tc3_kernel<false>, dim3(grid), block, lt3_smem_bytes(), st, tq, tk, tv, a);
+        return check_launch("aotb_lt_attn_tc_f16x2");
+    }
     switch (exact & 3) {      // bit 0: fp16x2 "exact" operands; bit 1: two-group softmax layout
         case 3: launch(tc::lt_attn_tc_kernel<true, true>, dim3(grid), block, smem, st, tq, tk, tv, a); break;
         case 2: launch(tc::lt_attn_tc_kernel<false, true>, dim3(grid), block, smem, st, tq, tk, tv, a); break;

@@ -343,6 +343,8 @@ def tc_pack_rows(src, dst, row_off=0, div=1.0, row_off_dev=None, stream=None):
 # softmax layout of the tensor-core attention kernel:
 #   "tile"   all 16 softmax warps on one 128x128 score tile at a time (4 threads per row)
 #   "groups" two groups of 8 warps, one per query tile, running out of phase (2 threads per row, 64 scores in registers)
+#   "ahead"  three score buffers in TMEM: S runs one tile ahead of the softmax and the TMEM read of the next tile is
+#            issued under the ex2 pass of the current one (built at the end of round 1, NOT yet run on a GPU)
 LT_VARIANT = os.environ.get("AOTB_LT_VARIANT", "tile")
 # 1: the mbarrier waits on the softmax -> MMA -> softmax chain poll instead of sleeping with a suspend-time hint
 LT_SPIN = os.environ.get("AOTB_LT_SPIN", "0") == "1"
@@ -352,11 +354,11 @@ def lt_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True
                     merge=True, variant=None):
     """Qp [H, Nq_cap, 64], Kp/Vp [H, kv_cap, 64] packed fp16x2; O [N, H*32] fp32.
     With splits > 1, `part` = (Opart [S,N,H*32], Mpart [S,H,N], Lpart [S,H,N]) and O receives the merge.
-    `variant` (default: AOTB_LT_VARIANT) selects the softmax layout, "tile" or "groups"."""
+    `variant` (default: AOTB_LT_VARIANT) selects the softmax layout: "tile", "groups" or "ahead"."""
     v = LT_VARIANT if variant is None else variant
-    if v not in ("tile", "groups"):
-        raise AotbError(f"unknown long-term attention variant '{v}' (tile | groups)")
-    mode = (1 if exact else 0) | (2 if v == "groups" else 0) | (4 if LT_SPIN else 0)
+    if v not in ("tile", "groups", "ahead"):
+        raise AotbError(f"unknown long-term attention variant '{v}' (tile | groups | ahead)")
+    mode = (1 if exact else 0) | (2 if v == "groups" else 0) | (4 if LT_SPIN else 0) | (8 if v == "ahead" else 0)
     H, nq_cap, _ = Qp.shape
     kv_cap = Kp.shape[1]
     if splits > 1:

@@ -166,6 +166,9 @@ int aotb_nearest_resize_f32(const float* in, float* out, int H, int W, int Ho, i
  *                            16 softmax warps on one 128x128 score tile at a time (4 threads per query row); set =
  *                            two groups of 8 warps, one per query tile, out of phase (2 threads per row, one TMEM
  *                            read per tile).  Same arithmetic; row sums are associated differently (~1e-7 relative).
+ *                            exact bit 3: "ahead" layout -- three score buffers in TMEM (P_hi and P_lo both alias the
+ *                            owning thread's score columns), S issued one tile ahead, the TMEM read of tile n+1 under the
+ *                            ex2 pass of tile n (experimental: built at the end of round 1, not yet run on a GPU).
  *                            exact bit 2: the mbarrier waits between the softmax warps and the MMA issuer poll instead
  *                            of sleeping (latency experiment; results unchanged).  splits > 1 writes split-KV partials
  *                            for aotb_attn_merge_f32.  dbg (optional) receives S and O' of CTA 0. */

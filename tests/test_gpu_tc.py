@@ -105,21 +105,25 @@ def test_lt_attention_tc_matches_simt_and_splits():
     assert (O4 - ref).abs().max().item() < 1e-4
 
 
-def _groups_enabled():
+def _variant_enabled(v):
+    """Non-default softmax layouts are tested when they are the configured default or named in AOTB_TEST_VARIANTS
+    (comma-separated), e.g. AOTB_TEST_VARIANTS=groups,ahead."""
     import os
     from aot_benchmark_b200 import ops
-    return ops.LT_VARIANT == "groups" or os.environ.get("AOTB_TEST_GROUPS", "0") == "1"
+    return ops.LT_VARIANT == v or v in os.environ.get("AOTB_TEST_VARIANTS", "").split(",") or \
+        (v == "groups" and os.environ.get("AOTB_TEST_GROUPS", "0") == "1")
 
 
+@pytest.mark.parametrize("variant", ["groups", "ahead"])
 @pytest.mark.parametrize("N,Tk,splits,exact", [(128, 128, 1, True), (300, 700, 1, True), (1674, 5022 + 77, 1, True),
                                                (1674, 1674 * 7, 5, True), (200, 300, 8, True), (300, 700, 1, False),
                                                (1674, 1674 * 3 + 5, 3, False)])
-def test_lt_attention_tc_groups_layout(N, Tk, splits, exact):
-    """The two-group softmax layout (2 threads per row, one TMEM read per tile) computes the same maxima and the same
-    P as the one-tile layout; only the association of the row sums differs: outputs agree to ~1e-6 and both match the
-    fp64 oracle."""
-    if not _groups_enabled():
-        pytest.skip("two-group layout not enabled (AOTB_LT_VARIANT=groups or AOTB_TEST_GROUPS=1)")
+def test_lt_attention_tc_layouts(N, Tk, splits, exact, variant):
+    """The alternative softmax layouts ("groups": 2 threads per row, one TMEM read per tile; "ahead": three score
+    buffers, TMEM read under the ex2 pass) compute the same maxima and the same P as the default one-tile layout; only
+    the association of the row sums may differ: outputs agree to ~1e-6 and all match the fp64 oracle."""
+    if not _variant_enabled(variant):
+        pytest.skip(f"layout '{variant}' not enabled (AOTB_LT_VARIANT={variant} or AOTB_TEST_VARIANTS={variant})")
     from aot_benchmark_b200 import ops
     d = torch.device("cuda:0")
     g = torch.Generator().manual_seed(N * 7 + Tk)
@@ -130,13 +134,13 @@ def test_lt_attention_tc_groups_layout(N, Tk, splits, exact):
     kcap = ((Tk + 127) // 128) * 128 + 128
     Qp, Kp, Vp = _pack(Q, ncap, math.sqrt(32.0)), _pack(K, kcap), _pack(V, kcap)
     outs = []
-    for variant in ("tile", "groups"):
+    for v in ("tile", variant):
         part = None
         if splits > 1:
             part = (torch.zeros(splits, N, 256, device=d), torch.zeros(splits, H, N, device=d),
                     torch.zeros(splits, H, N, device=d))
         O = torch.full((N, 256), float("nan"), device=d)
-        ops.lt_attention_tc(Qp, Kp, Vp, N, Tk, O=O, splits=splits, exact=exact, part=part, variant=variant)
+        ops.lt_attention_tc(Qp, Kp, Vp, N, Tk, O=O, splits=splits, exact=exact, part=part, variant=v)
         torch.cuda.synchronize()
         outs.append((O, part))
     assert torch.isfinite(outs[1][0]).all()
