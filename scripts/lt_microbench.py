@@ -47,7 +47,10 @@ def main():
     Q = (torch.randn(N, H * D, generator=g) * 3).to(dev)
     ncap = ((N + 255) // 256) * 256
     Qp = pack(Q, ncap, math.sqrt(D))
-    sm_clock = torch.cuda.clock_rate() * 1e3 if hasattr(torch.cuda, "clock_rate") else 1.965e9
+    try:
+        sm_clock = torch.cuda.clock_rate() * 1e6            # MHz (NVML) -> Hz, sampled once; B200 boost is 1965 MHz
+    except Exception:
+        sm_clock = 1.965e9
     rows = []
     for m in [int(x) for x in a.frames.split(",")]:
         Tk = N * m
