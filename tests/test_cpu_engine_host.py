@@ -1,0 +1,65 @@
+"""CPU: host-side logic of the drop-in engines -- weight packing (plan.py: FrozenBN folding, fused projections, ID-bank
+prefix sums), buffer wiring, call order, memory-bank bookkeeping, short-term ring, multi-engine facade -- checked against
+the oracle (pinned to the real reference by tests/golden) with every C-ABI entry point replaced by a torch-CPU emulation of
+its documented contract (tests/emu_ops.py).  The CUDA kernels themselves are checked on the GPU (tests/test_gpu_*.py);
+this suite is what lets the engine be refactored without a GPU at hand."""
+import os
+
+import pytest
+import torch
+
+from oracle import aot_oracle as O
+from oracle import weights as OW
+
+
+def _engine(model_name, sd, gap):
+    from aot_benchmark_b200 import EngineConfig, build_engine, build_vos_model
+    cfg = EngineConfig("t", model_name)
+    model = build_vos_model(cfg.MODEL_VOS, cfg).eval()
+    model.load_state_dict(sd, strict=True)
+    eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=0, long_term_mem_gap=gap,
+                       short_term_mem_skip=cfg.TEST_SHORT_TERM_MEM_SKIP)
+    eng.eval()
+    return eng
+
+
+@pytest.mark.parametrize("lt_impl", ["tc_exact", "simt"])
+@pytest.mark.parametrize("name", ["aott_raw_257", "r50_aotl_small", "r50_deaotl_small", "deaott_small",
+                                  "swinb_aotl_small", "swinb_deaotl_small"])
+def test_engine_orchestration_vs_reference_golden(monkeypatch, golden_dir, name, lt_impl):
+    import emu_ops
+    from aot_benchmark_b200 import engine
+    emu_ops.install_engine(monkeypatch)
+    monkeypatch.setattr(engine, "LT_IMPL", lt_impl)
+    g = torch.load(os.path.join(golden_dir, f"video_{name}.pt"))
+    if lt_impl == "simt" and (g["model"].endswith(("deaotl", "deaott")) or g["model"].startswith("swinb")):
+        pytest.skip("DeAOT always uses the fp32 SIMT attention; the Swin clips are covered once")
+    T = min(g["frames"], 3 if g["model"].startswith("swinb") else 5)
+    sd = OW.build_state_dict(g["model"], seed=g["seed"], flavour=g["flavour"])
+    frames, mask = O.synthetic_video(g["frames"], g["H"], g["W"], g["objs"], seed=1234 + g["seed"])
+    eng = _engine(g["model"], sd, g["gap"])
+    forced = [l.float() for l in g["ref_labels"]]
+    with torch.no_grad():
+        lo, labels = O.run_video(eng, frames[:T], mask, g["objs"], tuple(g["out_size"]), forced_masks=forced)
+    n = g["objs"] + 1
+    dmax = max((a[:, :n] - b[:, :n]).abs().max().item() for a, b in zip(lo, g["ref_logits_lo"]))
+    assert dmax < 2e-4, f"max |dlogit| vs reference = {dmax}"
+    e0 = eng.aot_engines[0]
+    assert e0.bank_len == e0.enc_hw * (1 + (T - 1) // g["gap"])          # reference frame + every gap-th frame
+
+
+def test_multi_engine_and_new_objects_orchestration(monkeypatch, golden_dir):
+    import emu_ops
+    emu_ops.install_engine(monkeypatch)
+    g = torch.load(os.path.join(golden_dir, "events_aott_multi14_events.pt"))
+    sd = OW.build_state_dict(g["model"], seed=g["seed"])
+    frames, full = O.synthetic_video(g["frames"], g["H"], g["W"], 14, seed=g["video_seed"])
+    first = torch.where(full <= g["first_objs"], full, torch.zeros_like(full))
+    eng = _engine(g["model"], sd, g["gap"])
+    with torch.no_grad():
+        lo, _ = O.run_video_events(eng, frames, first, g["first_objs"], tuple(g["out_size"]),
+                                   new_objects={g["event_frame"]: g["new_label"].float()},
+                                   forced_masks=[l.float() for l in g["ref_labels"]])
+    assert len(eng.aot_engines) == 2
+    for a, b, n in zip(lo, g["ref_logits"], g["live_channels"]):
+        assert (a[:, :n] - b).abs().max().item() < 2e-4
