@@ -54,17 +54,20 @@ VIDEO_CASES = {
     # 144x208 -> 36x52 / 18x26 / 9x13 maps: window padding and shifted-window masks at every stage
     "swinb_aotl_small": ("swinb_aotl", 144, 208, 130, 200, 5, 6, 2, "calibrated"),
     "swinb_deaotl_small": ("swinb_deaotl", 112, 176, 112, 176, 4, 3, 2, "calibrated"),
+    # TEST_SHORT_TERM_MEM_SKIP = 2: the short-term memory is the frame BEFORE the previous one (aot_engine.py:329-332)
+    "aott_skip2": ("aott", 129, 177, 129, 177, 6, 3, 2, "calibrated", 2),
+    "deaott_skip3": ("deaott", 113, 145, 113, 145, 6, 2, 3, "calibrated", 3),
 }
 
 
-def run_reference_video(model_name, H, W, oh, ow, T, objs, gap, flavour, seed=0):
+def run_reference_video(model_name, H, W, oh, ow, T, objs, gap, flavour, skip=1, seed=0):
     torch.manual_seed(0)
     sd = OW.build_state_dict(model_name, seed=seed, flavour=flavour)
     rcfg = DefaultEngineConfig("golden", model_name)
     ref_model = ref_build_model(rcfg.MODEL_VOS, rcfg).eval()
     ref_model.load_state_dict(sd, strict=True)
     engine = ref_build_engine(rcfg.MODEL_ENGINE, phase="eval", aot_model=ref_model, gpu_id=-1,
-                              long_term_mem_gap=gap, short_term_mem_skip=1)
+                              long_term_mem_gap=gap, short_term_mem_skip=skip)
     engine.eval()
     frames, mask = O.synthetic_video(T, H, W, objs, seed=1234 + seed)
     with torch.no_grad():
@@ -73,11 +76,12 @@ def run_reference_video(model_name, H, W, oh, ow, T, objs, gap, flavour, seed=0)
 
 
 def video_case(name, out_dir):
-    model_name, H, W, oh, ow, T, objs, gap, flavour = VIDEO_CASES[name]
-    sd, frames, mask, ref_lo, ref_labels = run_reference_video(model_name, H, W, oh, ow, T, objs, gap, flavour)
+    model_name, H, W, oh, ow, T, objs, gap, flavour = VIDEO_CASES[name][:9]
+    skip = VIDEO_CASES[name][9] if len(VIDEO_CASES[name]) > 9 else 1
+    sd, frames, mask, ref_lo, ref_labels = run_reference_video(model_name, H, W, oh, ow, T, objs, gap, flavour, skip)
     # pin the oracle (teacher-forced with the reference's own labels)
     ocfg = O.OracleConfig(model_name)
-    oe = O.OracleEngine(sd, ocfg, long_term_mem_gap=gap)
+    oe = O.OracleEngine(sd, ocfg, long_term_mem_gap=gap, short_term_mem_skip=skip)
     with torch.no_grad():
         o_lo, o_labels = O.run_video(oe, frames, mask, objs, (oh, ow), forced_masks=ref_labels)
     max_d = max((a - b).abs().max().item() for a, b in zip(ref_lo, o_lo))
@@ -87,18 +91,21 @@ def video_case(name, out_dir):
           f"|logit|max={max(a[:, :objs + 1].abs().max().item() for a in ref_lo):.2f} labels used={used}")
     torch.save({
         "model": model_name, "H": H, "W": W, "out_size": (oh, ow), "frames": T, "objs": objs, "gap": gap,
-        "flavour": flavour, "seed": 0, "weights_checksum": OW.checksum(sd),
+        "flavour": flavour, "seed": 0, "skip": skip, "weights_checksum": OW.checksum(sd),
         "ref_logits_lo": [t.to(torch.float32) for t in ref_lo],
         "ref_labels": [t.to(torch.uint8) for t in ref_labels],
         "oracle_pin_max_dlogit": max_d, "oracle_pin_label_mismatch": mism,
     }, os.path.join(out_dir, f"video_{name}.pt"))
 
 
+EVENT_CASES = {"aott_multi14_events": "aott", "deaott_multi14_events": "deaott"}
+
+
 def events_case(out_dir, name="aott_multi14_events"):
     """> 10 objects and objects that first appear mid-video, through the reference's AOTInferEngine exactly as
     Evaluator.evaluating drives it (evaluator.py:302-446): 8 objects at frame 0, ids 9..14 annotated at frame 2 (a second
     sub-engine is created there, aot_engine.py:588-594), merged logits from soft_logit_aggregation (:565-582)."""
-    model_name, H, W, oh, ow, T, gap = "aott", 97, 129, 64, 80, 6, 2
+    model_name, H, W, oh, ow, T, gap = EVENT_CASES[name], 97, 129, 64, 80, 6, 2
     torch.manual_seed(0)
     sd = OW.build_state_dict(model_name, seed=0, flavour="calibrated")
     rcfg = DefaultEngineConfig("golden", model_name)
@@ -212,8 +219,9 @@ def main():
     for name in VIDEO_CASES:
         if a.only in (None, name):
             video_case(name, a.out)
-    if a.only in (None, "events"):
-        events_case(a.out)
+    for name in EVENT_CASES:
+        if a.only in (None, "events", name):
+            events_case(a.out, name)
 
 
 if __name__ == "__main__":

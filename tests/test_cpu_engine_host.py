@@ -12,20 +12,20 @@ from oracle import aot_oracle as O
 from oracle import weights as OW
 
 
-def _engine(model_name, sd, gap):
+def _engine(model_name, sd, gap, skip=None):
     from aot_benchmark_b200 import EngineConfig, build_engine, build_vos_model
     cfg = EngineConfig("t", model_name)
     model = build_vos_model(cfg.MODEL_VOS, cfg).eval()
     model.load_state_dict(sd, strict=True)
     eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=0, long_term_mem_gap=gap,
-                       short_term_mem_skip=cfg.TEST_SHORT_TERM_MEM_SKIP)
+                       short_term_mem_skip=cfg.TEST_SHORT_TERM_MEM_SKIP if skip is None else skip)
     eng.eval()
     return eng
 
 
 @pytest.mark.parametrize("lt_impl", ["tc_exact", "simt"])
 @pytest.mark.parametrize("name", ["aott_raw_257", "r50_aotl_small", "r50_deaotl_small", "deaott_small",
-                                  "swinb_aotl_small", "swinb_deaotl_small"])
+                                  "swinb_aotl_small", "swinb_deaotl_small", "aott_skip2", "deaott_skip3"])
 def test_engine_orchestration_vs_reference_golden(monkeypatch, golden_dir, name, lt_impl):
     import emu_ops
     from aot_benchmark_b200 import engine
@@ -34,10 +34,10 @@ def test_engine_orchestration_vs_reference_golden(monkeypatch, golden_dir, name,
     g = torch.load(os.path.join(golden_dir, f"video_{name}.pt"))
     if lt_impl == "simt" and (g["model"].endswith(("deaotl", "deaott")) or g["model"].startswith("swinb")):
         pytest.skip("DeAOT always uses the fp32 SIMT attention; the Swin clips are covered once")
-    T = min(g["frames"], 3 if g["model"].startswith("swinb") else 5)
+    T = min(g["frames"], 3 if g["model"].startswith("swinb") else 6)
     sd = OW.build_state_dict(g["model"], seed=g["seed"], flavour=g["flavour"])
     frames, mask = O.synthetic_video(g["frames"], g["H"], g["W"], g["objs"], seed=1234 + g["seed"])
-    eng = _engine(g["model"], sd, g["gap"])
+    eng = _engine(g["model"], sd, g["gap"], g.get("skip"))
     forced = [l.float() for l in g["ref_labels"]]
     with torch.no_grad():
         lo, labels = O.run_video(eng, frames[:T], mask, g["objs"], tuple(g["out_size"]), forced_masks=forced)
@@ -48,10 +48,11 @@ def test_engine_orchestration_vs_reference_golden(monkeypatch, golden_dir, name,
     assert e0.bank_len == e0.enc_hw * (1 + (T - 1) // g["gap"])          # reference frame + every gap-th frame
 
 
-def test_multi_engine_and_new_objects_orchestration(monkeypatch, golden_dir):
+@pytest.mark.parametrize("case", ["aott_multi14_events", "deaott_multi14_events"])
+def test_multi_engine_and_new_objects_orchestration(monkeypatch, golden_dir, case):
     import emu_ops
     emu_ops.install_engine(monkeypatch)
-    g = torch.load(os.path.join(golden_dir, "events_aott_multi14_events.pt"))
+    g = torch.load(os.path.join(golden_dir, f"events_{case}.pt"))
     sd = OW.build_state_dict(g["model"], seed=g["seed"])
     frames, full = O.synthetic_video(g["frames"], g["H"], g["W"], 14, seed=g["video_seed"])
     first = torch.where(full <= g["first_objs"], full, torch.zeros_like(full))

@@ -10,7 +10,7 @@ from oracle import aot_oracle as O
 from oracle import weights as OW
 
 VIDEO = ["aott_256", "aott_raw_257", "r50_aotl_small", "r50_deaotl_small", "deaott_small", "swinb_aotl_small",
-         "swinb_deaotl_small"]
+         "swinb_deaotl_small", "aott_skip2", "deaott_skip3"]
 
 
 @pytest.fixture(scope="module")
@@ -86,7 +86,8 @@ def test_video_vs_reference_golden(name, golden_dir):
     sd = OW.build_state_dict(g["model"], seed=g["seed"], flavour=g["flavour"])
     assert OW.checksum(sd) == g["weights_checksum"], "seeded weights are not reproducible on this machine"
     frames, mask = O.synthetic_video(g["frames"], g["H"], g["W"], g["objs"], seed=1234 + g["seed"])
-    eng = O.OracleEngine(sd, O.OracleConfig(g["model"]), long_term_mem_gap=g["gap"])
+    eng = O.OracleEngine(sd, O.OracleConfig(g["model"]), long_term_mem_gap=g["gap"],
+                         short_term_mem_skip=g.get("skip", 1))
     forced = [l.float() for l in g["ref_labels"]]
     with torch.no_grad():
         lo, labels = O.run_video(eng, frames, mask, g["objs"], tuple(g["out_size"]), forced_masks=forced)
@@ -104,10 +105,11 @@ def _events_inputs(g):
     return frames, first, {g["event_frame"]: g["new_label"].float()}
 
 
-def test_multi_engine_and_new_objects_vs_reference_golden(golden_dir):
-    """AOTInferEngine with 14 objects (2 sub-engines, soft_logit_aggregation) where ids 9..14 first appear at frame 2
-    (second reference frame mid-video, evaluator.py:362-402): reference outputs (stored) vs the oracle."""
-    g = torch.load(os.path.join(golden_dir, "events_aott_multi14_events.pt"))
+@pytest.mark.parametrize("case", ["aott_multi14_events", "deaott_multi14_events"])
+def test_multi_engine_and_new_objects_vs_reference_golden(golden_dir, case):
+    """AOTInferEngine / DeAOTInferEngine with 14 objects (2 sub-engines, soft_logit_aggregation) where ids 9..14 first
+    appear at frame 2 (second reference frame mid-video, evaluator.py:362-402): reference outputs (stored) vs the oracle."""
+    g = torch.load(os.path.join(golden_dir, f"events_{case}.pt"))
     sd = OW.build_state_dict(g["model"], seed=g["seed"])
     assert OW.checksum(sd) == g["weights_checksum"]
     frames, first, new = _events_inputs(g)
