@@ -36,6 +36,10 @@ LT_PROBE = None
 import os as _os
 LT_IMPL = _os.environ.get("AOTB_LT_IMPL", "tc_exact")
 LOCAL_IMPL = _os.environ.get("AOTB_LOCAL_IMPL", "tile")      # "tile" (halo in smem) | "warp" (generic kernel)
+# DeAOT long-term attention (1 head, d_qk 128, d_v 1024): "simt" fp32 flash kernel | "gemm" = tensor-core GEMM (Q K^T) ->
+# row softmax -> tensor-core GEMM (P V) over split-fp16 operand copies of the bank (deaot_lt.cu; built at the end of
+# round 1, host logic checked on CPU, kernels not yet run on a GPU -> not the default)
+DEAOT_LT = _os.environ.get("AOTB_DEAOT_LT", "simt")
 _LT_NAMES = {"simt": "attn_f32_kernel<32,32> (fp32 SIMT flash attention)",
              "tc_exact": "lt_attn_tc_kernel (tcgen05 fp16x2 exact: 6+16 MMAs/tile)",
              "tc_fast": "lt_attn_tc_kernel (tcgen05 fp16 fast: 2+8 MMAs/tile)"}
@@ -429,6 +433,9 @@ class AOTEngine(nn.Module):
         self.bank_K = [f(cap, self._kdim) for _ in range(L)]
         self.bank_V = [f(cap, self._vdim) for _ in range(L)]
         self.bank_len = 0
+        self._gemm_lt = bool(P.deaot and DEAOT_LT == "gemm")
+        if self._gemm_lt:
+            self._alloc_gemm_lt(cap, ws=ws)
         self._tc = LT_IMPL.startswith("tc") and (not P.deaot) and (C // P.H == 32)
         if self._tc:
             hz = lambda *s: torch.zeros(s, dtype=torch.float16, device=dev)
@@ -441,6 +448,26 @@ class AOTEngine(nn.Module):
         self._st_ring = []
         self._ws = ws
         self._dec_bufs = {}
+
+    def _alloc_gemm_lt(self, cap, old_len=0, old=None, ws=None):
+        """Split-fp16 operand copies of the DeAOT bank for the GEMM formulation: keys [cap64][d] (weights of Q K^T),
+        values transposed [4C][cap64] (weights of P V), zero beyond the live rows, plus the score matrix [N][cap64]."""
+        P = self._plan()
+        dev = P.device
+        capw = ((cap + 63) // 64) * 64
+        hz = lambda *s: torch.zeros(s, dtype=torch.float16, device=dev)
+        Kh, Kl = [hz(capw, self._kdim) for _ in range(P.L)], [hz(capw, self._kdim) for _ in range(P.L)]
+        Vh, Vl = [hz(self._vdim, capw) for _ in range(P.L)], [hz(self._vdim, capw) for _ in range(P.L)]
+        if old is not None:
+            for new_l, old_l in zip((Kh, Kl), old[:2]):
+                for a, b in zip(new_l, old_l):
+                    a[:old_len].copy_(b[:old_len])
+            for new_l, old_l in zip((Vh, Vl), old[2:]):
+                for a, b in zip(new_l, old_l):
+                    a[:, :old_len].copy_(b[:, :old_len])
+        self.bank_Kh, self.bank_Kl, self.bank_VhT, self.bank_VlT = Kh, Kl, Vh, Vl
+        self._capw = capw
+        (self._ws if ws is None else ws).S = torch.empty((self.enc_hw, capw), dtype=torch.float32, device=dev)
 
     def _bank_reserve(self, rows):
         if self.bank_len + rows <= self.bank_cap:
@@ -457,6 +484,8 @@ class AOTEngine(nn.Module):
                     nb = torch.zeros((old.shape[0], new_cap, 64), dtype=torch.float16, device=old.device)
                     nb[:, : self.bank_len].copy_(old[:, : self.bank_len])
                     lst[i] = nb
+        if getattr(self, "_gemm_lt", False):
+            self._alloc_gemm_lt(new_cap, self.bank_len, (self.bank_Kh, self.bank_Kl, self.bank_VhT, self.bank_VlT))
         self.bank_cap = new_cap
         self.graphs.clear()            # captured launches point at the old bank
 
@@ -633,6 +662,9 @@ class AOTEngine(nn.Module):
             if self._tc:
                 ops.tc_pack_rows(K_src[li], self.bank_Kp[li], 0, row_off_dev=off, stream=st)
                 ops.tc_pack_rows(V_src[li], self.bank_Vp[li], 0, row_off_dev=off, stream=st)
+            if self._gemm_lt:
+                ops.split_rows(K_src[li], self.bank_Kh[li], self.bank_Kl[li], row_off_dev=off, stream=st)
+                ops.split_cols(V_src[li], self.bank_VhT[li], self.bank_VlT[li], col_off_dev=off, stream=st)
         ops.counter_add(off, N, stream=st)
         if count:
             self.bank_len += N
@@ -942,7 +974,13 @@ class DeAOTEngine(AOTEngine):
             if probe is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            ops.attention(cQ, gK, gV, ws.core, 1, d, C4, Tk=Tk, Tk_dev=None if is_ref else self.tk_dev, stream=st)
+            if self._gemm_lt and not is_ref:
+                # S = Q K^T -> softmax(S / T) over the live keys -> P V, all on the tensor-core GEMM (deaot_lt.cu)
+                ops.linear_tc(cQ, self.bank_Kh[li], self.bank_Kl[li], None, ws.S, stream=st)
+                ops.row_softmax(ws.S, self._capw, Tk, 1.0 / math.sqrt(d), Tk_dev=self.tk_dev, stream=st)
+                ops.linear_tc(ws.S, self.bank_VhT[li], self.bank_VlT[li], None, ws.core, stream=st)
+            else:
+                ops.attention(cQ, gK, gV, ws.core, 1, d, C4, Tk=Tk, Tk_dev=None if is_ref else self.tk_dev, stream=st)
             if probe is not None:
                 e1.record()
                 probe.append((e0, e1, 2.0 * N * Tk * (d + C4)))      # FLOPs = 2*N*Tk*(d_qk + d_v), SURVEY 8d

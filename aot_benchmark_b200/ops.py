@@ -126,6 +126,51 @@ def linear(x, wt, bias, out, res=None, act=ACT_NONE, stream=None):
     return out
 
 
+def linear_tc(x, wh, wl, bias, out, res=None, act=ACT_NONE, stream=None):
+    """out[M][N] = act(x[M][K] @ W^T + bias + res) on the tensor-core GEMM with explicitly given split-fp16 weights
+    wh / wl [N][K] (K % 64 == 0, N % 64 == 0) -- e.g. operand copies of the memory bank."""
+    _chk(x, bias, out, res)
+    if wh.dtype != torch.float16 or wl.dtype != torch.float16 or wh.shape != wl.shape or not wh.is_contiguous() \
+            or not wl.is_contiguous():
+        raise AotbError("linear_tc: wh / wl must be contiguous fp16 tensors of the same shape [N, K]")
+    M, K = x.shape
+    N = wh.shape[0]
+    if wh.shape[1] != K or K % 64 or N % 64 or out.shape[0] != M or out.shape[1] != N:
+        raise AotbError(f"linear_tc: shapes x {tuple(x.shape)}, w {tuple(wh.shape)}, out {tuple(out.shape)}")
+    ws = _tc_workspace(x.device)
+    check(lib().aotb_conv2d_nhwc_tc(_p(x), wh.data_ptr(), wl.data_ptr(), _p(bias), _p(res), _p(out), 1, M, 1, K,
+                                    x.stride(0), N, out.stride(0), res.stride(0) if res is not None else 0, 1, 1, 1, 0,
+                                    act, ws.data_ptr(), ws.numel(), _st(stream)), "aotb_conv2d_nhwc_tc")
+    return out
+
+
+def split_rows(src, hi, lo, row_off=0, row_off_dev=None, stream=None):
+    """src fp32 [rows, C] -> hi / lo fp16 [cap, ldw] rows [row_off, row_off + rows)."""
+    _chk(src)
+    rows, C = src.shape
+    check(lib().aotb_split_rows_f16x2(_p(src), src.stride(0), hi.data_ptr(), lo.data_ptr(), hi.stride(0), rows, C,
+                                      int(row_off), row_off_dev.data_ptr() if row_off_dev is not None else None,
+                                      _st(stream)), "aotb_split_rows_f16x2")
+
+
+def split_cols(src, hiT, loT, col_off=0, col_off_dev=None, stream=None):
+    """src fp32 [rows, C] -> columns [col_off, col_off + rows) of hiT / loT fp16 [C, cap]."""
+    _chk(src)
+    rows, C = src.shape
+    check(lib().aotb_split_cols_f16x2(_p(src), src.stride(0), hiT.data_ptr(), loT.data_ptr(), hiT.stride(0), rows, C,
+                                      int(col_off), col_off_dev.data_ptr() if col_off_dev is not None else None,
+                                      _st(stream)), "aotb_split_cols_f16x2")
+
+
+def row_softmax(S, cols, Tk, scale, Tk_dev=None, stream=None):
+    """In place on S [N, >= cols]: softmax(scale * S[r, :live]) in columns [0, live), zeros in [live, cols)."""
+    _chk(S)
+    check(lib().aotb_row_softmax_f32(_p(S), S.stride(0), S.shape[0], int(cols), int(Tk),
+                                     Tk_dev.data_ptr() if Tk_dev is not None else None, float(scale), _st(stream)),
+          "aotb_row_softmax_f32")
+    return S
+
+
 def nchw_to_nhwc(x, out, stream=None):
     _chk(x, out)
     B, C, H, W = x.shape

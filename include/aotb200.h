@@ -179,6 +179,22 @@ int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp, const void
                           const int* Tk_dev, int H, float* O, int ldo, float* Opart, float* Mpart, float* Lpart,
                           int splits, int exact, float* dbg, void* stream);
 
+/* DeAOT long-term attention as GEMM -> row softmax -> GEMM on the tensor cores (AOTB_DEAOT_LT=gemm):
+ * GatedPropagation.forward networks/layers/attention.py:672-704 with 1 head, d_qk = 128, d_v = 1024.  The two GEMMs are
+ * aotb_conv2d_nhwc_tc with the bank as pre-split weights; these entry points maintain those copies and do the softmax.
+ *   aotb_split_rows_f16x2: src fp32 [rows][lds] (C columns) -> hi / lo fp16 [.][ldw] rows [row_off, row_off + rows)
+ *                          (hi = fp16(x), lo = fp16(x - hi)); the keys [Tk_cap][128] = weights of S = Q K^T.
+ *   aotb_split_cols_f16x2: the same values written as COLUMNS [col_off, col_off + rows) of hiT / loT [C][ldt]: the
+ *                          transposed value bank [1024][Tk_cap] = weights of O = P V.
+ *   aotb_row_softmax_f32 : S [N][ld] in place: columns [0, live) <- softmax(scale * S[r][0:live]) (attention.py:686-693,
+ *                          scale = 1 / T applied to the scores instead of to Q), columns [live, cols) <- 0; live = *Tk_dev
+ *                          if given, else Tk.  Offsets / counts may be device-resident so a captured graph can be replayed. */
+int aotb_split_rows_f16x2(const float* src, int lds, void* hi, void* lo, int ldw, int rows, int C, int row_off,
+                          const int* row_off_dev, void* stream);
+int aotb_split_cols_f16x2(const float* src, int lds, void* hiT, void* loT, int ldt, int rows, int C, int col_off,
+                          const int* col_off_dev, void* stream);
+int aotb_row_softmax_f32(float* S, int ld, int N, int cols, int Tk, const int* Tk_dev, float scale, void* stream);
+
 /* Long-term memory append in place (replaces torch.cat, networks/engines/aot_engine.py:291-305). */
 int aotb_bank_append_f32(const float* src, int lds, float* bank, int ldb, int rows, int cols, int offset,
                          const int* offset_dev, void* stream);

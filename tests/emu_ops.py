@@ -317,11 +317,43 @@ def counter_add(counter, delta, stream=None):
     return counter
 
 
+def linear_tc(x, wh, wl, bias, out, res=None, act=0, stream=None):
+    y = x @ (wh.float() + wl.float()).t()
+    if bias is not None:
+        y = y + bias
+    if res is not None:
+        y = y + res
+    out.copy_(_act(y, act))
+    return out
+
+
+def split_rows(src, hi, lo, row_off=0, row_off_dev=None, stream=None):
+    off = int(row_off_dev.item()) if row_off_dev is not None else int(row_off)
+    h = src.half()
+    hi[off:off + src.shape[0], :src.shape[1]] = h
+    lo[off:off + src.shape[0], :src.shape[1]] = (src - h.float()).half()
+
+
+def split_cols(src, hiT, loT, col_off=0, col_off_dev=None, stream=None):
+    off = int(col_off_dev.item()) if col_off_dev is not None else int(col_off)
+    h = src.half()
+    hiT[:src.shape[1], off:off + src.shape[0]] = h.t()
+    loT[:src.shape[1], off:off + src.shape[0]] = (src - h.float()).half().t()
+
+
+def row_softmax(S, cols, Tk, scale, Tk_dev=None, stream=None):
+    live = min(int(Tk_dev.item()) if Tk_dev is not None else int(Tk), cols)
+    p = torch.softmax(S[:, :live] * scale, dim=1)
+    S[:, :cols] = 0
+    S[:, :live] = p
+    return S
+
+
 EMULATED = ("image_to_nhwc4", "conv2d", "linear", "layernorm", "window_attention", "patch_merge", "eltwise",
             "nchw_to_nhwc", "nhwc_to_nchw", "maxpool3x3s2", "dwconv", "bilinear", "groupnorm_workspace", "groupnorm",
             "attention", "attn_merge", "tc_pack_rows", "lt_attention_tc", "local_attention", "local_attention_tile",
             "id_embed", "id_embed_runs", "logits_postproc", "logits_argmax", "nearest_resize", "bank_append",
-            "counter_add")
+            "counter_add", "linear_tc", "split_rows", "split_cols", "row_softmax")
 
 
 class _FakeStream:

@@ -64,3 +64,26 @@ def test_multi_engine_and_new_objects_orchestration(monkeypatch, golden_dir, cas
     assert len(eng.aot_engines) == 2
     for a, b, n in zip(lo, g["ref_logits"], g["live_channels"]):
         assert (a[:, :n] - b).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("name", ["r50_deaotl_small", "deaott_skip3"])
+def test_deaot_gemm_long_term_attention_orchestration(monkeypatch, golden_dir, name):
+    """AOTB_DEAOT_LT=gemm: Q K^T GEMM -> row softmax over the live keys -> P V GEMM over split-fp16 copies of the bank
+    (kept up to date at append time, including a capacity growth) gives the reference's logits."""
+    import emu_ops
+    from aot_benchmark_b200 import engine
+    emu_ops.install_engine(monkeypatch)
+    monkeypatch.setattr(engine, "DEAOT_LT", "gemm")
+    monkeypatch.setattr(engine, "BANK_INIT_FRAMES", 1)           # force bank re-allocations mid-clip
+    g = torch.load(os.path.join(golden_dir, f"video_{name}.pt"))
+    sd = OW.build_state_dict(g["model"], seed=g["seed"], flavour=g["flavour"])
+    frames, mask = O.synthetic_video(g["frames"], g["H"], g["W"], g["objs"], seed=1234 + g["seed"])
+    eng = _engine(g["model"], sd, g["gap"], g.get("skip"))
+    with torch.no_grad():
+        lo, _ = O.run_video(eng, frames, mask, g["objs"], tuple(g["out_size"]),
+                            forced_masks=[l.float() for l in g["ref_labels"]])
+    e0 = eng.aot_engines[0]
+    assert e0._gemm_lt and e0.bank_len > e0.enc_hw                 # grew past the initial capacity
+    n = g["objs"] + 1
+    dmax = max((a[:, :n] - b[:, :n]).abs().max().item() for a, b in zip(lo, g["ref_logits_lo"]))
+    assert dmax < 2e-4, f"max |dlogit| vs reference = {dmax}"

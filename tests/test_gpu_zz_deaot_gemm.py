@@ -1,0 +1,98 @@
+"""GPU: DeAOT long-term attention as tensor-core GEMM -> row softmax -> tensor-core GEMM (AOTB_DEAOT_LT=gemm,
+csrc/deaot_lt.cu): the three helper kernels against torch, the composed attention against the fp32 SIMT kernel and the
+fp64 oracle, and the DeAOT engine against the real reference's golden.  (Sorted last: these kernels were written after
+the round's last GPU trip.)"""
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_split_rows_and_cols_kernels():
+    from aot_benchmark_b200 import ops
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    rows, C, cap = 77, 128, 256
+    src = (torch.randn(rows, C, generator=g) * 3).to(d)
+    hi = torch.zeros(cap, C, dtype=torch.float16, device=d)
+    lo = torch.zeros(cap, C, dtype=torch.float16, device=d)
+    off = torch.tensor([40], dtype=torch.int32, device=d)
+    ops.split_rows(src, hi, lo, row_off_dev=off)
+    h = src.half()
+    assert torch.equal(hi[40:40 + rows], h) and torch.equal(lo[40:40 + rows], (src - h.float()).half())
+    assert hi[:40].abs().max() == 0 and hi[40 + rows:].abs().max() == 0
+    C2 = 200                                             # not a multiple of 32: partial tiles
+    src2 = (torch.randn(rows, C2, generator=g) * 3).to(d)
+    hiT = torch.zeros(C2, cap, dtype=torch.float16, device=d)
+    loT = torch.zeros(C2, cap, dtype=torch.float16, device=d)
+    ops.split_cols(src2, hiT, loT, col_off=100)
+    h2 = src2.half()
+    assert torch.equal(hiT[:, 100:100 + rows], h2.t()) and torch.equal(loT[:, 100:100 + rows], (src2 - h2.float()).half().t())
+    assert hiT[:, :100].abs().max() == 0 and hiT[:, 100 + rows:].abs().max() == 0
+
+
+@pytest.mark.parametrize("N,cols,live", [(5, 64, 64), (37, 256, 201), (3, 4160, 4099), (2, 128, 1)])
+def test_row_softmax_kernel(N, cols, live):
+    from aot_benchmark_b200 import ops
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(cols + live)
+    S = (torch.randn(N, cols, generator=g) * 40).to(d)
+    want = torch.zeros(N, cols, dtype=torch.float64)
+    want[:, :live] = torch.softmax(S[:, :live].double().cpu() / math.sqrt(128.0), dim=1)
+    tk = torch.tensor([live], dtype=torch.int32, device=d)
+    ops.row_softmax(S, cols, 0, 1.0 / math.sqrt(128.0), Tk_dev=tk)
+    torch.cuda.synchronize()
+    assert (S.cpu().double() - want).abs().max().item() < 2e-6
+    assert S[:, live:].abs().max().item() == 0 if live < cols else True
+
+
+@pytest.mark.parametrize("N,Tk", [(176, 176 * 3 + 11), (1674, 1674 * 2)])
+def test_gemm_attention_matches_simt_and_oracle(N, Tk):
+    from aot_benchmark_b200 import ops
+    from oracle import aot_oracle as O
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(N)
+    Q = (torch.randn(N, 128, generator=g) * 2).to(d)
+    K = torch.randn(Tk, 128, generator=g).to(d)
+    V = torch.randn(Tk, 1024, generator=g).to(d)
+    capw = ((Tk + 500 + 63) // 64) * 64
+    Kh = torch.zeros(capw, 128, dtype=torch.float16, device=d)
+    Kl = torch.zeros_like(Kh)
+    VhT = torch.zeros(1024, capw, dtype=torch.float16, device=d)
+    VlT = torch.zeros_like(VhT)
+    ops.split_rows(K, Kh, Kl)
+    ops.split_cols(V, VhT, VlT)
+    S = torch.empty(N, capw, device=d)
+    out = torch.empty(N, 1024, device=d)
+    ops.linear_tc(Q, Kh, Kl, None, S)
+    ops.row_softmax(S, capw, Tk, 1.0 / math.sqrt(128.0))
+    ops.linear_tc(S, VhT, VlT, None, out)
+    simt = torch.empty(N, 1024, device=d)
+    ops.attention(Q, K, V, simt, 1, 128, 1024)
+    torch.cuda.synchronize()
+    assert (out - simt).abs().max().item() < 1e-4
+    ref = O.multihead_attention(Q.double().cpu().unsqueeze(1), K.double().cpu().unsqueeze(1),
+                                V.double().cpu().unsqueeze(1), 1, d_att=128)[:, 0]
+    assert (out.cpu().double() - ref).abs().max().item() < 1e-4
+
+
+def test_deaot_engine_gemm_path_vs_reference_golden(golden_dir, monkeypatch):
+    from aot_benchmark_b200 import engine
+    from oracle import aot_oracle as O
+    from oracle import weights as OW
+    from test_gpu_engine import _build_cuda_engine
+    monkeypatch.setattr(engine, "DEAOT_LT", "gemm")
+    g = torch.load(os.path.join(golden_dir, "video_r50_deaotl_small.pt"))
+    sd = OW.build_state_dict(g["model"], seed=g["seed"], flavour=g["flavour"])
+    frames, mask = O.synthetic_video(g["frames"], g["H"], g["W"], g["objs"], seed=1234 + g["seed"])
+    eng = _build_cuda_engine(g["model"], sd, g["gap"])
+    with torch.no_grad():
+        lo, _ = O.run_video(eng, [f.cuda() for f in frames], mask.cuda(), g["objs"], tuple(g["out_size"]),
+                            forced_masks=[l.float() for l in g["ref_labels"]])
+    assert eng.aot_engines[0]._gemm_lt
+    n = g["objs"] + 1
+    dmax = max((a.cpu()[:, :n] - b[:, :n]).abs().max().item() for a, b in zip(lo, g["ref_logits_lo"]))
+    assert dmax < 1e-3, f"max |dlogit| vs reference = {dmax}"
