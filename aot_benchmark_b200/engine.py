@@ -40,6 +40,7 @@ LOCAL_IMPL = _os.environ.get("AOTB_LOCAL_IMPL", "tile")      # "tile" (halo in s
 # row softmax -> tensor-core GEMM (P V) over split-fp16 operand copies of the bank (deaot_lt.cu; built at the end of
 # round 1, host logic checked on CPU, kernels not yet run on a GPU -> not the default)
 DEAOT_LT = _os.environ.get("AOTB_DEAOT_LT", "simt")
+GEMM_GROW_FRAMES = int(_os.environ.get("AOTB_GEMM_GROW_FRAMES", "8"))   # bank growth step of the GEMM path (memory frames)
 _LT_NAMES = {"simt": "attn_f32_kernel<32,32> (fp32 SIMT flash attention)",
              "tc_exact": "lt_attn_tc_kernel (tcgen05 fp16x2 exact: 6+16 MMAs/tile)",
              "tc_fast": "lt_attn_tc_kernel (tcgen05 fp16 fast: 2+8 MMAs/tile)"}
@@ -428,7 +429,7 @@ class AOTEngine(nn.Module):
             self._kdim, self._vdim = d, 4 * C
         ws.mask = f(*self.input_size_2d)                            # static copy of the caller's label map
         self._dec_out = {}
-        cap = BANK_INIT_FRAMES * N
+        cap = (min(BANK_INIT_FRAMES, GEMM_GROW_FRAMES) if (P.deaot and DEAOT_LT == "gemm") else BANK_INIT_FRAMES) * N
         self.bank_cap = cap
         self.bank_K = [f(cap, self._kdim) for _ in range(L)]
         self.bank_V = [f(cap, self._vdim) for _ in range(L)]
@@ -473,6 +474,10 @@ class AOTEngine(nn.Module):
         if self.bank_len + rows <= self.bank_cap:
             return
         new_cap = max(2 * self.bank_cap, self.bank_len + rows)
+        if getattr(self, "_gemm_lt", False):
+            # the GEMM formulation of DeAOT's long-term attention costs O(capacity), not O(live keys): grow in steps of
+            # GEMM_GROW_FRAMES memory frames (a few graph re-captures per clip) instead of doubling
+            new_cap = max(self.bank_cap + GEMM_GROW_FRAMES * self.enc_hw, self.bank_len + rows)
         for lst in (self.bank_K, self.bank_V):
             for i, old in enumerate(lst):
                 nb = torch.empty((new_cap, old.shape[1]), dtype=torch.float32, device=old.device)
