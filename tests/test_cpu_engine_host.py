@@ -87,3 +87,23 @@ def test_deaot_gemm_long_term_attention_orchestration(monkeypatch, golden_dir, n
     n = g["objs"] + 1
     dmax = max((a[:, :n] - b[:, :n]).abs().max().item() for a, b in zip(lo, g["ref_logits_lo"]))
     assert dmax < 2e-4, f"max |dlogit| vs reference = {dmax}"
+
+
+@pytest.mark.parametrize("model_name,H,W,objs", [("aott", 100, 150, 0), ("aott", 83, 61, 1), ("deaott", 70, 95, 10)])
+def test_engine_edge_cases_vs_oracle(monkeypatch, model_name, H, W, objs):
+    """No objects at all, a single object on a tiny odd-sized frame, the maximum object count of one engine: the product
+    engine (emulated entry points) against the oracle on the same seeded inputs, free-running (no teacher forcing)."""
+    import emu_ops
+    emu_ops.install_engine(monkeypatch)
+    sd = OW.build_state_dict(model_name, seed=5)
+    frames, mask = O.synthetic_video(4, H, W, objs, seed=17)
+    oe = O.OracleEngine(sd, O.OracleConfig(model_name), long_term_mem_gap=2)
+    eng = _engine(model_name, sd, 2)
+    with torch.no_grad():
+        o_lo, o_labels = O.run_video(oe, frames, mask, objs, (H, W))
+        c_lo, c_labels = O.run_video(eng, frames, mask, objs, (H, W), forced_masks=o_labels)
+    n = objs + 1
+    for a, b in zip(c_lo, o_lo):
+        assert (a[:, :n] - b[:, :n]).abs().max().item() < 2e-4
+    if objs == 0:
+        assert all(int(l.max()) == 0 for l in c_labels)          # nothing but background can be predicted
