@@ -92,42 +92,6 @@ struct __align__(8) Barriers {
     float xsum[8][BM];
 };
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-}
-
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
-
-// critical-path wait: with `spin` the thread polls try_wait (hardware default time limit) instead of the NANOSLEEP-backed
-// suspend-hint loop, whose wake-up latency sits on the softmax -> MMA -> softmax dependency chain of every key tile
-__device__ __forceinline__ void mbar_wait_cp(uint64_t* bar, uint32_t parity, int spin) {
-    if (spin) mbar_wait_spin(bar, parity);
-    else mbar_wait(bar, parity);
-}
-
 template <bool EXACT, bool GROUPS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -535,23 +499,13 @@ struct __align__(8) Barriers3 {
     uint64_t kv_free[STAGES3];
     uint64_t s_full[3];     // S(n) complete in buffer n % 3; use k = n / 3 of a buffer completes phase k
     uint64_t p_full[3];     // 512 arrivals: P(n) written over S(n)
-    uint64_t o_done[2];     // PV(n) complete, n % 2 == i; the j-th PV of query tile i completes phase j
+    uint64_t o_done[2];     // PV(n) complete, n % 2 == i; the j-th PV of query tile i completes phase j (rescale guard: at
+                            // tile (j, i) the softmax knows PV(j - 2, i) is complete, so it is at most one phase behind)
+    uint64_t o_final[2];    // last PV into O_i complete (single phase: the epilogue may be two o_done phases behind)
     uint32_t tmem_base;
     float xmax[8][BM];      // [(n & 1) * 4 + column quarter][row]
     float xsum[8][BM];      // [query tile * 4 + column quarter][row]
 };
-
-// tcgen05.wait::ld that also names the registers a still in-flight tcgen05.ld writes: the "+r" ties make every later use
-// of them depend on this statement, so the compiler cannot hoist arithmetic on the prefetched scores above the wait.
-__device__ __forceinline__ void tmem_wait_ld32(uint32_t* r) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
-}
 
 template <bool EXACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -572,7 +526,7 @@ lt_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_init(&B->q_full, 1);
         for (int s = 0; s < STAGES3; ++s) { mbar_init(&B->kv_full[s], 1); mbar_init(&B->kv_free[s], 1); }
         for (int b = 0; b < 3; ++b) { mbar_init(&B->s_full[b], 1); mbar_init(&B->p_full[b], 4 * BM); }
-        for (int i = 0; i < 2; ++i) mbar_init(&B->o_done[i], 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&B->o_done[i], 1); mbar_init(&B->o_final[i], 1); }
         fence_mbar_init();
     }
     if (warp == MMA_WARP) tmem_alloc<512>(&B->tmem_base);
@@ -644,6 +598,7 @@ lt_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         mma_ts(d, p + 32 * (kk >> 1) + 16 + 8 * (kk & 1), v + 128 * kk, IDESC_O, 1);
                 }
                 mma_commit(&B->o_done[i]);
+                if (n + 2 >= nT) mma_commit(&B->o_final[i]);        // the last PV into O_i
                 if (i == 1) mma_commit(&B->kv_free[s]);
             };
             mbar_wait(&B->q_full, 0);
@@ -769,7 +724,7 @@ lt_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const int q = q0 + i * BM + row;
             float o[8];
             if (T > 0) {
-                mbar_wait(&B->o_done[i], (uint32_t)((T - 1) & 1));       // the last PV into O_i
+                mbar_wait(&B->o_final[i], 0);                            // the last PV into O_i
                 tc_fence_after();
                 uint32_t o0[8], o1[8];
                 tmem_ld8(tO + qt * 8, o0);

@@ -37,8 +37,9 @@ import os as _os
 LT_IMPL = _os.environ.get("AOTB_LT_IMPL", "tc_exact")
 LOCAL_IMPL = _os.environ.get("AOTB_LOCAL_IMPL", "tile")      # "tile" (halo in smem) | "warp" (generic kernel)
 # DeAOT long-term attention (1 head, d_qk 128, d_v 1024): "simt" fp32 flash kernel | "gemm" = tensor-core GEMM (Q K^T) ->
-# row softmax -> tensor-core GEMM (P V) over split-fp16 operand copies of the bank (deaot_lt.cu; built at the end of
-# round 1, host logic checked on CPU, kernels not yet run on a GPU -> not the default)
+# row softmax -> tensor-core GEMM (P V) over split-fp16 operand copies of the bank (deaot_lt.cu) | "tc" = fused tcgen05
+# kernel (gp_attn_tc.cu).  "gemm" and "tc" were built at the end of round 1: host logic checked on CPU, protocol of the
+# fused kernel model-checked, kernels not yet run on a GPU -> not the default
 DEAOT_LT = _os.environ.get("AOTB_DEAOT_LT", "simt")
 GEMM_GROW_FRAMES = int(_os.environ.get("AOTB_GEMM_GROW_FRAMES", "8"))   # bank growth step of the GEMM path (memory frames)
 _LT_NAMES = {"simt": "attn_f32_kernel<32,32> (fp32 SIMT flash attention)",
@@ -437,6 +438,13 @@ class AOTEngine(nn.Module):
         self._gemm_lt = bool(P.deaot and DEAOT_LT == "gemm")
         if self._gemm_lt:
             self._alloc_gemm_lt(cap, ws=ws)
+        self._gp_tc = bool(P.deaot and DEAOT_LT == "tc")
+        if self._gp_tc:
+            hz = lambda *s: torch.zeros(s, dtype=torch.float16, device=dev)
+            ws.gpQp = hz(self._kdim // 32, ((N + 127) // 128) * 128, 64)
+            self.bank_gpK = [hz(self._kdim // 32, cap, 64) for _ in range(L)]     # split-fp16 rows, one "head" / 32 channels
+            self.bank_gpV = [hz(self._vdim // 32, cap, 64) for _ in range(L)]
+            ws.gp_part = {}
         self._tc = LT_IMPL.startswith("tc") and (not P.deaot) and (C // P.H == 32)
         if self._tc:
             hz = lambda *s: torch.zeros(s, dtype=torch.float16, device=dev)
@@ -491,6 +499,12 @@ class AOTEngine(nn.Module):
                     lst[i] = nb
         if getattr(self, "_gemm_lt", False):
             self._alloc_gemm_lt(new_cap, self.bank_len, (self.bank_Kh, self.bank_Kl, self.bank_VhT, self.bank_VlT))
+        if getattr(self, "_gp_tc", False):
+            for lst in (self.bank_gpK, self.bank_gpV):
+                for i, old in enumerate(lst):
+                    nb = torch.zeros((old.shape[0], new_cap, 64), dtype=torch.float16, device=old.device)
+                    nb[:, : self.bank_len].copy_(old[:, : self.bank_len])
+                    lst[i] = nb
         self.bank_cap = new_cap
         self.graphs.clear()            # captured launches point at the old bank
 
@@ -670,6 +684,9 @@ class AOTEngine(nn.Module):
             if self._gemm_lt:
                 ops.split_rows(K_src[li], self.bank_Kh[li], self.bank_Kl[li], row_off_dev=off, stream=st)
                 ops.split_cols(V_src[li], self.bank_VhT[li], self.bank_VlT[li], col_off_dev=off, stream=st)
+            if getattr(self, "_gp_tc", False):
+                ops.tc_pack_rows(K_src[li], self.bank_gpK[li], 0, row_off_dev=off, stream=st)
+                ops.tc_pack_rows(V_src[li], self.bank_gpV[li], 0, row_off_dev=off, stream=st)
         ops.counter_add(off, N, stream=st)
         if count:
             self.bank_len += N
@@ -979,7 +996,21 @@ class DeAOTEngine(AOTEngine):
             if probe is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            if self._gemm_lt and not is_ref:
+            if self._gp_tc and not is_ref:
+                # fused tcgen05 kernel (gp_attn_tc.cu): 128 queries x 128 value channels per CTA, KV splits to fill the GPU
+                ops.tc_pack_rows(cQ, ws.gpQp, 0, div=math.sqrt(d), stream=st)
+                base = ((N + 127) // 128) * (C4 // 128)
+                tiles = (max(Tk, 1) + 63) // 64
+                splits = max(1, min(tiles // 4 if tiles >= 8 else 1, max(1, (2 * 148) // base)))
+                part = None
+                if splits > 1:
+                    part = ws.gp_part.get(splits)
+                    if part is None:
+                        fz = lambda *s: torch.empty(s, dtype=torch.float32, device=cQ.device)
+                        part = ws.gp_part[splits] = (fz(splits, N, C4), fz(splits, 1, N), fz(splits, 1, N))
+                ops.gp_attention_tc(ws.gpQp, self.bank_gpK[li], self.bank_gpV[li], N, Tk, O=ws.core, Tk_dev=self.tk_dev,
+                                    splits=splits, exact=True, part=part, stream=st)
+            elif self._gemm_lt and not is_ref:
                 # S = Q K^T -> softmax(S / T) over the live keys -> P V, all on the tensor-core GEMM (deaot_lt.cu)
                 ops.linear_tc(cQ, self.bank_Kh[li], self.bank_Kl[li], None, ws.S, stream=st)
                 ops.row_softmax(ws.S, self._capw, Tk, 1.0 / math.sqrt(d), Tk_dev=self.tk_dev, stream=st)

@@ -418,3 +418,22 @@ def lt_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True
     if splits > 1 and merge:
         attn_merge(Op, Mp, Lp, O, H, 32, stream=stream)
     return O
+
+
+def gp_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True, part=None, stream=None, merge=True):
+    """Fused DeAOT long-term attention (EXPERIMENTAL): Qp [4, Nq_cap, 64], Kp [4, kv_cap, 64], Vp [dv/32, kv_cap, 64] packed
+    fp16x2 (one 'head' per 32 channels); O [N, dv] fp32.  With splits > 1, `part` = (Opart [S,N,dv], Mpart [S,1,N],
+    Lpart [S,1,N]) and O receives the merge."""
+    nq_cap, kv_cap, dv = Qp.shape[1], Kp.shape[1], Vp.shape[0] * 32
+    if splits > 1:
+        Op, Mp, Lp = part
+    else:
+        Op = Mp = Lp = None
+    mode = (1 if exact else 0) | (4 if LT_SPIN else 0)
+    check(lib().aotb_gp_attn_tc_f16x2(Qp.data_ptr(), nq_cap, Kp.data_ptr(), Vp.data_ptr(), kv_cap, N, int(Tk),
+                                      Tk_dev.data_ptr() if Tk_dev is not None else None, dv,
+                                      _p(O) if splits == 1 else None, O.stride(0) if O is not None else 0,
+                                      _p(Op), _p(Mp), _p(Lp), splits, mode, _st(stream)), "aotb_gp_attn_tc_f16x2")
+    if splits > 1 and merge:
+        attn_merge(Op, Mp, Lp, O, 1, dv, stream=stream)
+    return O

@@ -195,6 +195,16 @@ int aotb_split_cols_f16x2(const float* src, int lds, void* hiT, void* loT, int l
                           const int* col_off_dev, void* stream);
 int aotb_row_softmax_f32(float* S, int ld, int N, int cols, int Tk, const int* Tk_dev, float scale, void* stream);
 
+/* DeAOT long-term attention fused on the tensor cores (EXPERIMENTAL, AOTB_DEAOT_LT=tc; gp_attn_tc.cu): GatedPropagation.forward
+ * networks/layers/attention.py:672-704 with 1 head, d_qk = 128, d_v = dv (1024).  Operands in the split-fp16 row format of
+ * aotb_tc_pack_rows_f16x2 with one "head" per 32 channels: Qp [4][Nq_cap][64] (Q / T, T = sqrt(128), Nq_cap a multiple of 128),
+ * Kp [4][kv_cap][64], Vp [dv/32][kv_cap][64].  O [N][ldo] = softmax((Q / T) K^T) V.  exact bit 0 / bit 2 as in
+ * aotb_lt_attn_tc_f16x2.  splits > 1 writes un-normalised partials Opart [splits][N][dv], Mpart / Lpart [splits][1][N] for
+ * aotb_attn_merge_f32 (H = 1, d_v = dv). */
+int aotb_gp_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp, const void* Vp, int kv_cap, int N, int Tk,
+                          const int* Tk_dev, int dv, float* O, int ldo, float* Opart, float* Mpart, float* Lpart,
+                          int splits, int exact, void* stream);
+
 /* Long-term memory append in place (replaces torch.cat, networks/engines/aot_engine.py:291-305). */
 int aotb_bank_append_f32(const float* src, int lds, float* bank, int ldb, int rows, int cols, int offset,
                          const int* offset_dev, void* stream);

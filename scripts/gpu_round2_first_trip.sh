@@ -9,6 +9,8 @@ note "1. whole GPU suite (includes the DeAOT GEMM-path kernels, events / skip go
 timeout 420 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_gpu.txt 2>&1; echo "exit $?" >> gpurun_out/r2_pytest_gpu.txt; tail -4 gpurun_out/r2_pytest_gpu.txt
 note "2. 'ahead' LT layout parity (three score buffers; never run on a GPU before) -- short timeout: a protocol bug would hang"
 AOTB_TEST_VARIANTS=ahead timeout 60 python -m pytest tests/test_gpu_tc.py -m gpu -q -k "layouts and ahead" > gpurun_out/r2_pytest_ahead.txt 2>&1; echo "exit $?" >> gpurun_out/r2_pytest_ahead.txt; tail -4 gpurun_out/r2_pytest_ahead.txt
+note "2b. fused DeAOT long-term attention kernel (gp_attn_tc.cu; never run on a GPU before) -- short timeout"
+AOTB_TEST_VARIANTS=gp_tc timeout 60 python -m pytest tests/test_gpu_zz_deaot_gemm.py -m gpu -q -k "fused" > gpurun_out/r2_pytest_gp_tc.txt 2>&1; echo "exit $?" >> gpurun_out/r2_pytest_gp_tc.txt; tail -4 gpurun_out/r2_pytest_gp_tc.txt
 note "3. LT microbench: tile vs ahead at 1 / 5 / 10 / 20 memory frames"
 timeout 60 python scripts/lt_microbench.py --variants tile,ahead --frames 1,5,10,20 --json gpurun_out/r2_lt_microbench.json 2>&1 | tail -9
 note "4. bench cfg2: default, then AOTB_LT_VARIANT=ahead"
@@ -17,6 +19,7 @@ AOTB_LT_VARIANT=ahead timeout 60 python bench.py --skip-cpu-baseline > gpurun_ou
 note "5. bench cfg3 model (r50_deaotl): SIMT long-term attention vs GEMM path"
 timeout 120 python bench.py --model r50_deaotl --skip-cpu-baseline > gpurun_out/r2_bench_deaotl_simt.json 2> gpurun_out/r2_bench_deaotl_simt.err; grep -o '"value": [0-9.]*\|avg_launch_us": [0-9.]*' gpurun_out/r2_bench_deaotl_simt.json | head -3
 AOTB_DEAOT_LT=gemm timeout 120 python bench.py --model r50_deaotl --skip-cpu-baseline > gpurun_out/r2_bench_deaotl_gemm.json 2> gpurun_out/r2_bench_deaotl_gemm.err; grep -o '"value": [0-9.]*\|avg_launch_us": [0-9.]*' gpurun_out/r2_bench_deaotl_gemm.json | head -3; tail -2 gpurun_out/r2_bench_deaotl_gemm.err
+AOTB_DEAOT_LT=tc timeout 120 python bench.py --model r50_deaotl --skip-cpu-baseline > gpurun_out/r2_bench_deaotl_tc.json 2> gpurun_out/r2_bench_deaotl_tc.err; grep -o '"value": [0-9.]*\|avg_launch_us": [0-9.]*' gpurun_out/r2_bench_deaotl_tc.json | head -3; tail -2 gpurun_out/r2_bench_deaotl_tc.err
 note "6. ncu --set full of a LONG LT launch (20 memory frames), default layout"
 timeout 90 ncu --set full --clock-control none --import-source on -k regex:lt_attn_tc -s 6 -c 1 -o gpurun_out/r2_prof_lt_m20 python scripts/lt_microbench.py --variants tile --frames 20 --reps 2 > gpurun_out/r2_prof_lt_m20.log 2>&1; ls -la gpurun_out/*.ncu-rep 2>/dev/null
 note "7. ncu launch list of the default bench (kernel shares of the step)"

@@ -51,6 +51,7 @@ class Sim:
         self.s_full = [MBar(1) for _ in range(3)]
         self.p_full = [MBar(1) for _ in range(3)]      # 512 thread arrivals modelled as one (lockstep agent)
         self.o_done = [MBar(1) for _ in range(2)]
+        self.o_final = [MBar(1) for _ in range(2)]
         self.pipe_free_at = 0.0        # in-order tensor pipe
         self.sbuf = [None, None, None]  # what each score buffer holds: ("S", n) | ("P", n) | None
         self.kv_stage = [None] * STAGES  # key tile resident in each smem stage
@@ -148,8 +149,11 @@ class Sim:
             def done(n=n, b=b):
                 self.sbuf[b] = ("Pused", n)
                 self.pv_done.add(n)
-            self.mma(self.rng.uniform(450, 600), done)
+            # occasionally a very slow PV: exposes waits that only hold when the tensor pipe keeps up
+            self.mma(self.rng.uniform(450, 600) * (8 if self.rng.random() < 0.15 else 1), done)
             self.commit(self.o_done[i])
+            if n + 2 >= nT:
+                self.commit(self.o_final[i])
             if i == 1:
                 self.commit(self.kv_free[s])
             yield ("delay", 5)
@@ -198,7 +202,7 @@ class Sim:
                 b = bn
         for i in (0, 1):
             if T > 0:
-                yield ("wait", self.o_done[i], (T - 1) & 1)
+                yield ("wait", self.o_final[i], 0)
                 assert all((2 * j + i) in self.pv_done for j in range(T)), f"epilogue read O_{i} early"
 
     def run(self):

@@ -349,11 +349,46 @@ def row_softmax(S, cols, Tk, scale, Tk_dev=None, stream=None):
     return S
 
 
+def gp_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True, part=None, stream=None, merge=True):
+    """Packed operands, one 'head' per 32 channels; 64-key tiles split over `splits`."""
+    tk = int(Tk_dev.item()) if Tk_dev is not None else int(Tk)
+
+    def unpack(P, rows, lo=True):              # [C/32, cap, 64] -> [rows, C]
+        x = P[:, :rows, :32].float() + (P[:, :rows, 32:].float() if lo else 0)
+        return x.permute(1, 0, 2).reshape(rows, -1)
+    q, k, v = unpack(Qp, N, exact), unpack(Kp, tk, exact), unpack(Vp, tk)
+    dv = v.shape[1]
+    tiles = (tk + 63) // 64
+    per = (tiles + splits - 1) // splits
+    parts = []
+    for z in range(splits):
+        k0, k1 = min(z * per * 64, tk), min((z + 1) * per * 64, tk)
+        if k1 > k0:
+            s = q @ k[k0:k1].t()
+            m = s.max(-1).values
+            p = torch.exp(s - m.unsqueeze(-1))
+            parts.append((p @ v[k0:k1], m, p.sum(-1)))
+        else:
+            parts.append((torch.zeros(N, dv), torch.full((N,), float("-inf")), torch.zeros(N)))
+    if splits == 1:
+        o, m, l = parts[0]
+        O.copy_(o / l.unsqueeze(-1))
+        return O
+    Op, Mp, Lp = part
+    for z, (o, m, l) in enumerate(parts):
+        Op[z].copy_(o)
+        Mp[z, 0].copy_(m)
+        Lp[z, 0].copy_(l)
+    if merge:
+        attn_merge(Op, Mp, Lp, O, 1, dv)
+    return O
+
+
 EMULATED = ("image_to_nhwc4", "conv2d", "linear", "layernorm", "window_attention", "patch_merge", "eltwise",
             "nchw_to_nhwc", "nhwc_to_nchw", "maxpool3x3s2", "dwconv", "bilinear", "groupnorm_workspace", "groupnorm",
             "attention", "attn_merge", "tc_pack_rows", "lt_attention_tc", "local_attention", "local_attention_tile",
             "id_embed", "id_embed_runs", "logits_postproc", "logits_argmax", "nearest_resize", "bank_append",
-            "counter_add", "linear_tc", "split_rows", "split_cols", "row_softmax")
+            "counter_add", "linear_tc", "split_rows", "split_cols", "row_softmax", "gp_attention_tc")
 
 
 class _FakeStream:

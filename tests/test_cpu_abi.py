@@ -119,7 +119,7 @@ def test_kernel_register_budgets_fit_their_block_sizes():
     r = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True)
     if r.returncode != 0:
         pytest.skip("cuobjdump unavailable")
-    blocks = {"lt_attn_tc_kernel": 576, "lt_attn_tc3_kernel": 576, "conv_tc_kernel": 320, "local_attn_tile_kernel": 512,
+    blocks = {"lt_attn_tc_kernel": 576, "lt_attn_tc3_kernel": 576, "gp_attn_tc_kernel": 608, "conv_tc_kernel": 320, "local_attn_tile_kernel": 512,
               "conv_igemm_kernel": 256, "attn_f32_kernel": 256, "local_attn_kernel": 256, "window_attn_kernel": 64}
     cur, seen = None, 0
     for line in r.stdout.splitlines():
@@ -136,4 +136,4 @@ def test_kernel_register_budgets_fit_their_block_sizes():
                     warps4 = (warps + 3) // 4 * 4
                     assert regs * 32 * warps4 <= 65536, f"{cur}: {regs} regs x {threads} threads does not fit"
                     seen += 1
-    assert seen >= 8
+    assert seen >= 9

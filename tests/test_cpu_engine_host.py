@@ -107,3 +107,26 @@ def test_engine_edge_cases_vs_oracle(monkeypatch, model_name, H, W, objs):
         assert (a[:, :n] - b[:, :n]).abs().max().item() < 2e-4
     if objs == 0:
         assert all(int(l.max()) == 0 for l in c_labels)          # nothing but background can be predicted
+
+
+@pytest.mark.parametrize("name", ["r50_deaotl_small", "deaott_skip3"])
+def test_deaot_fused_tc_long_term_attention_orchestration(monkeypatch, golden_dir, name):
+    """AOTB_DEAOT_LT=tc: the packed-operand bank copies ([C/32][cap][64] split-fp16 rows), the Q packing with the 1/T
+    division, the KV-split policy + merge and the capacity growth around the fused kernel give the reference's logits."""
+    import emu_ops
+    from aot_benchmark_b200 import engine
+    emu_ops.install_engine(monkeypatch)
+    monkeypatch.setattr(engine, "DEAOT_LT", "tc")
+    monkeypatch.setattr(engine, "BANK_INIT_FRAMES", 1)
+    g = torch.load(os.path.join(golden_dir, f"video_{name}.pt"))
+    sd = OW.build_state_dict(g["model"], seed=g["seed"], flavour=g["flavour"])
+    frames, mask = O.synthetic_video(g["frames"], g["H"], g["W"], g["objs"], seed=1234 + g["seed"])
+    eng = _engine(g["model"], sd, g["gap"], g.get("skip"))
+    with torch.no_grad():
+        lo, _ = O.run_video(eng, frames, mask, g["objs"], tuple(g["out_size"]),
+                            forced_masks=[l.float() for l in g["ref_labels"]])
+    e0 = eng.aot_engines[0]
+    assert e0._gp_tc and e0.bank_len > e0.enc_hw
+    n = g["objs"] + 1
+    dmax = max((a[:, :n] - b[:, :n]).abs().max().item() for a, b in zip(lo, g["ref_logits_lo"]))
+    assert dmax < 2e-4, f"max |dlogit| vs reference = {dmax}"

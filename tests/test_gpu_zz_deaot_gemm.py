@@ -96,3 +96,64 @@ def test_deaot_engine_gemm_path_vs_reference_golden(golden_dir, monkeypatch):
     n = g["objs"] + 1
     dmax = max((a.cpu()[:, :n] - b[:, :n]).abs().max().item() for a, b in zip(lo, g["ref_logits_lo"]))
     assert dmax < 1e-3, f"max |dlogit| vs reference = {dmax}"
+
+
+def _gp_enabled():
+    from aot_benchmark_b200 import engine
+    return engine.DEAOT_LT == "tc" or "gp_tc" in os.environ.get("AOTB_TEST_VARIANTS", "").split(",")
+
+
+@pytest.mark.parametrize("N,Tk,splits,exact", [(128, 64, 1, True), (176, 176 * 3 + 11, 1, True), (1674, 1674 * 2, 2, True),
+                                               (300, 1000, 4, True), (200, 100, 4, True), (176, 600, 1, False)])
+def test_fused_gp_attention_kernel(N, Tk, splits, exact):
+    """EXPERIMENTAL fused DeAOT long-term attention (gp_attn_tc.cu) vs the fp32 SIMT kernel and the fp64 oracle."""
+    if not _gp_enabled():
+        pytest.skip("fused DeAOT kernel not enabled (AOTB_DEAOT_LT=tc or AOTB_TEST_VARIANTS=gp_tc)")
+    from aot_benchmark_b200 import ops
+    from oracle import aot_oracle as O
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(N + Tk)
+    Q = (torch.randn(N, 128, generator=g) * 2).to(d)
+    K = torch.randn(Tk, 128, generator=g).to(d)
+    V = torch.randn(Tk, 1024, generator=g).to(d)
+    ncap, kcap = ((N + 127) // 128) * 128, ((Tk + 63) // 64) * 64 + 64
+    Qp = torch.zeros(4, ncap, 64, dtype=torch.float16, device=d)
+    Kp = torch.zeros(4, kcap, 64, dtype=torch.float16, device=d)
+    Vp = torch.zeros(32, kcap, 64, dtype=torch.float16, device=d)
+    ops.tc_pack_rows(Q, Qp, 0, div=math.sqrt(128.0))
+    ops.tc_pack_rows(K, Kp, 0)
+    ops.tc_pack_rows(V, Vp, 0)
+    part = None
+    if splits > 1:
+        part = (torch.zeros(splits, N, 1024, device=d), torch.zeros(splits, 1, N, device=d), torch.zeros(splits, 1, N, device=d))
+    out = torch.full((N, 1024), float("nan"), device=d)
+    ops.gp_attention_tc(Qp, Kp, Vp, N, Tk, O=out, splits=splits, exact=exact, part=part)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    simt = torch.empty(N, 1024, device=d)
+    ops.attention(Q, K, V, simt, 1, 128, 1024)
+    tol = 1e-4 if exact else 2e-2
+    assert (out - simt).abs().max().item() < tol
+    ref = O.multihead_attention(Q.double().cpu().unsqueeze(1), K.double().cpu().unsqueeze(1),
+                                V.double().cpu().unsqueeze(1), 1, d_att=128)[:, 0]
+    assert (out.cpu().double() - ref).abs().max().item() < tol
+
+
+def test_deaot_engine_fused_tc_path_vs_reference_golden(golden_dir, monkeypatch):
+    if not _gp_enabled():
+        pytest.skip("fused DeAOT kernel not enabled (AOTB_DEAOT_LT=tc or AOTB_TEST_VARIANTS=gp_tc)")
+    from aot_benchmark_b200 import engine
+    from oracle import aot_oracle as O
+    from oracle import weights as OW
+    from test_gpu_engine import _build_cuda_engine
+    monkeypatch.setattr(engine, "DEAOT_LT", "tc")
+    g = torch.load(os.path.join(golden_dir, "video_r50_deaotl_small.pt"))
+    sd = OW.build_state_dict(g["model"], seed=g["seed"], flavour=g["flavour"])
+    frames, mask = O.synthetic_video(g["frames"], g["H"], g["W"], g["objs"], seed=1234 + g["seed"])
+    eng = _build_cuda_engine(g["model"], sd, g["gap"])
+    with torch.no_grad():
+        lo, _ = O.run_video(eng, [f.cuda() for f in frames], mask.cuda(), g["objs"], tuple(g["out_size"]),
+                            forced_masks=[l.float() for l in g["ref_labels"]])
+    n = g["objs"] + 1
+    dmax = max((a.cpu()[:, :n] - b[:, :n]).abs().max().item() for a, b in zip(lo, g["ref_logits_lo"]))
+    assert dmax < 1e-3, f"max |dlogit| vs reference = {dmax}"
