@@ -58,3 +58,63 @@ def test_two_rank_sharded_bank_merge_and_partition():
         assert abs(t - 11.0) < 1e-9
     assert sorted(ret[0][2] + ret[1][2]) == list(range(7))
     assert sorted(ret[0][3] + ret[1][3]) == list(range(5))
+
+
+class _MP:
+    """pytest's monkeypatch is not available inside spawned workers: plain setattr is enough there."""
+    def setattr(self, obj, name, val):
+        setattr(obj, name, val)
+
+
+def _engine_worker(rank, world, port, ret):
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import emu_ops
+    from aot_benchmark_b200 import EngineConfig, build_engine, build_vos_model
+    from oracle import aot_oracle as O
+    from oracle import weights as OW
+    emu_ops.install_engine(_MP())
+    name, H, W, objs, T = "aott", 97, 129, 3, 6
+    sd = OW.build_state_dict(name, seed=1)
+    cfg = EngineConfig("t", name)
+    model = build_vos_model(cfg.MODEL_VOS, cfg).eval()
+    model.load_state_dict(sd)
+    frames, mask = O.synthetic_video(T, H, W, objs, seed=3)
+    outs = {}
+    for mode in ("plain", "sharded"):
+        eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=0, long_term_mem_gap=1)
+        if mode == "sharded":
+            eng.enable_kv_sharding(rank, world)
+        with torch.no_grad():
+            lo, labels = O.run_video(eng, frames, mask, objs, (H, W),
+                                     forced_masks=outs["plain"][1] if mode == "sharded" else None)
+        outs[mode] = (lo, labels)
+        if mode == "sharded":
+            e0 = eng.aot_engines[0]
+            local_rows, mem_frames, n = e0.bank_len, e0._mem_frames, e0.enc_hw
+    d = max((a[:, :objs + 1] - b[:, :objs + 1]).abs().max().item() for a, b in zip(outs["plain"][0], outs["sharded"][0]))
+    ret[rank] = (d, local_rows, mem_frames, n)
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_engine_matches_unsharded():
+    """BASELINE configs[3] mechanism end to end on CPU: two ranks run the drop-in engine (C-ABI entry points emulated) with
+    the long-term bank sharded by memory frame; the all-gather + exact merge must reproduce the unsharded logits, and
+    the memory frames must be split between the ranks."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_engine_worker, args=(world, 29717 + os.getpid() % 200, ret), nprocs=world, join=True)
+    assert len(ret) == 2
+    rows = 0
+    for rank in range(world):
+        d, local_rows, mem_frames, n = ret[rank]
+        assert d < 1e-4, f"rank {rank}: sharded vs unsharded max |dlogit| = {d}"
+        assert mem_frames == 6                       # reference frame + 5 propagated frames at gap 1
+        rows += local_rows
+    assert rows == 6 * ret[0][3]                      # every memory frame lives on exactly one rank
+    assert ret[0][1] == ret[1][1] == 3 * ret[0][3]    # round-robin: three frames each
