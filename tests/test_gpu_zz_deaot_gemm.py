@@ -45,7 +45,7 @@ def test_row_softmax_kernel(N, cols, live):
     tk = torch.tensor([live], dtype=torch.int32, device=d)
     ops.row_softmax(S, cols, 0, 1.0 / math.sqrt(128.0), Tk_dev=tk)
     torch.cuda.synchronize()
-    assert (S.cpu().double() - want).abs().max().item() < 2e-6
+    assert (S.cpu().double() - want).abs().max().item() < 5e-6
     assert S[:, live:].abs().max().item() == 0 if live < cols else True
 
 
