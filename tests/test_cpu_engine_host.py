@@ -89,10 +89,12 @@ def test_deaot_gemm_long_term_attention_orchestration(monkeypatch, golden_dir, n
     assert dmax < 2e-4, f"max |dlogit| vs reference = {dmax}"
 
 
-@pytest.mark.parametrize("model_name,H,W,objs", [("aott", 100, 150, 0), ("aott", 83, 61, 1), ("deaott", 70, 95, 10)])
+@pytest.mark.parametrize("model_name,H,W,objs", [("aott", 100, 150, 0), ("aott", 83, 61, 1), ("deaott", 70, 95, 10),
+                                                 ("aotb", 97, 113, 4), ("deaotl", 81, 129, 3)])
 def test_engine_edge_cases_vs_oracle(monkeypatch, model_name, H, W, objs):
-    """No objects at all, a single object on a tiny odd-sized frame, the maximum object count of one engine: the product
-    engine (emulated entry points) against the oracle on the same seeded inputs, free-running (no teacher forcing)."""
+    """No objects at all, a single object on a tiny odd-sized frame, the maximum object count of one engine, and the
+    multi-layer MobileNetV2 configurations (AOT-B: 3 LSTT layers; DeAOT-L: 3 GPM layers): the product engine (emulated
+    entry points) against the oracle on the same seeded inputs, free-running (no teacher forcing)."""
     import emu_ops
     emu_ops.install_engine(monkeypatch)
     sd = OW.build_state_dict(model_name, seed=5)
