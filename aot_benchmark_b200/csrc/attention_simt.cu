@@ -255,6 +255,57 @@ __global__ void attn_merge_kernel(const float* __restrict__ Opart, const float* 
 }
 }  // namespace aotb
 
+// ---------------------------------------------------------------- split-KV merge over PEER memory (cfg4 row e.2)
+// Same merge, but the partials of rank r are read straight from rank r's buffer: the pointers are peer mappings of a
+// symmetric-memory allocation (NVLink P2P loads), so the gather of the exchange step happens inside this kernel instead of
+// in three NCCL all-gathers.  Rank r's arrays are Opart_r [S][N][H*dv], Mpart_r / Lpart_r [S][H][N]; partials are visited
+// in (rank, split) order on every rank, so all ranks produce bit-identical outputs.
+namespace aotb {
+struct MergePeers { const float* O[8]; const float* M[8]; const float* L[8]; };
+
+__global__ void attn_merge_peers_kernel(const MergePeers p, float* __restrict__ O, int R, int S, int N, int H, int dv,
+                                        int ldo) {
+    pdl_sync();
+    const size_t total = (size_t)N * H * dv;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = i % dv;
+        const int h = (i / dv) % H;
+        const int q = i / ((size_t)dv * H);
+        float m = -INFINITY;
+        for (int r = 0; r < R; ++r)
+            for (int s = 0; s < S; ++s) m = fmaxf(m, p.M[r][((size_t)s * H + h) * N + q]);
+        float num = 0.f, den = 0.f;
+        for (int r = 0; r < R; ++r)
+            for (int s = 0; s < S; ++s) {
+                const float mr = p.M[r][((size_t)s * H + h) * N + q];
+                const float w = (mr == -INFINITY) ? 0.f : expf(mr - m);
+                num += w * p.O[r][((size_t)s * N + q) * H * dv + (size_t)h * dv + c];
+                den += w * p.L[r][((size_t)s * H + h) * N + q];
+            }
+        O[(size_t)q * ldo + (size_t)h * dv + c] = num / den;
+    }
+}
+}  // namespace aotb
+
+// Oparts / Mparts / Lparts: HOST arrays of `ranks` device pointers (local buffer + peer mappings), ranks <= 8.
+extern "C" int aotb_attn_merge_peers_f32(const void* const* Oparts, const void* const* Mparts, const void* const* Lparts,
+                                         int ranks, int splits, float* O, int N, int H, int d_v, int ldo, void* stream) {
+    AOTB_REQUIRE(Oparts && Mparts && Lparts && O && ranks > 0 && ranks <= 8 && splits > 0 && N > 0 && H > 0 && d_v > 0,
+                 "aotb_attn_merge_peers_f32: bad args (at most 8 ranks)");
+    MergePeers p;
+    for (int r = 0; r < 8; ++r) {
+        p.O[r] = r < ranks ? (const float*)Oparts[r] : nullptr;
+        p.M[r] = r < ranks ? (const float*)Mparts[r] : nullptr;
+        p.L[r] = r < ranks ? (const float*)Lparts[r] : nullptr;
+        AOTB_REQUIRE(r >= ranks || (p.O[r] && p.M[r] && p.L[r]), "aotb_attn_merge_peers_f32: null peer pointer");
+    }
+    const size_t total = (size_t)N * H * d_v;
+    int g = (int)((total + 255) / 256);
+    if (g > 148 * 8) g = 148 * 8;
+    launch(attn_merge_peers_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, p, O, ranks, splits, N, H, d_v, ldo);
+    return check_launch("aotb_attn_merge_peers_f32");
+}
+
 extern "C" int aotb_attn_merge_f32(const float* Opart, const float* Mpart, const float* Lpart, float* O, int R,
                                    int N, int H, int d_v, int ldo, void* stream) {
     AOTB_REQUIRE(Opart && Mpart && Lpart && O && R > 0 && N > 0 && H > 0 && d_v > 0, "aotb_attn_merge_f32: bad args");

@@ -41,6 +41,23 @@ LOCAL_IMPL = _os.environ.get("AOTB_LOCAL_IMPL", "tile")      # "tile" (halo in s
 # kernel (gp_attn_tc.cu).  "gemm" and "tc" were built at the end of round 1: host logic checked on CPU, protocol of the
 # fused kernel model-checked, kernels not yet run on a GPU -> not the default
 DEAOT_LT = _os.environ.get("AOTB_DEAOT_LT", "simt")
+# exchange step of the sharded long-term bank (BASELINE configs[3]): "nccl" = three all-gathers of the (m, l, O) partials +
+# local merge; "p2p" = the partials live in a torch symmetric-memory allocation and every rank's merge kernel reads its
+# peers' partials in place over NVLink (aotb_attn_merge_peers_f32) behind one device-side barrier -- no NCCL on the data
+# path.  "p2p" was written without multi-GPU access (logic checked on CPU with an in-process stand-in for the allocator).
+SHARD_XCHG = _os.environ.get("AOTB_SHARD_XCHG", "nccl")
+SHARD_SMAX = 16          # split capacity of the symmetric partial buffers
+
+
+def _symm_alloc(numel, device, group):
+    """-> (handle, rank -> flat fp32 view of that rank's buffer) for a symmetric-memory allocation of `numel` floats."""
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    t = symm_mem.empty(numel, dtype=torch.float32, device=device)
+    hdl = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+    return hdl, (lambda r, sizes, off: hdl.get_buffer(r, sizes, torch.float32, off))
+
+
 GEMM_GROW_FRAMES = int(_os.environ.get("AOTB_GEMM_GROW_FRAMES", "8"))   # bank growth step of the GEMM path (memory frames)
 _LT_NAMES = {"simt": "attn_f32_kernel<32,32> (fp32 SIMT flash attention)",
              "tc_exact": "lt_attn_tc_kernel (tcgen05 fp16x2 exact: 6+16 MMAs/tile)",
@@ -809,6 +826,8 @@ class AOTEngine(nn.Module):
         N = self.enc_hw
         frames_per_rank = (self._mem_frames + world - 1) // world
         splits = max(2, lt_splits(N, P.H, max(frames_per_rank, 1) * N))      # identical on every rank
+        if SHARD_XCHG == "p2p":
+            return self._sharded_attention_p2p(li, out, st, splits)
         key = ("shard", splits)
         bufs = ws.part.get(key)
         if bufs is None:
@@ -826,6 +845,37 @@ class AOTEngine(nn.Module):
         dist.all_gather_into_tensor(Mg, Mp, group=group)
         dist.all_gather_into_tensor(Lg, Lp, group=group)
         ops.attn_merge(Og, Mg, Lg, out, P.H, P.C // P.H, stream=st)
+
+    def _sharded_attention_p2p(self, li, out, st, splits):
+        """Exchange over peer memory: the local partials are written into this rank's slice of a symmetric allocation, one
+        device-side barrier makes every rank's partials of this layer visible, and the merge kernel reads all ranks'
+        partials in place (NVLink P2P loads).  One allocation per layer, so the next write of a buffer (this layer, next
+        frame) is separated from its readers by the barriers of the other layers; single-layer models add a second barrier."""
+        rank, world, group = self.kv_shard
+        P = self._plan()
+        ws = self._ws
+        N, C, H = self.enc_hw, P.C, P.H
+        assert splits <= SHARD_SMAX
+        key = ("p2p", li)
+        buf = ws.part.get(key)
+        if buf is None:
+            nO, nM = SHARD_SMAX * N * C, SHARD_SMAX * H * N
+            hdl, view = _symm_alloc(nO + 2 * nM, out.device, group)
+            views = [(view(r, (SHARD_SMAX, N, C), 0), view(r, (SHARD_SMAX, H, N), nO), view(r, (SHARD_SMAX, H, N), nO + nM))
+                     for r in range(world)]
+            buf = ws.part[key] = (hdl, views)
+        hdl, views = buf
+        Op, Mp, Lp = (t[:splits] for t in views[rank])
+        if self.bank_len > 0:
+            ops.lt_attention_tc(ws.Qp, self.bank_Kp[li], self.bank_Vp[li], N, self.bank_len, O=None, Tk_dev=self.tk_dev,
+                                splits=splits, exact=(LT_IMPL == "tc_exact"), part=(Op, Mp, Lp), stream=st, merge=False)
+        else:                                  # this rank holds no memory frame yet: neutral partial
+            Op.zero_(); Lp.zero_(); Mp.fill_(float("-inf"))
+        hdl.barrier()
+        ops.attn_merge_peers([v[0] for v in views], [v[1] for v in views], [v[2] for v in views], out, splits, H, C // H,
+                             stream=st)
+        if P.L < 2:
+            hdl.barrier()
 
     # short-term memory slots (TEST_SHORT_TERM_MEM_SKIP ring, aot_engine.py:329-332)
     def _next_short_slot(self):

@@ -292,6 +292,18 @@ def attn_merge(Opart, Mpart, Lpart, O, H, d_v, stream=None):
     return O
 
 
+def attn_merge_peers(Oparts, Mparts, Lparts, O, splits, H, d_v, stream=None):
+    """Merge split-KV partials that live in `len(Oparts)` ranks' buffers (local tensor + peer views of a symmetric-memory
+    allocation): Oparts[r] [>=splits, N, H*d_v], Mparts[r] / Lparts[r] [>=splits, H, N]."""
+    import ctypes
+    _chk(O, *Oparts, *Mparts, *Lparts)
+    R, N = len(Oparts), O.shape[0]
+    arr = lambda ts: (ctypes.c_void_p * R)(*[t.data_ptr() for t in ts])
+    check(lib().aotb_attn_merge_peers_f32(arr(Oparts), arr(Mparts), arr(Lparts), R, int(splits), _p(O), N, H, d_v,
+                                          O.stride(0), _st(stream)), "aotb_attn_merge_peers_f32")
+    return O
+
+
 def local_attention(q, k, v, relk_w, relk_b, relv, out, h, w, H, d_att, d_v, stream=None):
     """q,k [hw, H*d_att], v [hw, H*d_v], out [hw, H*d_v]."""
     _chk(q, k, v, relk_w, relk_b, relv, out)

@@ -121,6 +121,14 @@ int aotb_attention_f32(const float* Q, int ldq, const float* K, int ldk, const f
 int aotb_attn_merge_f32(const float* Opart, const float* Mpart, const float* Lpart, float* O, int R, int N,
                         int H, int d_v, int ldo, void* stream);
 
+/* The same merge with every rank's partials read in place over peer memory (sharded long-term bank, BASELINE configs[3]):
+ * Oparts / Mparts / Lparts are HOST arrays of `ranks` (<= 8) device pointers -- the local buffer and the NVLink peer mappings
+ * of a symmetric-memory allocation -- to Opart_r [splits][N][H*d_v] and Mpart_r / Lpart_r [splits][H][N]; the exchange step of
+ * the split-KV attention (otherwise three NCCL all-gathers per layer) is the P2P loads of this kernel.  Partials are merged in
+ * (rank, split) order on every rank: outputs are bit-identical across ranks. */
+int aotb_attn_merge_peers_f32(const void* const* Oparts, const void* const* Mparts, const void* const* Lparts, int ranks,
+                              int splits, float* O, int N, int H, int d_v, int ldo, void* stream);
+
 /* 15x15 local-window attention with relative_emb_k / relative_emb_v:
  * networks/layers/attention.py:308-428 (MultiheadLocalAttentionV2) and :789-914 (LocalGatedPropagation);
  * replaces the third-party spatial_correlation_sampler call sites :341,:828. */

@@ -27,19 +27,25 @@ def main():
     frames = [f.cuda() for f in frames]
     mask = mask.cuda()
     outs = {}
-    for mode in ("plain", "sharded"):
+    from aot_benchmark_b200 import engine as engine_mod
+    modes = ("plain", "sharded") + (("sharded_p2p",) if os.environ.get("AOTB_TEST_P2P", "1") == "1" else ())
+    for mode in modes:
+        engine_mod.SHARD_XCHG = "p2p" if mode == "sharded_p2p" else "nccl"      # peer-memory exchange vs NCCL all-gathers
         eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=local, long_term_mem_gap=1)
-        if mode == "sharded":
+        if mode != "plain":
             eng.enable_kv_sharding(rank, world)
         with torch.no_grad():
             lo, labels = O.run_video(eng, frames, mask, 10, (240, 320),
-                                     forced_masks=outs["plain"][1] if mode == "sharded" else None)
+                                     forced_masks=outs["plain"][1] if mode != "plain" else None)
         outs[mode] = (lo, labels)
-        if mode == "sharded":
+        if mode != "plain":
             e0 = eng.aot_engines[0]
-            print(f"rank {rank}: local bank rows {e0.bank_len} of {e0._mem_frames} memory frames x {e0.enc_hw}")
-    d = max((a[:, :11] - b[:, :11]).abs().max().item() for a, b in zip(outs["plain"][0], outs["sharded"][0]))
-    print(f"rank {rank}/{world}: max |dlogit| sharded vs unsharded = {d:.3e}")
+            print(f"rank {rank}: [{mode}] local bank rows {e0.bank_len} of {e0._mem_frames} memory frames x {e0.enc_hw}")
+    d = 0.0
+    for mode in modes[1:]:
+        dm = max((a[:, :11] - b[:, :11]).abs().max().item() for a, b in zip(outs["plain"][0], outs[mode][0]))
+        print(f"rank {rank}/{world}: max |dlogit| {mode} vs unsharded = {dm:.3e}")
+        d = max(d, dm)
     t = torch.tensor([d], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.destroy_process_group()

@@ -201,6 +201,13 @@ def attn_merge(Opart, Mpart, Lpart, O, H, d_v, stream=None):
     return O
 
 
+def attn_merge_peers(Oparts, Mparts, Lparts, O, splits, H, d_v, stream=None):
+    Og = torch.cat([t[:splits] for t in Oparts], dim=0)
+    Mg = torch.cat([t[:splits] for t in Mparts], dim=0)
+    Lg = torch.cat([t[:splits] for t in Lparts], dim=0)
+    return attn_merge(Og, Mg, Lg, O, H, d_v)
+
+
 def tc_pack_rows(src, dst, row_off=0, div=1.0, row_off_dev=None, stream=None):
     """fp32 [rows, H*32] -> fp16 [H, cap, 64] rows [off, off+rows) as [hi(32) | lo(32)], values / div first."""
     Hh = dst.shape[0]
@@ -386,7 +393,7 @@ def gp_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True
 
 EMULATED = ("image_to_nhwc4", "conv2d", "linear", "layernorm", "window_attention", "patch_merge", "eltwise",
             "nchw_to_nhwc", "nhwc_to_nchw", "maxpool3x3s2", "dwconv", "bilinear", "groupnorm_workspace", "groupnorm",
-            "attention", "attn_merge", "tc_pack_rows", "lt_attention_tc", "local_attention", "local_attention_tile",
+            "attention", "attn_merge", "attn_merge_peers", "tc_pack_rows", "lt_attention_tc", "local_attention", "local_attention_tile",
             "id_embed", "id_embed_runs", "logits_postproc", "logits_argmax", "nearest_resize", "bank_append",
             "counter_add", "linear_tc", "split_rows", "split_cols", "row_softmax", "gp_attention_tc")
 

@@ -118,3 +118,81 @@ def test_two_rank_sharded_engine_matches_unsharded():
         rows += local_rows
     assert rows == 6 * ret[0][3]                      # every memory frame lives on exactly one rank
     assert ret[0][1] == ret[1][1] == 3 * ret[0][3]    # round-robin: three frames each
+
+
+def test_sharded_engine_peer_memory_exchange(monkeypatch):
+    """AOTB_SHARD_XCHG=p2p: the partials live in per-rank buffers that every rank's merge reads in place behind a
+    barrier (torch symmetric memory + aotb_attn_merge_peers_f32 on GPUs).  Here: two ranks as two threads of one process, the
+    allocator replaced by an in-process stand-in (shared tensors + threading.Barrier), entry points emulated -- the
+    sharded logits must equal the unsharded ones, for a 1-layer (second barrier) and a 3-layer model."""
+    import threading
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import emu_ops
+    from aot_benchmark_b200 import EngineConfig, build_engine, build_vos_model, engine
+    from oracle import aot_oracle as O
+    from oracle import weights as OW
+    emu_ops.install_engine(monkeypatch)
+    monkeypatch.setattr(engine, "SHARD_XCHG", "p2p")
+    world = 2
+
+    class Registry:
+        def __init__(self):
+            self.lock, self.bufs, self.count = threading.Lock(), {}, {}
+            self.bar = threading.Barrier(world)
+
+    class Group:                       # what enable_kv_sharding receives as `group`
+        def __init__(self, rank, reg):
+            self.rank, self.reg = rank, reg
+
+    class Handle:
+        def __init__(self, reg):
+            self.reg = reg
+
+        def barrier(self, channel=0):
+            self.reg.bar.wait(timeout=120)
+
+    def fake_alloc(numel, device, group):
+        reg = group.reg
+        with reg.lock:
+            k = reg.count.get(group.rank, 0)          # the k-th allocation of this rank pairs with the k-th of its peers
+            reg.count[group.rank] = k + 1
+            for r in range(world):
+                reg.bufs.setdefault((k, r), torch.zeros(numel))
+        reg.bar.wait(timeout=120)                     # rendezvous
+        return Handle(reg), (lambda r, sizes, off: reg.bufs[(k, r)][off:off + int(torch.Size(sizes).numel())].view(sizes))
+
+    monkeypatch.setattr(engine, "_symm_alloc", fake_alloc)
+    for name in ("aott", "aotb"):
+        H, W, objs, T = 97, 129, 3, 6
+        sd = OW.build_state_dict(name, seed=1)
+        cfg = EngineConfig("t", name)
+        model = build_vos_model(cfg.MODEL_VOS, cfg).eval()
+        model.load_state_dict(sd)
+        frames, mask = O.synthetic_video(T, H, W, objs, seed=3)
+        plain = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=0, long_term_mem_gap=1)
+        with torch.no_grad():
+            p_lo, p_labels = O.run_video(plain, frames, mask, objs, (H, W))
+        reg, res, errs = Registry(), {}, []
+
+        def worker(rank):
+            try:
+                eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=0, long_term_mem_gap=1)
+                eng.enable_kv_sharding(rank, world, Group(rank, reg))
+                with torch.no_grad():
+                    lo, _ = O.run_video(eng, frames, mask, objs, (H, W), forced_masks=p_labels)
+                res[rank] = (lo, eng.aot_engines[0].bank_len, eng.aot_engines[0].enc_hw)
+            except Exception as e:                     # pragma: no cover
+                errs.append(repr(e))
+                reg.bar.abort()
+
+        ths = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join(timeout=600)
+        assert not errs, errs
+        for rank in range(world):
+            lo, rows, n = res[rank]
+            d = max((a[:, :objs + 1] - b[:, :objs + 1]).abs().max().item() for a, b in zip(p_lo, lo))
+            assert d < 1e-4, f"{name} rank {rank}: peer-memory sharded vs unsharded max |dlogit| = {d}"
+            assert rows == 3 * n

@@ -157,3 +157,23 @@ def test_deaot_engine_fused_tc_path_vs_reference_golden(golden_dir, monkeypatch)
     n = g["objs"] + 1
     dmax = max((a.cpu()[:, :n] - b[:, :n]).abs().max().item() for a, b in zip(lo, g["ref_logits_lo"]))
     assert dmax < 1e-3, f"max |dlogit| vs reference = {dmax}"
+
+
+def test_attn_merge_peers_kernel_matches_gathered_merge():
+    """aotb_attn_merge_peers_f32 over several buffers (stand-ins for peer mappings) == aotb_attn_merge_f32 over their
+    concatenation, bit for bit (same (rank, split) visiting order)."""
+    from aot_benchmark_b200 import ops
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(9)
+    R, S, SMAX, N, H, dv = 3, 2, 4, 333, 8, 32
+    Os = [torch.randn(SMAX, N, H * dv, generator=g).to(d) for _ in range(R)]
+    Ms = [(torch.randn(SMAX, H, N, generator=g) * 5).to(d) for _ in range(R)]
+    Ls = [(torch.rand(SMAX, H, N, generator=g) + 0.5).to(d) for _ in range(R)]
+    Ms[1][0, :, :50] = float("-inf")                        # an empty shard for some rows
+    Ls[1][0, :, :50] = 0
+    out = torch.empty(N, H * dv, device=d)
+    ops.attn_merge_peers(Os, Ms, Ls, out, S, H, dv)
+    ref = torch.empty(N, H * dv, device=d)
+    ops.attn_merge(torch.cat([t[:S] for t in Os]), torch.cat([t[:S] for t in Ms]), torch.cat([t[:S] for t in Ls]), ref, H, dv)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
