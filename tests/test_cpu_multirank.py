@@ -78,7 +78,7 @@ def _engine_worker(rank, world, port, ret):
     from oracle import aot_oracle as O
     from oracle import weights as OW
     emu_ops.install_engine(_MP())
-    name, H, W, objs, T = "aott", 97, 129, 3, 6
+    name, H, W, objs, T = "aott", 65, 81, 2, 6
     sd = OW.build_state_dict(name, seed=1)
     cfg = EngineConfig("t", name)
     model = build_vos_model(cfg.MODEL_VOS, cfg).eval()
@@ -163,7 +163,7 @@ def test_sharded_engine_peer_memory_exchange(monkeypatch):
 
     monkeypatch.setattr(engine, "_symm_alloc", fake_alloc)
     for name in ("aott", "aotb"):
-        H, W, objs, T = 97, 129, 3, 6
+        H, W, objs, T = 65, 81, 2, 6
         sd = OW.build_state_dict(name, seed=1)
         cfg = EngineConfig("t", name)
         model = build_vos_model(cfg.MODEL_VOS, cfg).eval()
