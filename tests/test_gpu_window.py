@@ -127,3 +127,43 @@ def test_swin_engine_vs_reference_golden(name, golden_dir):
     total = sum(b.numel() for b in g["ref_labels"])
     mism = sum((a.cpu().to(torch.uint8) != b).sum().item() for a, b in zip(labels, g["ref_labels"]))
     assert mism <= 2e-4 * total
+
+
+def test_full_size_cfg4_geometry_tensor_core_vs_fp32_cuda_core_paths():
+    """BASELINE configs[3] geometry (SwinB-AOTL, 592x1040 -> 148x260 / 74x130 / 37x65 maps, 10 objects, gap 5) is too big for
+    the CPU oracle in a test: at full size the tensor-core path (tcgen05 GEMMs + attention, CUDA graphs) and the fp32
+    CUDA-core path (no graphs) must agree on logits and masks, the run must be deterministic, and the bank must grow as
+    the reference schedule says."""
+    from aot_benchmark_b200 import engine as engine_mod
+    from aot_benchmark_b200 import ops
+    from oracle import aot_oracle as O
+    from oracle import weights as OW
+    from test_gpu_engine import _build_cuda_engine
+    sd = OW.build_state_dict("swinb_aotl", seed=11)
+    T = 8
+    frames, mask = O.synthetic_video(T, 592, 1040, 10, seed=4)
+    frames = [f.cuda() for f in frames]
+    mask = mask.cuda()
+    runs = {}
+    for name, (lt, conv, graphs) in {"tc": ("tc_exact", "tc", True), "tc2": ("tc_exact", "tc", True),
+                                     "simt": ("simt", "simt", False)}.items():
+        old = (engine_mod.LT_IMPL, ops.CONV_IMPL, engine_mod.USE_GRAPHS)
+        engine_mod.LT_IMPL, ops.CONV_IMPL, engine_mod.USE_GRAPHS = lt, conv, graphs
+        try:
+            eng = _build_cuda_engine("swinb_aotl", sd, 5)
+            with torch.no_grad():
+                lo, labels = O.run_video(eng, frames, mask, 10, (480, 854),
+                                         forced_masks=runs["tc"][1] if name != "tc" else None)
+            runs[name] = (lo, labels, eng.aot_engines[0].bank_len, eng.aot_engines[0].enc_hw)
+        finally:
+            engine_mod.LT_IMPL, ops.CONV_IMPL, engine_mod.USE_GRAPHS = old
+    lo, labels, bank_len, N = runs["tc"]
+    assert N == 37 * 65 == 2405
+    assert bank_len == N * (1 + (T - 1) // 5)
+    for a, b in zip(lo, runs["tc2"][0]):
+        assert torch.equal(a, b)                                    # run-to-run determinism
+    dmax = max((a[:, :11] - b[:, :11]).abs().max().item() for a, b in zip(lo, runs["simt"][0]))
+    assert dmax < 1e-3, dmax
+    mism = sum((a != b).sum().item() for a, b in zip(labels, runs["simt"][1]))
+    total = sum(a.numel() for a in labels)
+    assert mism <= 1e-4 * total, (mism, total)
