@@ -164,6 +164,9 @@ def test_full_size_cfg4_geometry_tensor_core_vs_fp32_cuda_core_paths():
         assert torch.equal(a, b)                                    # run-to-run determinism
     dmax = max((a[:, :11] - b[:, :11]).abs().max().item() for a, b in zip(lo, runs["simt"][0]))
     assert dmax < 1e-3, dmax
+    # label differences between the two arithmetic paths are only legitimate inside the tie band
+    from test_gpu_engine import _tie_band_ok
+    assert _tie_band_ok(lo, [t.cpu() for t in runs["simt"][0]], labels, runs["simt"][1], (480, 854), 11, align=False) == 0
     mism = sum((a != b).sum().item() for a, b in zip(labels, runs["simt"][1]))
     total = sum(a.numel() for a in labels)
-    assert mism <= 1e-4 * total, (mism, total)
+    assert mism <= 1e-3 * total, (mism, total)
