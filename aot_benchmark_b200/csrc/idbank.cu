@@ -229,6 +229,56 @@ __global__ void nearest_kernel(const float* __restrict__ in, float* __restrict__
     }
 }
 
+
+// soft_logit_aggregation (aot_engine.py:565-582) for E sub-engines of max_obj objects each, fused: per output pixel
+//   prob_e = softmax over the 1 + max_obj channels of engine e;  bg = prod_e prob_e[0];
+//   merged = clamp([bg, prob_0[1:], prob_1[1:], ...], 1e-5, 1 - 1e-5);  out = log(merged / (1 - merged))   (torch.logit)
+// One thread per pixel: the E x (1 + max_obj) logits of a pixel are read once (channel planes are HW apart, so a warp reads
+// 128 contiguous bytes per channel) and the 1 + E * max_obj merged logits written once.  The reference materialises E softmax
+// tensors, two concatenations, a product, a clamp and a logit (7 passes over E x 18 MB at 480p).
+struct AggArgs { const float* logits[8]; };
+
+template <int NC>
+__global__ void soft_logit_aggregation_kernel(const AggArgs a, int E, float* __restrict__ out, int HW) {
+    pdl_sync();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        float bg = 1.f;
+        for (int e = 0; e < E; ++e) {
+            const float* l = a.logits[e] + i;
+            float v[NC];
+            float m = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { v[c] = l[(size_t)c * HW]; m = fmaxf(m, v[c]); }
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { v[c] = expf(v[c] - m); sum += v[c]; }
+            bg *= v[0] / sum;
+            float* o = out + (size_t)(1 + e * (NC - 1)) * HW + i;
+#pragma unroll
+            for (int c = 1; c < NC; ++c) {
+                const float p = fminf(fmaxf(v[c] / sum, 1e-5f), 1.f - 1e-5f);
+                o[(size_t)(c - 1) * HW] = logf(p / (1.f - p));
+            }
+        }
+        const float p = fminf(fmaxf(bg, 1e-5f), 1.f - 1e-5f);
+        out[i] = logf(p / (1.f - p));
+    }
+}
+
+
+// separate_mask for label maps (aot_engine.py:515-533): engine e keeps ids [e*max_obj + 1, (e+1)*max_obj], renumbered from 1,
+// everything else becomes background.  One pass writes all E maps (the reference builds E boolean masks and 3 E temporaries).
+__global__ void separate_labels_kernel(const float* __restrict__ mask, int E, int max_obj, float* __restrict__ out, int HW) {
+    pdl_sync();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const float m = mask[i];
+        for (int e = 0; e < E; ++e) {
+            const float lo = (float)(e * max_obj + 1), hi = (float)((e + 1) * max_obj);
+            out[(size_t)e * HW + i] = (m >= lo && m <= hi) ? m - lo + 1.f : 0.f;
+        }
+    }
+}
+
 // rows x cols copy into bank at row offset (host value or device counter)
 __global__ void bank_append_kernel(const float* __restrict__ src, int lds, float* __restrict__ bank, int ldb,
                                    int rows, int cols4, int offset, const int* __restrict__ offset_dev) {
@@ -316,6 +366,30 @@ extern "C" int aotb_nearest_resize_f32(const float* in, float* out, int H, int W
     AOTB_REQUIRE(in && out && H > 0 && W > 0 && Ho > 0 && Wo > 0, "aotb_nearest_resize_f32: bad args");
     launch(nearest_kernel, dim3(cdiv(Ho * Wo, 256)), dim3(256), 0, (cudaStream_t)stream, in, out, H, W, Ho, Wo);
     return check_launch("aotb_nearest_resize_f32");
+}
+
+
+// logits: E device pointers to NCHW fp32 maps [1 + max_obj][HW] (the sub-engines' upsampled logits); out [1 + E*max_obj][HW].
+extern "C" int aotb_soft_logit_aggregation_f32(const float* const* logits, int n_engines, int max_obj, float* out, int HW,
+                                               void* stream) {
+    AOTB_REQUIRE(logits && out && n_engines >= 1 && n_engines <= 8 && HW > 0, "aotb_soft_logit_aggregation_f32: bad args");
+    AOTB_REQUIRE(max_obj == 10, "aotb_soft_logit_aggregation_f32: built for MODEL_MAX_OBJ_NUM = 10 (got %d)", max_obj);
+    AggArgs a;
+    for (int e = 0; e < 8; ++e) a.logits[e] = e < n_engines ? logits[e] : nullptr;
+    for (int e = 0; e < n_engines; ++e) AOTB_REQUIRE(a.logits[e], "aotb_soft_logit_aggregation_f32: null logit map");
+    int g = cdiv(HW, 256);
+    if (g > 148 * 8) g = 148 * 8;
+    launch(soft_logit_aggregation_kernel<11>, dim3(g), dim3(256), 0, (cudaStream_t)stream, a, n_engines, out, HW);
+    return check_launch("aotb_soft_logit_aggregation_f32");
+}
+
+
+extern "C" int aotb_separate_labels_f32(const float* mask, int n_engines, int max_obj, float* out, int HW, void* stream) {
+    AOTB_REQUIRE(mask && out && n_engines >= 1 && max_obj >= 1 && HW > 0, "aotb_separate_labels_f32: bad args");
+    int g = cdiv(HW, 256);
+    if (g > 148 * 8) g = 148 * 8;
+    launch(separate_labels_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, mask, n_engines, max_obj, out, HW);
+    return check_launch("aotb_separate_labels_f32");
 }
 
 extern "C" int aotb_bank_append_f32(const float* src, int lds, float* bank, int ldb, int rows, int cols, int offset,

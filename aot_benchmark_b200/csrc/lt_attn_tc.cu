@@ -794,6 +794,12 @@ __global__ void pack_rows64_kernel(const float* __restrict__ src, int ld, __half
 }  // namespace tc
 }  // namespace aotb
 
+namespace aotb { namespace tc {
+int launch_lt_attn_pair(const void* Qp, int Nq_cap, const void* Kp, const void* Vp, int kv_cap, int N, int Tk,
+                        const int* Tk_dev, int H, float* O, int ldo, float* Opart, float* Mpart, float* Lpart, int splits,
+                        int exact, int spin, cudaStream_t st);      // lt_attn_tc2.cu
+} }
+
 using namespace aotb;
 
 // Pack fp32 rows into the split-fp16 operand layout of the tensor-core attention kernel.
@@ -829,6 +835,9 @@ extern "C" int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp,
     AOTB_REQUIRE(splits == 1 ? (O != nullptr && ldo % 4 == 0) : (Opart && Mpart && Lpart),
                  "aotb_lt_attn_tc_f16x2: output buffers");
     AOTB_REQUIRE(((uintptr_t)Qp | (uintptr_t)Kp | (uintptr_t)Vp) % 128 == 0, "aotb_lt_attn_tc_f16x2: alignment");
+    if (exact & 16)           // bit 4: "pair" layout (two co-resident CTAs per SM, 64-key tiles; lt_attn_tc2.cu)
+        return tc::launch_lt_attn_pair(Qp, Nq_cap, Kp, Vp, kv_cap, N, Tk, Tk_dev, H, O, ldo, Opart, Mpart, Lpart, splits,
+                                       exact & 1, (exact >> 2) & 1, (cudaStream_t)stream);
     CUtensorMap tq, tk, tv;
     int rc;
     if ((rc = tc::make_tmap_rows64(&tq, Qp, Nq_cap, H)) != AOTB_OK) return rc;

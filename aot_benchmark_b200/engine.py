@@ -36,17 +36,19 @@ LT_PROBE = None
 import os as _os
 LT_IMPL = _os.environ.get("AOTB_LT_IMPL", "tc_exact")
 LOCAL_IMPL = _os.environ.get("AOTB_LOCAL_IMPL", "tile")      # "tile" (halo in smem) | "warp" (generic kernel)
-# DeAOT long-term attention (1 head, d_qk 128, d_v 1024): "simt" fp32 flash kernel | "gemm" = tensor-core GEMM (Q K^T) ->
-# row softmax -> tensor-core GEMM (P V) over split-fp16 operand copies of the bank (deaot_lt.cu) | "tc" = fused tcgen05
-# kernel (gp_attn_tc.cu).  "gemm" and "tc" were built at the end of round 1: host logic checked on CPU, protocol of the
-# fused kernel model-checked, kernels not yet run on a GPU -> not the default
-DEAOT_LT = _os.environ.get("AOTB_DEAOT_LT", "simt")
+# DeAOT long-term attention (1 head, d_qk 128, d_v 1024): "tc" = fused tcgen05 flash kernel (gp_attn_tc.cu, default since
+# round 2: 475 us per launch on the cfg3 clip against 661 for "gemm" and 4189 for "simt", profiles/r02_trip1_summary.md) |
+# "gemm" = tensor-core GEMM (Q K^T) -> row softmax -> tensor-core GEMM (P V) over split-fp16 operand copies of the bank
+# (deaot_lt.cu) | "simt" = fp32 CUDA-core flash kernel
+DEAOT_LT = _os.environ.get("AOTB_DEAOT_LT", "tc")
 # exchange step of the sharded long-term bank (BASELINE configs[3]): "nccl" = three all-gathers of the (m, l, O) partials +
 # local merge; "p2p" = the partials live in a torch symmetric-memory allocation and every rank's merge kernel reads its
 # peers' partials in place over NVLink (aotb_attn_merge_peers_f32) behind one device-side barrier -- no NCCL on the data
 # path.  "p2p" was written without multi-GPU access (logic checked on CPU with an in-process stand-in for the allocator).
 SHARD_XCHG = _os.environ.get("AOTB_SHARD_XCHG", "nccl")
 SHARD_SMAX = 16          # split capacity of the symmetric partial buffers
+SUB_ENGINE_STREAMS = _os.environ.get("AOTB_SUB_ENGINE_STREAMS", "1") == "1"   # > 10 objects: sub-engines on concurrent streams
+SHARD_GRAPHS = _os.environ.get("AOTB_SHARD_GRAPHS", "1") == "1"   # capture the LSTT call (incl. the exchange) in sharded mode
 
 
 def _symm_alloc(numel, device, group):
@@ -62,6 +64,17 @@ GEMM_GROW_FRAMES = int(_os.environ.get("AOTB_GEMM_GROW_FRAMES", "8"))   # bank g
 _LT_NAMES = {"simt": "attn_f32_kernel<32,32> (fp32 SIMT flash attention)",
              "tc_exact": "lt_attn_tc_kernel (tcgen05 fp16x2 exact: 6+16 MMAs/tile)",
              "tc_fast": "lt_attn_tc_kernel (tcgen05 fp16 fast: 2+8 MMAs/tile)"}
+_DEAOT_LT_NAMES = {"simt": "attn_f32_kernel<128,256> (fp32 SIMT flash attention, DeAOT 1 x 128 / 1024 head)",
+                   "gemm": "conv_tc_kernel (Q K^T) -> row_softmax_kernel -> conv_tc_kernel (P V): tcgen05 GEMMs over split-fp16 "
+                           "copies of the bank (deaot_lt.cu)",
+                   "tc": "gp_attn_tc_kernel (fused tcgen05 flash attention, 128 queries x 128 value channels per CTA)"}
+
+
+def deaot_lt_kernel_name():
+    """The DeAOT long-term attention implementation actually in use (bench.py's roofline entry names it)."""
+    return _DEAOT_LT_NAMES.get(DEAOT_LT, DEAOT_LT)
+
+
 LT_KERNEL_NAME = _LT_NAMES.get(LT_IMPL, LT_IMPL) + (f", softmax layout '{ops.LT_VARIANT}'" if LT_IMPL.startswith("tc") else "")
 
 
@@ -124,17 +137,20 @@ def _cur_stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def lt_splits(n_queries, heads, tk, sms=148):
-    """KV-split count for the tensor-core kernel: fill whole waves of `sms` CTAs (one CTA = 256 queries x
-    1 head x 1 split) while keeping >= 2 key tiles per split."""
-    base = ((n_queries + 255) // 256) * heads
+def lt_splits(n_queries, heads, tk, sms=148, variant=None):
+    """KV-split count for the tensor-core kernel: fill whole waves of CTA slots while keeping >= 2 x 128 keys per split.
+    One CTA = 256 queries x 1 head x 1 split at one CTA per SM ("tile" / "groups" / "ahead" layouts) or 128 queries x 1
+    head x 1 split at two CTAs per SM ("pair" layout)."""
+    pair = (ops.LT_VARIANT if variant is None else variant) == "pair"
+    qrows, slots = (128, 2 * sms) if pair else (256, sms)
+    base = ((n_queries + qrows - 1) // qrows) * heads
     tiles = (tk + 127) // 128
     effs = []
     for s in range(1, 17):
         if s > 1 and tiles < 2 * s:
             break
         ctas = base * s
-        effs.append((s, ctas / (((ctas + sms - 1) // sms) * sms)))
+        effs.append((s, ctas / (((ctas + slots - 1) // slots) * slots)))
     top = max(e for _, e in effs)
     return next(s for s, e in effs if e >= top - 0.05)     # fewest splits within 5 % of the best wave fill
 
@@ -393,7 +409,7 @@ class AOTEngine(nn.Module):
         N = self.enc_hw
         C = P.C
         L = P.L
-        key = (id(P), N, tuple(self.enc_size_2d), tuple(self.input_size_2d), LT_IMPL)
+        key = (id(P), N, tuple(self.enc_size_2d), tuple(self.input_size_2d), LT_IMPL, DEAOT_LT)
         if self._ws is not None and self._ws_key == key:
             # same geometry and weights as the previous video: keep buffers and captured graphs
             self.bank_len = 0
@@ -459,6 +475,9 @@ class AOTEngine(nn.Module):
         if self._gp_tc:
             hz = lambda *s: torch.zeros(s, dtype=torch.float16, device=dev)
             ws.gpQp = hz(self._kdim // 32, ((N + 127) // 128) * 128, 64)
+            ncap = ((N + 63) // 64) * 64 + 64                      # K / V of the CURRENT frame (self-attention, reference frame)
+            ws.gpSaK = hz(self._kdim // 32, ncap, 64)
+            ws.gpSaV = hz(self._vdim // 32, ncap, 64)
             self.bank_gpK = [hz(self._kdim // 32, cap, 64) for _ in range(L)]     # split-fp16 rows, one "head" / 32 channels
             self.bank_gpV = [hz(self._vdim // 32, cap, 64) for _ in range(L)]
             ws.gp_part = {}
@@ -632,7 +651,10 @@ class AOTEngine(nn.Module):
         self.curr_id_embs = id_emb
         self._lstt_forward(img_embs, id_emb, st)
         # lstt_long_memories of a reference frame = its own fused K/V (transformer.py:337-341)
-        self._append_short_to_bank(st)
+        if self._claim_memory_frame():
+            self._bank_reserve(self.enc_hw)
+            self._append_short_to_bank(st)
+            self.bank_len += self.enc_hw
         self.last_mem_step = self.frame_step
         self._have_lstt = True
 
@@ -644,9 +666,15 @@ class AOTEngine(nn.Module):
             img_embs = self._encode(img, st)
         self.curr_enc_embs = img_embs
         splits = lt_splits(self.enc_hw, self._plan().H, max(self.bank_len, 1)) if getattr(self, "_tc", False) else 0
-        self.graphs.run(("lstt", splits, id(img_embs.nhwc[-1])),
+        if getattr(self, "_gp_tc", False):
+            splits = self._gp_splits(self.bank_len)       # the fused DeAOT kernel's split count is part of the captured body
+        if self.kv_shard is not None:
+            # sharded bank: the captured body also depends on the shard split count (a function of the GLOBAL memory-frame
+            # count, identical on every rank) and on whether this rank holds any memory frame yet
+            splits = ("shard", self._shard_splits(), self.bank_len > 0, SHARD_XCHG)
+        self.graphs.run(("lstt", splits, img_embs.nhwc[-1].data_ptr()),
                         lambda: self._lstt_forward(img_embs, None, _cur_stream()),
-                        enabled=self.short_term_mem_skip <= 1 and self.kv_shard is None)
+                        enabled=self.short_term_mem_skip <= 1 and (self.kv_shard is None or SHARD_GRAPHS))
 
     def update_short_term_memory(self, curr_mask, curr_id_emb=None, skip_long_term_update=False):
         st = torch.cuda.current_stream().cuda_stream
@@ -654,12 +682,13 @@ class AOTEngine(nn.Module):
         if self.frame_step - self.last_mem_step >= self.long_term_mem_gap:
             append = not skip_long_term_update
             self.last_mem_step = self.frame_step
+        append = append and self._claim_memory_frame()       # sharded bank: only the owner rank stores this memory frame
         if append:
             self._bank_reserve(self.enc_hw)          # may re-allocate (and drop graphs) before anything is captured
         ws = self._ws
         label_map = curr_id_emb is None and not (curr_mask.dim() == 4 and curr_mask.shape[1] != 1) and \
             tuple(curr_mask.shape[-2:]) == tuple(ws.mask.shape)
-        if label_map and self.short_term_mem_skip <= 1 and self.kv_shard is None:
+        if label_map and self.short_term_mem_skip <= 1:
             m2 = curr_mask.reshape(ws.mask.shape).float().contiguous()
             ops.eltwise(ops.EW_COPY, m2, None, ws.mask, stream=st)
 
@@ -668,28 +697,27 @@ class AOTEngine(nn.Module):
                 self._id_from_static_mask(ws.mask, s2)
                 self._fuse_memories(ws.id_emb, s2)
                 if append:
-                    self._append_short_to_bank(s2, count=False)
+                    self._append_short_to_bank(s2)
             self.graphs.run(("upd", append), body)
+        else:
+            id_emb = self.assign_identity_from_mask(curr_mask, st) if curr_id_emb is None else curr_id_emb
+            self._fuse_memories(id_emb, st)
             if append:
-                self.bank_len += self.enc_hw
-            return
-        id_emb = self.assign_identity_from_mask(curr_mask, st) if curr_id_emb is None else curr_id_emb
-        self._fuse_memories(id_emb, st)
+                self._append_short_to_bank(st)
         if append:
-            self._append_short_to_bank(st)
+            self.bank_len += self.enc_hw
 
-    def _append_short_to_bank(self, st, count=True):
-        """Append the newest fused K/V of every layer at the device-side row counter, then advance it."""
+    def _claim_memory_frame(self):
+        """Count one more memory frame (global count, all shards) and say whether THIS rank stores it: always without
+        sharding, rank `f % world` for memory frame f with the bank sharded."""
+        f = self._mem_frames
+        self._mem_frames += 1
+        return self.kv_shard is None or f % self.kv_shard[1] == self.kv_shard[0]
+
+    def _append_short_to_bank(self, st):
+        """Append the newest fused K/V of every layer at the device-side row counter, then advance it (kernels only: the
+        host-side row count and capacity are the caller's business, so the body can be captured in a graph)."""
         N = self.enc_hw
-        if self.kv_shard is not None and count:
-            owner = self._mem_frames % self.kv_shard[1]
-            self._mem_frames += 1
-            if owner != self.kv_shard[0]:
-                return                # another rank keeps this memory frame
-        elif count:
-            self._mem_frames += 1
-        if count:
-            self._bank_reserve(N)
         K_src, V_src = self._latest_kv()
         off = self.tk_dev
         for li in range(self._plan().L):
@@ -705,8 +733,6 @@ class AOTEngine(nn.Module):
                 ops.tc_pack_rows(K_src[li], self.bank_gpK[li], 0, row_off_dev=off, stream=st)
                 ops.tc_pack_rows(V_src[li], self.bank_gpV[li], 0, row_off_dev=off, stream=st)
         ops.counter_add(off, N, stream=st)
-        if count:
-            self.bank_len += N
 
     def _latest_kv(self):
         return self._new_K, self._new_V
@@ -782,6 +808,9 @@ class AOTEngine(nn.Module):
             e0.record()
         if use_tc and self.kv_shard is not None:
             self._sharded_attention(li, out, st)
+        elif self.kv_shard is not None and K is self.bank_K[li]:
+            raise ops.AotbError("sharded long-term bank needs the tensor-core attention kernel (8 heads x 32); this model's "
+                                "head shape runs on the fp32 kernel, which has no partial (m, l, O) outputs")
         elif use_tc:
             self._tc_attention(None, None, None, self.bank_Kp[li], self.bank_Vp[li], Tk, out, st, Tk_dev=self.tk_dev)
         elif self._tc:
@@ -817,34 +846,50 @@ class AOTEngine(nn.Module):
         ops.lt_attention_tc(ws.Qp, Kp, Vp, N, Tk, O=out, Tk_dev=Tk_dev, splits=splits, exact=(LT_IMPL == "tc_exact"),
                             part=part, stream=st)
 
+    def _shard_splits(self):
+        """KV-split count of the per-rank partial attention in sharded mode: a function of the GLOBAL memory-frame count, so it
+        is identical on every rank (the exchanged buffers must have the same shape everywhere)."""
+        world = self.kv_shard[1]
+        frames_per_rank = (self._mem_frames + world - 1) // world
+        s = max(2, lt_splits(self.enc_hw, self._plan().H, max(frames_per_rank, 1) * self.enc_hw))
+        if s > SHARD_SMAX:
+            raise ops.AotbError(f"sharded long-term attention: {s} KV splits exceed the exchange buffer capacity {SHARD_SMAX}")
+        return s
+
     def _sharded_attention(self, li, out, st):
-        """Split-KV over ranks: local partials -> all_gather -> exact LSE merge.  Q was packed by the caller."""
+        """Split-KV over ranks: local partials -> ONE all-gather of the packed [O | m | l] block -> exact LSE
+        merge straight out of the gathered buffer (per-rank slices, no re-layout).  Q was packed by the caller."""
         import torch.distributed as dist
         rank, world, group = self.kv_shard
         P = self._plan()
         ws = self._ws
-        N = self.enc_hw
-        frames_per_rank = (self._mem_frames + world - 1) // world
-        splits = max(2, lt_splits(N, P.H, max(frames_per_rank, 1) * N))      # identical on every rank
+        N, C, H = self.enc_hw, P.C, P.H
+        splits = self._shard_splits()                                            # identical on every rank
+        if st != torch.cuda.current_stream().cuda_stream:
+            raise ops.AotbError("sharded long-term attention must run on torch's current stream (the collective / the "
+                                "symmetric-memory barrier are issued there)")
         if SHARD_XCHG == "p2p":
             return self._sharded_attention_p2p(li, out, st, splits)
         key = ("shard", splits)
         bufs = ws.part.get(key)
         if bufs is None:
-            fz = lambda *s: torch.empty(s, dtype=torch.float32, device=out.device)
-            bufs = (fz(splits, N, P.C), fz(splits, P.H, N), fz(splits, P.H, N),
-                    fz(world * splits, N, P.C), fz(world * splits, P.H, N), fz(world * splits, P.H, N))
-            ws.part[key] = bufs
-        Op, Mp, Lp, Og, Mg, Lg = bufs
+            nO, nM = splits * N * C, splits * H * N
+            mine = torch.empty(nO + 2 * nM, dtype=torch.float32, device=out.device)
+            allr = torch.empty(world * (nO + 2 * nM), dtype=torch.float32, device=out.device)
+            sl = lambda t: (t[:nO].view(splits, N, C), t[nO:nO + nM].view(splits, H, N), t[nO + nM:].view(splits, H, N))
+            per_rank = [sl(allr[r * (nO + 2 * nM):(r + 1) * (nO + 2 * nM)]) for r in range(world)]
+            bufs = ws.part[key] = (mine, allr, sl(mine), per_rank)
+        mine, allr, (Op, Mp, Lp), per_rank = bufs
         if self.bank_len > 0:
             ops.lt_attention_tc(ws.Qp, self.bank_Kp[li], self.bank_Vp[li], N, self.bank_len, O=None, Tk_dev=self.tk_dev,
                                 splits=splits, exact=(LT_IMPL == "tc_exact"), part=(Op, Mp, Lp), stream=st, merge=False)
         else:                                  # this rank holds no memory frame yet: neutral partial
-            Op.zero_(); Lp.zero_(); Mp.fill_(float("-inf"))
-        dist.all_gather_into_tensor(Og, Op, group=group)
-        dist.all_gather_into_tensor(Mg, Mp, group=group)
-        dist.all_gather_into_tensor(Lg, Lp, group=group)
-        ops.attn_merge(Og, Mg, Lg, out, P.H, P.C // P.H, stream=st)
+            ops.eltwise(ops.EW_FILL, None, None, mine[:Op.numel()].view(1, -1), scalar=0.0, stream=st)
+            ops.eltwise(ops.EW_FILL, None, None, Mp.view(1, -1), scalar=float("-inf"), stream=st)
+            ops.eltwise(ops.EW_FILL, None, None, Lp.view(1, -1), scalar=0.0, stream=st)
+        dist.all_gather_into_tensor(allr, mine, group=group)
+        ops.attn_merge_peers([v[0] for v in per_rank], [v[1] for v in per_rank], [v[2] for v in per_rank], out, splits, H,
+                             C // H, stream=st)
 
     def _sharded_attention_p2p(self, li, out, st, splits):
         """Exchange over peer memory: the local partials are written into this rank's slice of a symmetric allocation, one
@@ -855,7 +900,6 @@ class AOTEngine(nn.Module):
         P = self._plan()
         ws = self._ws
         N, C, H = self.enc_hw, P.C, P.H
-        assert splits <= SHARD_SMAX
         key = ("p2p", li)
         buf = ws.part.get(key)
         if buf is None:
@@ -870,7 +914,9 @@ class AOTEngine(nn.Module):
             ops.lt_attention_tc(ws.Qp, self.bank_Kp[li], self.bank_Vp[li], N, self.bank_len, O=None, Tk_dev=self.tk_dev,
                                 splits=splits, exact=(LT_IMPL == "tc_exact"), part=(Op, Mp, Lp), stream=st, merge=False)
         else:                                  # this rank holds no memory frame yet: neutral partial
-            Op.zero_(); Lp.zero_(); Mp.fill_(float("-inf"))
+            ops.eltwise(ops.EW_FILL, None, None, Op.reshape(1, -1), scalar=0.0, stream=st)
+            ops.eltwise(ops.EW_FILL, None, None, Mp.reshape(1, -1), scalar=float("-inf"), stream=st)
+            ops.eltwise(ops.EW_FILL, None, None, Lp.reshape(1, -1), scalar=0.0, stream=st)
         hdl.barrier()
         ops.attn_merge_peers([v[0] for v in views], [v[1] for v in views], [v[2] for v in views], out, splits, H, C // H,
                              stream=st)
@@ -971,7 +1017,7 @@ class AOTEngine(nn.Module):
             ops.logits_postproc(lg, bufs[0], bufs[1], obj, P.align_corners, stream=st)
             return bufs
 
-        lo, out = self.graphs.run(("dec", size, obj, id(self.curr_enc_embs.nhwc[0])), body)
+        lo, out = self.graphs.run(("dec", size, obj, self.curr_enc_embs.nhwc[0].data_ptr()), body)
         self.pred_id_logits = lo
         return lo if out is None else out
 
@@ -1048,18 +1094,9 @@ class DeAOTEngine(AOTEngine):
                 e0.record()
             if self._gp_tc and not is_ref:
                 # fused tcgen05 kernel (gp_attn_tc.cu): 128 queries x 128 value channels per CTA, KV splits to fill the GPU
-                ops.tc_pack_rows(cQ, ws.gpQp, 0, div=math.sqrt(d), stream=st)
-                base = ((N + 127) // 128) * (C4 // 128)
-                tiles = (max(Tk, 1) + 63) // 64
-                splits = max(1, min(tiles // 4 if tiles >= 8 else 1, max(1, (2 * 148) // base)))
-                part = None
-                if splits > 1:
-                    part = ws.gp_part.get(splits)
-                    if part is None:
-                        fz = lambda *s: torch.empty(s, dtype=torch.float32, device=cQ.device)
-                        part = ws.gp_part[splits] = (fz(splits, N, C4), fz(splits, 1, N), fz(splits, 1, N))
-                ops.gp_attention_tc(ws.gpQp, self.bank_gpK[li], self.bank_gpV[li], N, Tk, O=ws.core, Tk_dev=self.tk_dev,
-                                    splits=splits, exact=True, part=part, stream=st)
+                self._gp_attention(cQ, None, None, self.bank_gpK[li], self.bank_gpV[li], Tk, self.tk_dev, ws.core, st)
+            elif self._gp_tc:
+                self._gp_attention(cQ, gK, gV, None, None, N, None, ws.core, st)     # reference frame: its own K / V
             elif self._gemm_lt and not is_ref:
                 # S = Q K^T -> softmax(S / T) over the live keys -> P V, all on the tensor-core GEMM (deaot_lt.cu)
                 ops.linear_tc(cQ, self.bank_Kh[li], self.bank_Kl[li], None, ws.S, stream=st)
@@ -1083,7 +1120,10 @@ class DeAOTEngine(AOTEngine):
             ops.linear(ws.c[:, C:], Lw.sa_v2[0], Lw.sa_v2[1], ws.sa_v[:, C2:], act=A_SILU, stream=st)
             ops.linear(ws.c[:, :C], Lw.sa_u1[0], Lw.sa_u1[1], ws.sa_u[:, :C2], act=A_SILU, stream=st)
             ops.linear(ws.c[:, C:], Lw.sa_u2[0], Lw.sa_u2[1], ws.sa_u[:, C2:], act=A_SILU, stream=st)
-            ops.attention(ws.sa_qk, ws.sa_qk, ws.sa_v, ws.core, 1, d, C4, Tk=N, stream=st)
+            if self._gp_tc:
+                self._gp_attention(ws.sa_qk, ws.sa_qk, ws.sa_v, None, None, N, None, ws.core, st)
+            else:
+                ops.attention(ws.sa_qk, ws.sa_qk, ws.sa_v, ws.core, 1, d, C4, Tk=N, stream=st)
             self._gated_tail(ws.core, ws.sa_u, Lw.sa_dw, ws.dw[:, :C4], h, w, st)
             ops.linear(ws.dw[:, :C4], Lw.sa_proj_w, Lw.sa_proj_b, ws.xz, res=ws.xz, stream=st)
         # final GroupNorm1D(2C, groups=2) (transformer.py:197-200,241) -> decoder input
@@ -1092,6 +1132,33 @@ class DeAOTEngine(AOTEngine):
         if is_ref:
             self._commit_short_slot(stK, stV)
         self._have_lstt = True
+
+    def _gp_attention(self, Q, K, V, Kp, Vp, Tk, Tk_dev, out, st):
+        """softmax(Q K^T / T) V for the DeAOT head shape (1 x 128 / 1024) on the fused tcgen05 kernel.  Q fp32 [N, 128] is
+        packed (with the 1/T of attention.py:672) here; K / V fp32 of the current frame are packed unless already-packed
+        bank copies (Kp, Vp) are given."""
+        ws = self._ws
+        N = self.enc_hw
+        ops.tc_pack_rows(Q, ws.gpQp, 0, div=math.sqrt(self._kdim), stream=st)
+        if Kp is None:
+            ops.tc_pack_rows(K, ws.gpSaK, 0, stream=st)
+            ops.tc_pack_rows(V, ws.gpSaV, 0, stream=st)
+            Kp, Vp = ws.gpSaK, ws.gpSaV
+        splits = self._gp_splits(Tk)
+        part = None
+        if splits > 1:
+            part = ws.gp_part.get(splits)
+            if part is None:
+                fz = lambda *s: torch.empty(s, dtype=torch.float32, device=out.device)
+                part = ws.gp_part[splits] = (fz(splits, N, out.shape[1]), fz(splits, 1, N), fz(splits, 1, N))
+        ops.gp_attention_tc(ws.gpQp, Kp, Vp, N, Tk, O=out, Tk_dev=Tk_dev, splits=splits, exact=True, part=part, stream=st)
+
+    def _gp_splits(self, Tk):
+        """KV-split count of the fused DeAOT long-term attention kernel (one CTA = 128 queries x 128 value channels x one
+        split): about two waves of CTAs, at least four 64-key tiles per split."""
+        base = ((self.enc_hw + 127) // 128) * (4 * self._plan().C // 128)
+        tiles = (max(Tk, 1) + 63) // 64
+        return max(1, min(tiles // 4 if tiles >= 8 else 1, max(1, (2 * 148) // base)))
 
     def _fuse_id(self, li, cIDV, id_emb, out, st):
         """GatedPropagationModule.fuse_key_value_id (transformer.py:659-665)."""
@@ -1150,87 +1217,111 @@ class AOTInferEngine(nn.Module):
         self.aot_engines = []
         self.obj_nums = None
 
+    # ------------------------------------------------------------------ > max_aot_obj_num objects
+    # ceil(objects / 10) sub-engines share one encoder pass.  Their LSTT / decoder / memory-update work is independent, so
+    # every sub-engine after the first runs on its own side stream (forked from and joined to the caller's stream inside
+    # each protocol call) and the small per-engine kernels overlap on the GPU instead of queueing behind one another as in
+    # the reference's Python loop (aot_engine.py:584-630); mask separation and logit aggregation are one kernel each.
+    def _engine_streams(self):
+        n = len(self.aot_engines)
+        pool = getattr(self, "_side_streams", [])
+        while len(pool) < n - 1:
+            pool.append(torch.cuda.Stream())
+        self._side_streams = pool
+        return pool[: n - 1]
+
+    def _run_engines(self, fn):
+        """fn(index, engine) for every sub-engine; engine 0 on the current stream, the others concurrently on side streams."""
+        engines = self.aot_engines
+        if len(engines) == 1 or not SUB_ENGINE_STREAMS:
+            return [fn(i, e) for i, e in enumerate(engines)]
+        cur = torch.cuda.current_stream()
+        side = self._engine_streams()
+        for s in side:
+            s.wait_stream(cur)                      # fork: everything queued so far (shared encoding, masks) is visible
+        outs = [None] * len(engines)
+        for i in range(1, len(engines)):
+            with torch.cuda.stream(side[i - 1]):
+                outs[i] = fn(i, engines[i])
+        outs[0] = fn(0, engines[0])
+        for s in side:
+            cur.wait_stream(s)                      # join
+        return outs
+
     def separate_mask(self, mask, obj_nums):
-        # aot_engine.py:515-545
+        """aot_engine.py:515-545 -> (per-engine masks, per-engine object counts).  Label maps go through one kernel
+        (ids [10e+1, 10e+10] -> 1..10 for engine e); the probability form ([K, ...] foreground stack) slices channels."""
+        n = len(self.aot_engines)
         if mask is None:
-            return [None] * len(self.aot_engines)
-        if len(self.aot_engines) == 1:
+            return [None] * n
+        if n == 1:
             return [mask], [obj_nums]
-        separated_obj_nums = [self.max_aot_obj_num for _ in range(len(self.aot_engines))]
-        if obj_nums % self.max_aot_obj_num > 0:
-            separated_obj_nums[-1] = obj_nums % self.max_aot_obj_num
-        if len(mask.size()) == 3 or mask.size()[0] == 1:
-            separated_masks = []
-            for idx in range(len(self.aot_engines)):
-                start_id = idx * self.max_aot_obj_num + 1
-                end_id = (idx + 1) * self.max_aot_obj_num
-                fg_mask = ((mask >= start_id) & (mask <= end_id)).float()
-                separated_masks.append((fg_mask * mask - start_id + 1) * fg_mask)
-            return separated_masks, separated_obj_nums
-        prob = mask
-        separated_probs = []
-        for idx in range(len(self.aot_engines)):
-            start_id = idx * self.max_aot_obj_num + 1
-            end_id = (idx + 1) * self.max_aot_obj_num
-            fg_prob = prob[start_id:(end_id + 1)]
-            bg_prob = 1. - torch.sum(fg_prob, dim=1, keepdim=True)
-            separated_probs.append(torch.cat([bg_prob, fg_prob], dim=1))
-        return separated_probs, separated_obj_nums
+        per = self.max_aot_obj_num
+        counts = [per] * n
+        if obj_nums % per > 0:
+            counts[-1] = obj_nums % per
+        if mask.dim() == 3 or mask.shape[0] == 1:
+            m = mask.float().contiguous()
+            out = torch.empty((n,) + tuple(m.shape), dtype=torch.float32, device=m.device)
+            ops.separate_labels(m, out, per)
+            return [out[e] for e in range(n)], counts
+        probs = []
+        for e in range(n):
+            fg = mask[e * per + 1:(e + 1) * per + 1]
+            probs.append(torch.cat([1. - fg.sum(dim=1, keepdim=True), fg], dim=1))
+        return probs, counts
 
     def soft_logit_aggregation(self, all_logits):
-        # aot_engine.py:565-582 (identity for <= 10 objects; the >10-object merge is a "next" row and
-        # still uses element-wise tensor ops on the few merged logit maps)
+        """aot_engine.py:565-582: identity for one engine, otherwise the fused aggregation kernel."""
         if len(all_logits) == 1:
             return all_logits[0]
-        fg_probs, bg_probs = [], []
-        for logit in all_logits:
-            prob = torch.softmax(logit, dim=1)
-            bg_probs.append(prob[:, 0:1])
-            fg_probs.append(prob[:, 1:1 + self.max_aot_obj_num])
-        bg_prob = torch.prod(torch.cat(bg_probs, dim=1), dim=1, keepdim=True)
-        merged_prob = torch.cat([bg_prob] + fg_probs, dim=1).clamp(1e-5, 1 - 1e-5)
-        return torch.logit(merged_prob)
+        per = self.max_aot_obj_num
+        first = all_logits[0]
+        key = (len(all_logits), tuple(first.shape[-2:]))
+        buf = getattr(self, "_agg_out", None)
+        if buf is None or buf[0] != key:
+            buf = self._agg_out = (key, torch.empty((1, 1 + len(all_logits) * per) + tuple(first.shape[-2:]),
+                                                    dtype=torch.float32, device=first.device))
+        return ops.soft_logit_aggregation([t if t.is_contiguous() else t.contiguous() for t in all_logits], buf[1], per)
 
     def add_reference_frame(self, img, mask, obj_nums, frame_step=-1):
         if isinstance(obj_nums, list):
             obj_nums = obj_nums[0]
         self.obj_nums = obj_nums
-        aot_num = max(np.ceil(obj_nums / self.max_aot_obj_num), 1)
-        while aot_num > len(self.aot_engines):
-            if self._pool:
-                new_engine = self._pool.pop(0)
-                new_engine.restart_engine()
-            else:
-                new_engine = self._engine_cls(self.AOT, self.gpu_id, self.long_term_mem_gap, self.short_term_mem_skip)
-            new_engine.eval()
+        want = max(-(-int(obj_nums) // self.max_aot_obj_num), 1)          # ceil(objects / max_aot_obj_num), at least one
+        while len(self.aot_engines) < want:
+            eng = self._pool.pop(0) if self._pool else self._engine_cls(self.AOT, self.gpu_id, self.long_term_mem_gap,
+                                                                       self.short_term_mem_skip)
+            eng.restart_engine()
+            eng.eval()
             if self._kv_shard is not None:
-                new_engine.enable_kv_sharding(*self._kv_shard)
-            self.aot_engines.append(new_engine)
-        separated_masks, separated_obj_nums = self.separate_mask(mask, obj_nums)
-        img_embs = None
-        for aot_engine, separated_mask, separated_obj_num in zip(self.aot_engines, separated_masks,
-                                                                 separated_obj_nums):
-            aot_engine.add_reference_frame(img, separated_mask, obj_nums=[separated_obj_num], frame_step=frame_step,
-                                           img_embs=img_embs)
-            if img_embs is None:
-                img_embs = aot_engine.curr_enc_embs
+                eng.enable_kv_sharding(*self._kv_shard)
+            self.aot_engines.append(eng)
+        masks, counts = self.separate_mask(mask, obj_nums)
+        # engine 0 encodes the frame; the others reuse its feature maps (aot_engine.py:596-607)
+        first = self.aot_engines[0]
+        first.add_reference_frame(img, masks[0], obj_nums=[counts[0]], frame_step=frame_step)
+        embs = first.curr_enc_embs
+        if len(self.aot_engines) > 1:
+            self._run_engines(lambda i, e: None if i == 0 else e.add_reference_frame(
+                img, masks[i], obj_nums=[counts[i]], frame_step=frame_step, img_embs=embs))
         self.update_size()
 
     def match_propogate_one_frame(self, img=None):
-        img_embs = None
-        for aot_engine in self.aot_engines:
-            aot_engine.match_propogate_one_frame(img, img_embs=img_embs)
-            if img_embs is None:
-                img_embs = aot_engine.curr_enc_embs
+        first = self.aot_engines[0]
+        if len(self.aot_engines) == 1:
+            return first.match_propogate_one_frame(img)
+        first._check_img(img)
+        embs = first._encode(img, torch.cuda.current_stream().cuda_stream)       # shared by all sub-engines
+        self._run_engines(lambda i, e: e.match_propogate_one_frame(img, img_embs=embs))
 
     def decode_current_logits(self, output_size=None):
-        all_logits = [e.decode_current_logits(output_size) for e in self.aot_engines]
+        all_logits = self._run_engines(lambda i, e: e.decode_current_logits(output_size))
         return self.soft_logit_aggregation(all_logits)
 
     def update_memory(self, curr_mask, skip_long_term_update=False):
-        separated_masks, _ = self.separate_mask(curr_mask, self.obj_nums)
-        for aot_engine, separated_mask in zip(self.aot_engines, separated_masks):
-            aot_engine.update_short_term_memory(separated_mask, skip_long_term_update=skip_long_term_update)
+        masks, _ = self.separate_mask(curr_mask, self.obj_nums)
+        self._run_engines(lambda i, e: e.update_short_term_memory(masks[i], skip_long_term_update=skip_long_term_update))
 
     # BASELINE.json's north_star names this method; the reference's real name is update_memory
     update_short_long_term_memory = update_memory
@@ -1249,18 +1340,13 @@ class DeAOTInferEngine(AOTInferEngine):
     _engine_cls = DeAOTEngine
 
 
+_ENGINES = {("aotengine", "train"): AOTEngine, ("aotengine", "eval"): AOTInferEngine,
+            ("deaotengine", "train"): DeAOTEngine, ("deaotengine", "eval"): DeAOTInferEngine}
+
+
 def build_engine(name, phase='train', **kwargs):
-    """networks/engines/__init__.py:5-21."""
-    if name == 'aotengine':
-        if phase == 'train':
-            return AOTEngine(**kwargs)
-        elif phase == 'eval':
-            return AOTInferEngine(**kwargs)
+    """networks/engines/__init__.py:5-21: same names, same keyword arguments, NotImplementedError for anything else."""
+    cls = _ENGINES.get((name, phase))
+    if cls is None:
         raise NotImplementedError
-    elif name == 'deaotengine':
-        if phase == 'train':
-            return DeAOTEngine(**kwargs)
-        elif phase == 'eval':
-            return DeAOTInferEngine(**kwargs)
-        raise NotImplementedError
-    raise NotImplementedError
+    return cls(**kwargs)

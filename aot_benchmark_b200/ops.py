@@ -51,6 +51,25 @@ CONV_IMPL = os.environ.get("AOTB_CONV_IMPL", "tc")     # "tc" (tcgen05, fp16x2 s
 
 
 _TC_WS = {}
+# bench.py hook: when set to a list, every tensor-core conv / linear launch appends (start_event, end_event, flops) with
+# flops = 2 * M * N * K (algorithmic: one multiply-add per weight per output) so the conv family's roofline is measured live
+CONV_PROBE = None
+
+
+class _ConvProbe:
+    def __init__(self, flops, stream):
+        self.on = CONV_PROBE is not None and stream in (None, torch.cuda.current_stream().cuda_stream)
+        self.flops = flops
+
+    def __enter__(self):
+        if self.on:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.on:
+            self.e1.record()
+            CONV_PROBE.append((self.e0, self.e1, self.flops))
 
 
 def _tc_workspace(device):
@@ -82,9 +101,10 @@ def conv2d_tc(x, wh, wl, bias, out, res=None, KH=1, KW=1, stride=1, pad=0, act=A
     B, H, W, Cin = x.shape
     Cout = wh.shape[0]
     ws = _tc_workspace(x.device)
-    check(lib().aotb_conv2d_nhwc_tc(_p(x), wh.data_ptr(), wl.data_ptr(), _p(bias), _p(res), _p(out), B, H, W, Cin,
-                                    _nhwc_ld(x), Cout, _nhwc_ld(out), _nhwc_ld(res) if res is not None else 0, KH, KW,
-                                    stride, pad, act, ws.data_ptr(), ws.numel(), _st(stream)), "aotb_conv2d_nhwc_tc")
+    with _ConvProbe(2.0 * out.shape[0] * out.shape[1] * out.shape[2] * Cout * KH * KW * Cin, stream):
+        check(lib().aotb_conv2d_nhwc_tc(_p(x), wh.data_ptr(), wl.data_ptr(), _p(bias), _p(res), _p(out), B, H, W, Cin,
+                                        _nhwc_ld(x), Cout, _nhwc_ld(out), _nhwc_ld(res) if res is not None else 0, KH, KW,
+                                        stride, pad, act, ws.data_ptr(), ws.numel(), _st(stream)), "aotb_conv2d_nhwc_tc")
     return out
 
 
@@ -113,10 +133,11 @@ def linear(x, wt, bias, out, res=None, act=ACT_NONE, stream=None):
             M, K = x.shape
             N = wt.shape[1]
             ws = _tc_workspace(x.device)
-            check(lib().aotb_conv2d_nhwc_tc(_p(x), t[0].data_ptr(), t[1].data_ptr(), _p(bias), _p(res), _p(out), 1, M, 1,
-                                            K, x.stride(0), N, out.stride(0), res.stride(0) if res is not None else 0,
-                                            1, 1, 1, 0, act, ws.data_ptr(), ws.numel(), _st(stream)),
-                  "aotb_conv2d_nhwc_tc")
+            with _ConvProbe(2.0 * M * N * K, stream):
+                check(lib().aotb_conv2d_nhwc_tc(_p(x), t[0].data_ptr(), t[1].data_ptr(), _p(bias), _p(res), _p(out), 1, M, 1,
+                                                K, x.stride(0), N, out.stride(0), res.stride(0) if res is not None else 0,
+                                                1, 1, 1, 0, act, ws.data_ptr(), ws.numel(), _st(stream)),
+                      "aotb_conv2d_nhwc_tc")
             return out
     _chk(x, wt, bias, out, res)
     M, K = x.shape
@@ -358,6 +379,33 @@ def logits_argmax(lowres_nchw, label, align_corners, stream=None):
     return label
 
 
+def soft_logit_aggregation(logits, out, max_obj, stream=None):
+    """logits: list of E contiguous NCHW maps [1, 1 + max_obj, H, W]; out [1, 1 + E * max_obj, H, W]."""
+    import ctypes
+    _chk(out, *logits)
+    E = len(logits)
+    HW = out.shape[-2] * out.shape[-1]
+    for t in logits:
+        if not t.is_contiguous() or t.shape[1] != 1 + max_obj or t.shape[-2] * t.shape[-1] != HW:
+            raise AotbError("soft_logit_aggregation: logit maps must be contiguous [1, 1 + max_obj, H, W] of one size")
+    if not out.is_contiguous() or out.shape[1] != 1 + E * max_obj:
+        raise AotbError("soft_logit_aggregation: out must be contiguous [1, 1 + E * max_obj, H, W]")
+    arr = (ctypes.c_void_p * E)(*[t.data_ptr() for t in logits])
+    check(lib().aotb_soft_logit_aggregation_f32(arr, E, int(max_obj), _p(out), HW, _st(stream)),
+          "aotb_soft_logit_aggregation_f32")
+    return out
+
+
+def separate_labels(mask, out, max_obj, stream=None):
+    """mask: contiguous label map with HW elements; out [E, ...HW...] receives the per-engine renumbered label maps."""
+    _chk(mask, out)
+    E, HW = out.shape[0], mask.numel()
+    if not mask.is_contiguous() or not out.is_contiguous() or out.numel() != E * HW:
+        raise AotbError("separate_labels: mask [HW] and out [E, HW] must be contiguous")
+    check(lib().aotb_separate_labels_f32(_p(mask), E, int(max_obj), _p(out), HW, _st(stream)), "aotb_separate_labels_f32")
+    return out
+
+
 def nearest_resize(x, out, stream=None):
     _chk(x, out)
     H, W = x.shape[-2:]
@@ -401,7 +449,9 @@ def tc_pack_rows(src, dst, row_off=0, div=1.0, row_off_dev=None, stream=None):
 #   "tile"   all 16 softmax warps on one 128x128 score tile at a time (4 threads per row)
 #   "groups" two groups of 8 warps, one per query tile, running out of phase (2 threads per row, 64 scores in registers)
 #   "ahead"  three score buffers in TMEM: S runs one tile ahead of the softmax and the TMEM read of the next tile is
-#            issued under the ex2 pass of the current one (built at the end of round 1, NOT yet run on a GPU)
+#            issued under the ex2 pass of the current one (bit-identical to "tile", 16 % slower: profiles/r02_summary.md)
+#   "pair"   two co-resident CTAs per SM (128 queries, 64-key tiles, three score buffers each) whose softmax phases
+#            interleave on the MUFU pipe; packed-fp32 softmax arithmetic (lt_attn_tc2.cu)
 LT_VARIANT = os.environ.get("AOTB_LT_VARIANT", "tile")
 # 1: the mbarrier waits on the softmax -> MMA -> softmax chain poll instead of sleeping with a suspend-time hint
 LT_SPIN = os.environ.get("AOTB_LT_SPIN", "0") == "1"
@@ -413,9 +463,10 @@ def lt_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True
     With splits > 1, `part` = (Opart [S,N,H*32], Mpart [S,H,N], Lpart [S,H,N]) and O receives the merge.
     `variant` (default: AOTB_LT_VARIANT) selects the softmax layout: "tile", "groups" or "ahead"."""
     v = LT_VARIANT if variant is None else variant
-    if v not in ("tile", "groups", "ahead"):
-        raise AotbError(f"unknown long-term attention variant '{v}' (tile | groups | ahead)")
-    mode = (1 if exact else 0) | (2 if v == "groups" else 0) | (4 if LT_SPIN else 0) | (8 if v == "ahead" else 0)
+    if v not in ("tile", "groups", "ahead", "pair"):
+        raise AotbError(f"unknown long-term attention variant '{v}' (tile | groups | ahead | pair)")
+    mode = (1 if exact else 0) | (2 if v == "groups" else 0) | (4 if LT_SPIN else 0) | (8 if v == "ahead" else 0) | \
+        (16 if v == "pair" else 0)
     H, nq_cap, _ = Qp.shape
     kv_cap = Kp.shape[1]
     if splits > 1:

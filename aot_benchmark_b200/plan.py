@@ -42,7 +42,10 @@ class Plan:
         dev = next(model.parameters()).device
         self._require_cuda(dev)
         self.device = dev
-        sd = {k: v.detach() for k, v in model.state_dict().items()}
+        # all packing arithmetic (float64 BN fold, transposes, fp16 hi/lo splits, prefix sums) runs on the HOST on a copy of
+        # the state dict and only the finished tables are uploaded (_upload): building a plan launches no GPU kernels, so
+        # the first launches of a process are the path's own kernels (and a reload costs memcpys, not ~1000 tiny launches)
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
         self.sd = sd
         self.deaot = cfg.MODEL_VOS == "deaot"
         self.L = cfg.MODEL_LSTT_NUM
@@ -51,12 +54,52 @@ class Plan:
         self.align_corners = bool(cfg.MODEL_ALIGN_CORNERS)
         self.nid = cfg.MODEL_MAX_OBJ_NUM + 1
         self._tc_keys = []
+        self._tc_list = []
         self._encoder(cfg.MODEL_ENCODER)
         w = sd["encoder_projector.weight"]
         self.proj = NS(w=self._reg(self._conv_w(w), w.shape[1]), b=self._f(sd["encoder_projector.bias"]))
         self.layers = [self._gpm_layer(i) if self.deaot else self._lstt_layer(i) for i in range(self.L)]
         self._decoder()
         self._idbank()
+        self._upload()
+        self.sd = None
+
+    def _upload(self):
+        """Move every packed host tensor hanging off the plan to the device (shared tensors stay shared) and register the
+        split-fp16 [Cout, K] copies of the GEMM-shaped weights under their device pointers."""
+        from . import ops
+        memo = {}
+
+        def up(t):
+            e = memo.get(id(t))
+            if e is None:
+                e = memo[id(t)] = (t, t.to(self.device))      # keep the host tensor alive: ids stay unique during the walk
+            return e[1]
+
+        def walk(o):
+            if isinstance(o, torch.Tensor):
+                return up(o)
+            if isinstance(o, NS):
+                for k, v in list(vars(o).items()):
+                    setattr(o, k, walk(v))
+                return o
+            if isinstance(o, list):
+                return [walk(v) for v in o]
+            if isinstance(o, tuple):
+                return tuple(walk(v) for v in o)
+            return o
+
+        for k, v in list(vars(self).items()):
+            if k not in ("sd", "cfg", "device", "_tc_keys", "_tc_list"):
+                setattr(self, k, walk(v))
+        for w in self._tc_list:
+            e = memo.get(id(w))
+            if e is None:
+                continue                                       # e.g. Q / K projections that only live on concatenated
+            wh, wl = ops.split_fp16(w)
+            ops.register_tc_weights(e[1], wh.to(self.device), wl.to(self.device))
+            self._tc_keys.append(e[1].data_ptr())
+        self._tc_list = []
 
     @staticmethod
     def _require_cuda(dev):
@@ -67,13 +110,10 @@ class Plan:
     def _reg(self, w, cin=None):
         """Register split-fp16 [Cout, K] copies of a GEMM-shaped fp32 weight [K, Cout] for the tensor-core conv
         (eligible when the per-tap channel count and Cout are multiples of 64); ops.conv2d / ops.linear pick them up."""
-        from . import ops
         K, N = w.shape
         cin = K if cin is None else cin
         if cin % 4 == 0 and N % 64 == 0 and (cin % 64 == 0 or K != cin):   # general-Cin path only for real convs (stem)
-            wh, wl = ops.split_fp16(w)
-            ops.register_tc_weights(w, wh, wl)
-            self._tc_keys.append(w.data_ptr())
+            self._tc_list.append(w)                                         # split + registered at upload time
         return w
 
     def __del__(self):
@@ -86,7 +126,7 @@ class Plan:
 
     # ------------------------------------------------------------------ helpers
     def _f(self, t):
-        return t.to(self.device, torch.float32).contiguous()
+        return t.to(torch.float32).contiguous()            # host; uploaded by _upload()
 
     def _conv_w(self, w, scale=None):
         # [Cout,Cin,KH,KW] -> [KH*KW*Cin, Cout]
@@ -174,7 +214,7 @@ class Plan:
         pw = torch.nn.functional.pad(pw, (0, 0, 0, 0, 0, 4 - pw.shape[1]))        # zero 4th input channel (NHWC4 image)
         e = NS(embed=S["embed"], window=ws, patch=NS(w=self._conv_w(pw), b=self._f(sd[p + "patch_embed.proj.bias"])),
                patch_norm=self._norm(p + "patch_embed.norm"), stages=[])
-        idx = swin_relative_position_index(ws).reshape(-1).to(self.device)
+        idx = swin_relative_position_index(ws).reshape(-1)
         for i, (depth, heads) in enumerate(zip(S["depths"], S["heads"])):
             dim = S["embed"] * 2 ** i
             stg = NS(dim=dim, heads=heads, blocks=[], down=None, norm=self._norm(f"{p}norm{i}"))
@@ -194,7 +234,7 @@ class Plan:
             if (q + "reduction.weight") in sd:
                 w = self._reg(self._f(sd[q + "reduction.weight"].t()))
                 stg.down = NS(norm=self._norm(q + "norm"), w=w,
-                              b=torch.zeros(w.shape[1], dtype=torch.float32, device=self.device))   # bias=False :333
+                              b=torch.zeros(w.shape[1], dtype=torch.float32))   # bias=False :333
             e.stages.append(stg)
         return e
 

@@ -163,25 +163,29 @@ def run_ours(args):
         if world < 2:
             raise SystemExit("--mode shard needs torchrun with >= 2 ranks (the bank is sharded over ranks)")
         eng.enable_kv_sharding(rank, world)
-    frames, mask = make_clip(K + 1, seed=1234 + (0 if shard else rank))
+    FULL = 99                                          # BASELINE configs[1]: 1 reference + 99 propagated frames
+    want_full = (K != FULL) and not args.no_full_clip and not shard
+    n_frames = (max(K, FULL) if want_full else K) + 1
+    frames, mask = make_clip(n_frames, seed=1234 + (0 if shard else rank))
     frames_dev = [f.to(dev) for f in frames]          # ~4.9 MB each, 490 MB for the clip: larger than L2
     frames_host = [f.pin_memory() for f in frames]
     mask_dev = mask.to(dev)
     label_host = torch.empty((1, 1, H_OUT, W_OUT), dtype=torch.uint8).pin_memory()
+    from aot_benchmark_b200 import engine as engine_mod
+    from aot_benchmark_b200 import ops as ops_mod
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_clip(mode, n_steps, timed):
+    def run_clip(mode, n_steps):
         eng.restart_engine()
         with torch.no_grad():
             eng.add_reference_frame(frames_dev[0], mask_dev, obj_nums=[OBJS], frame_step=0)
             barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            from aot_benchmark_b200 import engine as _em
-            l0 = L.aotb_launch_count() + _em.REPLAYED_KERNELS[0]
+            l0 = L.aotb_launch_count() + engine_mod.REPLAYED_KERNELS[0]
             ev0.record()
             for t in range(1, n_steps + 1):
                 if mode == "fused":
@@ -190,7 +194,7 @@ def run_ours(args):
                     step_dropin(eng, frames_host[t], label_host, dev)
             ev1.record()
             barrier()
-            l1 = L.aotb_launch_count() + _em.REPLAYED_KERNELS[0]
+            l1 = L.aotb_launch_count() + engine_mod.REPLAYED_KERNELS[0]
         ms = ev0.elapsed_time(ev1)
         if dist is not None:
             t = torch.tensor([ms], device=dev)
@@ -201,45 +205,86 @@ def run_ours(args):
     with torch.no_grad():
         # warm-up passes (buffers, module load, CUDA-graph capture of every call variant incl. the every-5th-frame
         # bank append): >= W frames, at least 11 so both memory-update variants have been captured
-        run_clip("fused", min(max(Wm, 11), K), False)
-        run_clip("dropin", min(max(Wm, 11), K), False)
+        run_clip("fused", min(max(Wm, 11), K))
+        run_clip("dropin", min(max(Wm, 11), K))
     e0 = lambda: eng.aot_engines[0]
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    # ---- timed: value (fused mask path, resident inputs, CUDA graphs)
-    from aot_benchmark_b200 import engine as engine_mod
-    ms_value, launches = run_clip("fused", K, True)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = run_clip("dropin", K, True)
-    # ---- probe pass: same clip, eager launches, CUDA events around every long-term attention launch
-    eng_probe = []
-    engine_mod.LT_PROBE = eng_probe
-    run_clip("fused", K, True)
-    engine_mod.LT_PROBE = None
-    # ---- roofline of the long-term attention kernel (FLOPs = 4*N*Tk*C per launch)
-    torch.cuda.synchronize()
-    flops = sum(f for (_, _, f) in eng_probe)
-    lt_ms = sum(a.elapsed_time(b) for (a, b, _) in eng_probe)
     peaks, how = _peaks()
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    clips = 1 if shard else world            # shard mode: one clip, total work fixed -> strong scaling
+
+    def measure(n_steps, sample_clocks):
+        """value pass (fused mask path, resident inputs, CUDA graphs), e2e pass (drop-in API, pinned host frames), probe pass
+        (same clip, eager launches, CUDA events around every long-term attention and every tensor-core conv launch)."""
+        sampler = ClockSampler(local)
+        if sample_clocks and rank == 0:
+            sampler.start()
+        ms_value, launches = run_clip("fused", n_steps)
+        clocks = sampler.stop() if (sample_clocks and rank == 0) else None
+        ms_e2e, _ = run_clip("dropin", n_steps)
+        lt_probe, conv_probe = [], []
+        engine_mod.LT_PROBE = lt_probe
+        run_clip("fused", n_steps)
+        engine_mod.LT_PROBE = None
+        ops_mod.CONV_PROBE = conv_probe        # separate pass: events around ~75 short launches per frame perturb the LT timing
+        engine_mod.LT_PROBE = []
+        run_clip("fused", n_steps)
+        engine_mod.LT_PROBE = None
+        ops_mod.CONV_PROBE = None
+        torch.cuda.synchronize()
+        lt_flops = sum(f for (_, _, f) in lt_probe)
+        lt_ms = sum(a.elapsed_time(b) for (a, b, _) in lt_probe)
+        cv_flops = sum(f for (_, _, f) in conv_probe)
+        cv_ms = sum(a.elapsed_time(b) for (a, b, _) in conv_probe)
+        return {"ms_value": ms_value, "ms_e2e": ms_e2e, "launches": int(launches), "clocks": clocks,
+                "lt": (lt_flops, lt_ms, len(lt_probe)), "conv": (cv_flops, cv_ms, len(conv_probe))}
+
+    def lt_roofline(m, n_steps):
+        flops, ms, n = m["lt"]
+        achieved = flops / (ms / 1e3) / 1e12 if ms > 0 else 0.0
+        return {"achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+                "launches": n, "avg_launch_us": round(1e3 * ms / max(n, 1), 2)}
+
+    def conv_roofline(m, n_steps):
+        flops, ms, n = m["conv"]
+        achieved = flops / (ms / 1e3) / 1e12 if ms > 0 else 0.0
+        return {"kernel": "conv_tc_kernel family (tcgen05 implicit GEMM, fp16x2 split: every Conv2d / Linear of the frame)",
+                "bound": "tensor", "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
+                "frac": round(achieved / peak, 4), "launches_per_frame": round(n / max(n_steps, 1), 1),
+                "gflop_per_frame": round(flops / max(n_steps, 1) / 1e9, 2), "ms_per_frame": round(ms / max(n_steps, 1), 4),
+                "algorithmic": "FLOPs = 2*M*Cout*(KH*KW*Cin) per launch, summed over the launches of the clip",
+                "timing": "CUDA events around every launch in an eager (graph-free, PDL-free) probe pass of the same clip"}
+
+    m = measure(K, True)
+    m_full = measure(FULL, False) if want_full else None
+    cfg4 = None
+    if args.cfg4_frames > 0 and args.model == "r50_aotl" and not shard:
+        del frames_dev, frames_host, frames                 # ~1 GB of cfg2 frames
+        eng.restart_engine()
+        torch.cuda.empty_cache()
+        cfg4 = measure_cfg4(args.cfg4_frames, rank, world, dev, dist)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    clips = 1 if shard else world            # shard mode: one clip, total work fixed -> strong scaling
-    fps = clips * K / (ms_value / 1e3)
-    fps_e2e = clips * K / (ms_e2e / 1e3)
-    achieved = flops / (lt_ms / 1e3) / 1e12 if lt_ms > 0 else 0.0
-    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    fps = clips * K / (m["ms_value"] / 1e3)
+    fps_e2e = clips * K / (m["ms_e2e"] / 1e3)
     traffic, traffic_note = None, None
     ncu_json = os.path.join(REPO, "profiles", "lt_attn_ncu_latest.json")
-    if os.path.exists(ncu_json):
+    if os.path.exists(ncu_json) and cfg.MODEL_VOS == "aot":
         nj = json.load(open(ncu_json))
         traffic = nj.get("traffic_bytes")
         traffic_note = f"{nj.get('launch')}: dram read+write of one ncu --set full capture ({nj.get('source')})"
+    lt_name = engine_mod.LT_KERNEL_NAME if cfg.MODEL_VOS == "aot" else engine_mod.deaot_lt_kernel_name()
+    rl = {"kernel": lt_name, "bound": "tensor"}
+    rl.update(lt_roofline(m, K))
+    rl.update({"traffic": traffic, "traffic_note": traffic_note,
+               "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({how})",
+               "algorithmic": f"FLOPs = 4*N*Tk*C per launch (N={e0().enc_hw}, C=256, Tk={e0().enc_hw}*m)"
+               if cfg.MODEL_VOS == "aot" else f"FLOPs = 2*N*Tk*(128+1024) per launch (N={e0().enc_hw}, Tk={e0().enc_hw}*m)",
+               "timing": "CUDA events around every launch in an eager (graph-free) probe pass of the same clip"})
     out = {
         "metric": "frames/sec (480p, 10 obj)", "value": round(fps, 3), "unit": "frames/s", "n_gpus": world,
-        "steps": K, "warmup": Wm, "ms_per_step": round(ms_value / K, 4), "higher_is_better": True,
+        "steps": K, "warmup": Wm, "ms_per_step": round(m["ms_value"] / K, 4), "higher_is_better": True,
         "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.model} inference, synthetic {'1.3x480p' if H_IN > 481 else '480p'} clip (net input {H_IN}x{W_IN}, output "
                                f"{H_OUT}x{W_OUT}), {OBJS} objects, 1 reference + {K} propagated frames, long-term gap "
@@ -251,22 +296,135 @@ def run_ours(args):
         "e2e": {"value": round(fps_e2e, 3), "unit": "frames/s",
                 "h2d_bytes_per_step": int(frames_host[1].numel() * 4), "d2h_bytes_per_step": int(label_host.numel()),
                 "path": "AOTInferEngine drop-in API as networks/managers/evaluator.py drives it, pinned host frames"},
-        "gpu_launches": int(launches),
-        "roofline": {"kernel": engine_mod.LT_KERNEL_NAME if cfg.MODEL_VOS == "aot"
-                     else "attn_f32_kernel<128,256> (fp32 SIMT flash attention, DeAOT 1 x 128 / 1024 head)",
-                     "bound": "tensor", "achieved": round(achieved, 2),
-                     "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_note": traffic_note,
-                     "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({how})",
-                     "launches": len(eng_probe), "avg_launch_us": round(1e3 * lt_ms / max(len(eng_probe), 1), 2),
-                     "algorithmic": f"FLOPs = 4*N*Tk*C per launch (N={e0().enc_hw}, C=256, Tk={e0().enc_hw}*m)"
-                     if cfg.MODEL_VOS == "aot" else f"FLOPs = 2*N*Tk*(128+1024) per launch (N={e0().enc_hw}, Tk={e0().enc_hw}*m)",
-                     "timing": "CUDA events around every launch in an eager (graph-free) probe pass of the same clip"},
-        "clocks": clocks,
+        "gpu_launches": m["launches"],
+        "roofline": rl,
+        "roofline_conv": conv_roofline(m, K),
+        "clocks": m["clocks"],
     }
+    if m_full is not None:
+        # the BASELINE configs[1] clip in full (the bank reaches 20 memory frames), whatever --steps the driver passed
+        fl = {"kernel": lt_name, "bound": "tensor"}
+        fl.update(lt_roofline(m_full, FULL))
+        out["full_clip"] = {"steps": FULL, "value": round(clips * FULL / (m_full["ms_value"] / 1e3), 3), "unit": "frames/s",
+                            "ms_per_step": round(m_full["ms_value"] / FULL, 4),
+                            "e2e": round(clips * FULL / (m_full["ms_e2e"] / 1e3), 3), "gpu_launches": m_full["launches"],
+                            "roofline": fl, "roofline_conv": conv_roofline(m_full, FULL)}
+    if cfg4 is not None:
+        out["cfg4"] = cfg4
+    if not args.skip_cpu_baseline:
+        out["gpu_eager_baseline"] = gpu_eager_baseline(args.model, dev)
     out["cpu_baseline"] = None if args.skip_cpu_baseline else cpu_baseline(args.model, threads=os.cpu_count())
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def measure_cfg4(n_prop, rank, world, dev, dist, distinct=48):
+    """BASELINE configs[3]: SwinB-AOTL, ONE 1.3x480p clip (net input 592x1040) of 1 reference + n_prop propagated frames, long-term
+    gap 5 (the bank reaches 1 + n_prop/5 memory frames).  One GPU: the bank lives on that GPU.  N > 1 GPUs: every rank propagates
+    the same clip, memory frame f lives on rank f % N, each rank attends over its shard and the un-normalised (O | m | l)
+    partials are exchanged once per layer per frame (one packed all-gather) and merged exactly -- strong scaling of the
+    long-term attention, everything else replicated.  Inputs resident in HBM (48 distinct 7.4 MB frames, cycled: > L2)."""
+    from aot_benchmark_b200 import EngineConfig, build_engine, build_vos_model, ops
+    from oracle.aot_oracle import synthetic_video
+    Hc, Wc = 592, 1040
+    cfg = EngineConfig("bench4", "swinb_aotl")
+    torch.manual_seed(0)
+    model = build_vos_model(cfg.MODEL_VOS, cfg).to(dev).eval()
+    eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=dev.index,
+                       long_term_mem_gap=cfg.TEST_LONG_TERM_MEM_GAP, short_term_mem_skip=cfg.TEST_SHORT_TERM_MEM_SKIP).eval()
+    if world > 1:
+        eng.enable_kv_sharding(rank, world)
+    frames, mask = synthetic_video(distinct + 1, Hc, Wc, OBJS, seed=4321)          # the SAME clip on every rank
+    frames = [f.to(dev) for f in frames]
+    mask = mask.to(dev)
+
+    def clip(n):
+        eng.restart_engine()
+        with torch.no_grad():
+            eng.add_reference_frame(frames[0], mask, obj_nums=[OBJS], frame_step=0)
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for t in range(1, n + 1):
+                eng.match_propogate_one_frame(frames[1 + (t - 1) % distinct])
+                eng.decode_current_logits(None)
+                a0 = eng.aot_engines[0]
+                label = torch.empty((1, 1, Hc, Wc), dtype=torch.float32, device=dev)
+                ops.logits_argmax(a0.pred_id_logits, label, a0.align_corners)
+                eng.update_memory(label)
+            e1.record()
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    clip(min(n_prop, 26))                     # warm-up: graph capture of both memory-update variants, first bank growth
+    ms = clip(n_prop)
+    a0 = eng.aot_engines[0]
+    rec = {"workload": f"swinb_aotl inference, synthetic 1.3x480p clip (net input {Hc}x{Wc}), {OBJS} objects, 1 reference + "
+                       f"{n_prop} propagated frames, long-term gap {cfg.TEST_LONG_TERM_MEM_GAP}, ONE clip on {world} GPU(s)",
+           "n_gpus": world, "steps": n_prop, "value": round(n_prop / (ms / 1e3), 3), "unit": "frames/s",
+           "ms_per_step": round(ms / n_prop, 4), "scaling": "strong",
+           "mode": "bank on one GPU" if world == 1 else
+                   f"long-term bank sharded by memory frame over {world} GPUs, one packed (O|m|l) all-gather per layer per frame + exact merge",
+           "memory_frames_end": int(a0._mem_frames), "local_bank_rows_end": int(a0.bank_len), "tokens_per_frame": int(a0.enc_hw)}
+    del eng, model, frames
+    torch.cuda.empty_cache()
+    return rec
+
+
+def gpu_eager_baseline(model_name, dev, max_frames=12):
+    """The reference's algorithm as eager PyTorch on the SAME B200 (the bar a rewrite has to clear): the
+    oracle restatement with device='cuda', fp32, TF32 off, the evaluator's span, inputs resident; a bounded sample of the
+    clip.  A baseline arm only -- nothing on the product path touches it."""
+    from aot_benchmark_b200 import EngineConfig, build_vos_model
+    from oracle import aot_oracle as O
+    cfg = EngineConfig("eager", model_name)
+    torch.manual_seed(0)
+    sd = build_vos_model(cfg.MODEL_VOS, cfg).state_dict()
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        frames, mask = make_clip(max_frames + 1, seed=1234)
+        frames = [f.to(dev) for f in frames]
+        mask = mask.to(dev)
+        oe = O.OracleEngine(sd, O.OracleConfig(model_name), device=dev)
+
+        def one(t):
+            oe.match_propogate_one_frame(frames[t])
+            lg = oe.decode_current_logits((H_OUT, W_OUT))
+            lab = torch.softmax(lg, 1).argmax(1, keepdim=True).float()
+            oe.update_memory(F.interpolate(lab, size=oe.input_size_2d, mode="nearest"))
+
+        with torch.no_grad():
+            oe.add_reference_frame(frames[0], mask, [OBJS], 0)
+            for t in range(1, 4):                      # warm-up (cuDNN autotune, allocator)
+                one(t)
+            oe.restart_engine()
+            oe.add_reference_frame(frames[0], mask, [OBJS], 0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for t in range(1, max_frames + 1):
+                one(t)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        return {"value": round(max_frames / (ms / 1e3), 3), "unit": "frames/s", "kind": "port, eager PyTorch (cuDNN/cuBLAS fp32, TF32 off) on the same GPU",
+                "sample": f"frames 1-{max_frames} of the same clip (bank holds <= {1 + max_frames // cfg.TEST_LONG_TERM_MEM_GAP} memory frames)"}
+    except Exception as e:                              # a baseline arm must never take the bench line down
+        return {"value": None, "error": f"{type(e).__name__}: {e}"[:300]}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
 
 
 # ---------------------------------------------------------------------------------------------
@@ -286,7 +444,7 @@ def _best_threads(step_fn, candidates):
 
 def _thread_candidates():
     n = os.cpu_count() or 1
-    return sorted({n, max(1, n // 2), min(n, 32), min(n, 16)}, reverse=True)
+    return sorted({n, max(1, n // 2), min(n, 32), min(n, 16), min(n, 8), min(n, 4)}, reverse=True)
 
 
 def cpu_baseline(model_name, threads, max_frames=4, budget_s=40.0):
@@ -388,6 +546,11 @@ def main():
     ap.add_argument("--mode", default="dp", choices=["dp", "shard"],
                     help="dp: one clip per GPU (default, weak scaling); shard: one clip, long-term bank sharded over the "
                          "ranks with an NCCL exchange of the attention partials per layer (BASELINE configs[3], strong scaling)")
+    ap.add_argument("--cfg4-frames", type=int, default=int(os.environ.get("AOTB_BENCH_CFG4_FRAMES", "500")),
+                    help="propagated frames of the additional BASELINE configs[3] record (SwinB-AOTL, one clip, long-term bank "
+                         "sharded over the GPUs when N > 1); 0 disables it")
+    ap.add_argument("--no-full-clip", action="store_true",
+                    help="development only: when --steps != 99, skip the additional 99-frame full_clip sub-record")
     ap.add_argument("--skip-cpu-baseline", action="store_true",
                     help="development only: omit the cpu_baseline leg (the driver's default run keeps it)")
     args = ap.parse_args()

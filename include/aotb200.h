@@ -160,6 +160,14 @@ int aotb_logits_postproc_f32(const float* logits_nhwc, float* lowres_nchw, float
 /* fused upsample + argmax (networks/managers/evaluator.py:339-361 for one engine, no TTA). */
 int aotb_logits_argmax_f32(const float* lowres_nchw, float* label, int h, int w, int NC, int Ho, int Wo,
                            int align_corners, void* stream);
+/* networks/engines/aot_engine.py:565-582 (AOTInferEngine.soft_logit_aggregation) for n_engines sub-engines of max_obj (= 10)
+ * objects each, fused into one pass: logits[e] -> NCHW fp32 [1 + max_obj][HW] on the device (the array of pointers itself is
+ * host memory); out [1 + n_engines * max_obj][HW] = logit(clamp([prod_e softmax_e[0], softmax_0[1:], softmax_1[1:], ...])). */
+int aotb_soft_logit_aggregation_f32(const float* const* logits, int n_engines, int max_obj, float* out, int HW,
+                                    void* stream);
+/* networks/engines/aot_engine.py:515-533 (AOTInferEngine.separate_mask, label-map form): out[e][i] = mask[i] - e*max_obj if
+ * e*max_obj < mask[i] <= (e+1)*max_obj else 0, for e in [0, n_engines). */
+int aotb_separate_labels_f32(const float* mask, int n_engines, int max_obj, float* out, int HW, void* stream);
 /* F.interpolate(mode="nearest") of a label map: networks/managers/evaluator.py:418-421. */
 int aotb_nearest_resize_f32(const float* in, float* out, int H, int W, int Ho, int Wo, void* stream);
 

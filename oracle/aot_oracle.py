@@ -239,10 +239,10 @@ def swin_block(W: Dict[str, Tensor], p: str, x: Tensor, H: int, Wd: int, heads: 
     q, k, v = qkv[0] * (d ** -0.5), qkv[1], qkv[2]
     att = q @ k.transpose(-2, -1)                                              # [nW, heads, 49, 49]
     table = W[p + "attn.relative_position_bias_table"]                          # [(2ws-1)^2, heads]
-    bias = table[swin_rel_index(ws).reshape(-1)].view(ws * ws, ws * ws, heads).permute(2, 0, 1)
+    bias = table[swin_rel_index(ws).reshape(-1).to(table.device)].view(ws * ws, ws * ws, heads).permute(2, 0, 1)
     att = att + bias.unsqueeze(0)
     if shift > 0:
-        att = att + swin_shift_mask(Hp, Wp, ws, shift, att.dtype).unsqueeze(1)
+        att = att + swin_shift_mask(Hp, Wp, ws, shift, att.dtype).to(att.device).unsqueeze(1)
     att = torch.softmax(att, dim=-1)
     o = (att @ v).transpose(1, 2).reshape(nwy * nwx, ws * ws, C)
     o = _lin(o, W, p + "attn.proj")
@@ -325,7 +325,7 @@ def one_hot_mask(mask: Tensor, cls_num: int) -> Tensor:
     # utils/image.py:69-74
     if mask.dim() == 3:
         mask = mask.unsqueeze(1)
-    idx = torch.arange(0, cls_num + 1).view(1, -1, 1, 1).to(mask.dtype)
+    idx = torch.arange(0, cls_num + 1, device=mask.device).view(1, -1, 1, 1).to(mask.dtype)
     return (mask == idx).to(mask.dtype)
 
 
@@ -369,8 +369,8 @@ def local_window_scores(q2d: Tensor, k2d: Tensor, relk_w: Tensor, relk_b: Tensor
     rel = F.conv2d(q2d, relk_w, relk_b, groups=H).view(n, H, WINDOW * WINDOW, h, w)  # on UNSCALED q (:327)
     qs = (q2d / T).view(n, H, d, h, w)
     kp = F.pad(k2d, (MAX_DIS, MAX_DIS, MAX_DIS, MAX_DIS)).view(n, H, d, h + 2 * MAX_DIS, w + 2 * MAX_DIS)
-    ones = F.pad(torch.ones(1, 1, h, w, dtype=q2d.dtype), (MAX_DIS, MAX_DIS, MAX_DIS, MAX_DIS))
-    s = torch.empty(n, H, WINDOW * WINDOW, h, w, dtype=q2d.dtype)
+    ones = F.pad(torch.ones(1, 1, h, w, dtype=q2d.dtype, device=q2d.device), (MAX_DIS, MAX_DIS, MAX_DIS, MAX_DIS))
+    s = torch.empty(n, H, WINDOW * WINDOW, h, w, dtype=q2d.dtype, device=q2d.device)
     big = 1e8 if q2d.dtype in (torch.float32, torch.float64) else 1e4
     for iy in range(WINDOW):
         for ix in range(WINDOW):
@@ -388,7 +388,7 @@ def local_window_aggregate(p: Tensor, v2d: Tensor, H: int, relv: Optional[Tensor
     n, cv, h, w = v2d.shape
     dv = cv // H
     vp = F.pad(v2d, (MAX_DIS, MAX_DIS, MAX_DIS, MAX_DIS)).view(n, H, dv, h + 2 * MAX_DIS, w + 2 * MAX_DIS)
-    o = torch.zeros(n, H, dv, h, w, dtype=v2d.dtype)
+    o = torch.zeros(n, H, dv, h, w, dtype=v2d.dtype, device=v2d.device)
     for iy in range(WINDOW):
         for ix in range(WINDOW):
             wi = iy * WINDOW + ix
@@ -422,7 +422,7 @@ def local_attention(q2d, k2d, v2d, relk_w, relk_b, relv, H, chunk: int = 256) ->
     rel = F.conv2d(q2d, relk_w, relk_b, groups=H).view(n, H, P, h * w)
     ku = F.unfold(k2d, WINDOW, padding=MAX_DIS).view(n, H, d, P, h * w)
     s = torch.einsum("nhdp,nhdwp->nhwp", (q2d / T).view(n, H, d, h * w), ku) + rel
-    inside = F.unfold(torch.ones(1, 1, h, w, dtype=q2d.dtype), WINDOW, padding=MAX_DIS).view(1, 1, P, h * w)
+    inside = F.unfold(torch.ones(1, 1, h, w, dtype=q2d.dtype, device=q2d.device), WINDOW, padding=MAX_DIS).view(1, 1, P, h * w)
     s = s - (1 - inside) * 1e8
     p = torch.softmax(s, dim=2)
     o = torch.empty(n, H, dv, h * w, dtype=v2d.dtype)
@@ -641,10 +641,13 @@ class OracleEngine:
     AOTEngine / DeAOTEngine.  Method names follow the reference."""
 
     def __init__(self, weights: Dict[str, Tensor], cfg, long_term_mem_gap: Optional[int] = None,
-                 short_term_mem_skip: int = 1, dtype=torch.float32, keep_taps: bool = False):
+                 short_term_mem_skip: int = 1, dtype=torch.float32, keep_taps: bool = False, device="cpu"):
+        # device="cuda": the same eager restatement on a GPU (bench.py's gpu_eager_baseline arm -- what the reference's
+        # eager PyTorch code costs on the same B200; still a baseline / checker, never the product path)
         self.cfg = cfg
         self.dtype = dtype
-        self.W = {k: (v.detach().to("cpu").to(dtype) if v.is_floating_point() else v.detach().cpu())
+        self.device = torch.device(device)
+        self.W = {k: (v.detach().to(self.device).to(dtype) if v.is_floating_point() else v.detach().to(self.device))
                   for k, v in weights.items()}
         self.deaot = cfg.MODEL_VOS == "deaot"
         self.max_obj_num = cfg.MODEL_MAX_OBJ_NUM
@@ -707,7 +710,7 @@ class OracleEngine:
             self.enc_hw = self.enc_size_2d[0] * self.enc_size_2d[1]
         self.curr_enc_embs = enc
         if self.pos_emb is None:
-            self.pos_emb = pos_emb_sine(*self.enc_size_2d, dtype=self.dtype).view(1, -1, self.enc_hw).permute(2, 0, 1)
+            self.pos_emb = pos_emb_sine(*self.enc_size_2d, dtype=self.dtype).to(self.device).view(1, -1, self.enc_hw).permute(2, 0, 1)
         id_emb = self.assign_identity(one_hot)
         self.curr_lstt_output = self._lstt(enc, None, None, id_emb)
         _, _, long_m, short_m = self.curr_lstt_output

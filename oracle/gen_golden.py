@@ -98,6 +98,41 @@ def video_case(name, out_dir):
     }, os.path.join(out_dir, f"video_{name}.pt"))
 
 
+# BASELINE geometries (configs[1], [2], [3]) through the REAL reference: name -> (model, H, W, out_h, out_w, frames, objs, gap,
+# flavour, propagated frames whose low-res logits are stored).  Labels of every frame are stored zlib-compressed; logits only
+# for the listed frames (1.1-1.7 MB each): the first propagated frame, the frame before / at / after the first bank growth.
+FULL_CASES = {
+    "r50_aotl_480p": ("r50_aotl", 481, 849, 480, 854, 8, 10, 5, "calibrated", (1, 5, 6, 7)),
+    "r50_deaotl_480p": ("r50_deaotl", 481, 849, 480, 854, 8, 10, 5, "calibrated", (1, 5, 6, 7)),
+    "swinb_aotl_592": ("swinb_aotl", 592, 1040, 592, 1040, 4, 10, 2, "calibrated", (1, 2, 3)),
+}
+
+
+def full_case(name, out_dir):
+    import time
+    import zlib
+    model_name, H, W, oh, ow, T, objs, gap, flavour, keep = FULL_CASES[name]
+    t0 = time.time()
+    sd, frames, mask, ref_lo, ref_labels = run_reference_video(model_name, H, W, oh, ow, T, objs, gap, flavour)
+    t_ref = time.time() - t0
+    oe = O.OracleEngine(sd, O.OracleConfig(model_name), long_term_mem_gap=gap)
+    with torch.no_grad():
+        o_lo, o_labels = O.run_video(oe, frames, mask, objs, (oh, ow), forced_masks=ref_labels)
+    max_d = max((a - b).abs().max().item() for a, b in zip(ref_lo, o_lo))
+    mism = sum((a != b).sum().item() for a, b in zip(ref_labels, o_labels))
+    used = sorted(set(int(v) for l in ref_labels for v in l.unique().tolist()))
+    print(f"[{name}] reference ran {T - 1} propagated frames in {t_ref:.1f} s; oracle vs reference: max|dlogit|={max_d:.3e} "
+          f"label mismatches={mism} labels used={used}")
+    lab = torch.stack([t.to(torch.uint8).reshape(oh, ow) for t in ref_labels]).contiguous()
+    torch.save({
+        "model": model_name, "H": H, "W": W, "out_size": (oh, ow), "frames": T, "objs": objs, "gap": gap,
+        "flavour": flavour, "seed": 0, "weights_checksum": OW.checksum(sd),
+        "logit_frames": list(keep), "ref_logits_lo": {int(t): ref_lo[t - 1].to(torch.float32).clone() for t in keep},
+        "ref_labels_zlib": zlib.compress(lab.numpy().tobytes(), 9), "ref_labels_shape": tuple(lab.shape),
+        "oracle_pin_max_dlogit": max_d, "oracle_pin_label_mismatch": mism,
+    }, os.path.join(out_dir, f"full_{name}.pt"))
+
+
 EVENT_CASES = {"aott_multi14_events": "aott", "deaott_multi14_events": "deaott"}
 
 
@@ -222,6 +257,9 @@ def main():
     for name in EVENT_CASES:
         if a.only in (None, "events", name):
             events_case(a.out, name)
+    for name in FULL_CASES:
+        if a.only in ("full", name):              # not part of the default regeneration (minutes of CPU)
+            full_case(name, a.out)
 
 
 if __name__ == "__main__":

@@ -58,13 +58,13 @@ def main():
         V = torch.randn(Tk, H * D, generator=g).to(dev)
         kcap = ((Tk + 127) // 128) * 128 + 128
         Kp, Vp = pack(K, kcap), pack(V, kcap)
-        splits = a.splits or lt_splits(N, H, Tk)
-        part = None
-        if splits > 1:
-            part = (torch.empty(splits, N, H * D, device=dev), torch.empty(splits, H, N, device=dev),
-                    torch.empty(splits, H, N, device=dev))
         ref = None
         for v in a.variants.split(","):
+            splits = a.splits or lt_splits(N, H, Tk, variant=v)
+            part = None
+            if splits > 1:
+                part = (torch.empty(splits, N, H * D, device=dev), torch.empty(splits, H, N, device=dev),
+                        torch.empty(splits, H, N, device=dev))
             O = torch.empty(N, H * D, device=dev)
             run = lambda: ops.lt_attention_tc(Qp, Kp, Vp, N, Tk, O=O, splits=splits, exact=True, part=part, variant=v,
                                               merge=False)
@@ -83,10 +83,8 @@ def main():
             if ref is None:
                 ref = O.clone()
             err = (O - ref).abs().max().item()
-            tiles = ((N + 255) // 256) * 2 * H * ((Tk + 127) // 128)
-            ctas = ((N + 255) // 256) * H * splits
-            waves = math.ceil(ctas / 148)
-            clk_per_tile = us * 1e-6 * sm_clock / (tiles / min(ctas, 148) if waves == 1 else tiles / 148)
+            tiles = ((N + 127) // 128) * H * ((Tk + 127) // 128)      # 128 x 128 score tiles of the launch
+            clk_per_tile = us * 1e-6 * sm_clock / (tiles / 148)
             row = {"variant": v, "frames": m, "Tk": Tk, "splits": splits, "us": round(us, 2),
                    "tflops": round(4.0 * N * Tk * H * D / us / 1e6, 1), "clk_per_tile_per_sm": round(clk_per_tile),
                    "max_abs_diff_vs_first": err}

@@ -28,8 +28,8 @@ def main():
     mask = mask.cuda()
     outs = {}
     from aot_benchmark_b200 import engine as engine_mod
-    modes = ("plain", "sharded") + (("sharded_p2p",) if os.environ.get("AOTB_TEST_P2P", "1") == "1" else ())
-    for mode in modes:
+
+    def run(mode):
         engine_mod.SHARD_XCHG = "p2p" if mode == "sharded_p2p" else "nccl"      # peer-memory exchange vs NCCL all-gathers
         eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=local, long_term_mem_gap=1)
         if mode != "plain":
@@ -37,20 +37,42 @@ def main():
         with torch.no_grad():
             lo, labels = O.run_video(eng, frames, mask, 10, (240, 320),
                                      forced_masks=outs["plain"][1] if mode != "plain" else None)
+        lo = [t.clone() for t in lo]
         outs[mode] = (lo, labels)
         if mode != "plain":
             e0 = eng.aot_engines[0]
-            print(f"rank {rank}: [{mode}] local bank rows {e0.bank_len} of {e0._mem_frames} memory frames x {e0.enc_hw}")
-    d = 0.0
-    for mode in modes[1:]:
-        dm = max((a[:, :11] - b[:, :11]).abs().max().item() for a, b in zip(outs["plain"][0], outs[mode][0]))
-        print(f"rank {rank}/{world}: max |dlogit| {mode} vs unsharded = {dm:.3e}")
-        d = max(d, dm)
+            print(f"rank {rank}: [{mode}] local bank rows {e0.bank_len} of {e0._mem_frames} memory frames x {e0.enc_hw}", flush=True)
+            dm = max((a[:, :11] - b[:, :11]).abs().max().item() for a, b in zip(outs["plain"][0], lo))
+            print(f"rank {rank}/{world}: max |dlogit| {mode} vs unsharded = {dm:.3e}", flush=True)
+            return dm
+        return 0.0
+
+    run("plain")
+    # the NCCL exchange is validated and its verdict all-reduced BEFORE the peer-memory exchange is attempted, so a failure
+    # or hang of the latter cannot mask it
+    d = run("sharded")
     t = torch.tensor([d], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dist.destroy_process_group()
-    if t.item() > 1e-4:
-        sys.exit(1)
+    ok_nccl = t.item() <= 1e-4
+    if rank == 0:
+        print(f"nccl exchange: {'OK' if ok_nccl else 'FAILED'} (max |dlogit| over ranks {t.item():.3e})", flush=True)
+    ok_p2p = True
+    if os.environ.get("AOTB_TEST_P2P", "1") == "1":
+        try:
+            d2 = run("sharded_p2p")
+            t2 = torch.tensor([d2], device="cuda")
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            ok_p2p = t2.item() <= 1e-4
+            if rank == 0:
+                print(f"p2p exchange: {'OK' if ok_p2p else 'FAILED'} (max |dlogit| over ranks {t2.item():.3e})", flush=True)
+        except Exception as e:                     # reported separately; the NCCL verdict above stands
+            ok_p2p = False
+            print(f"rank {rank}: p2p exchange: FAILED with {type(e).__name__}: {e}", flush=True)
+    try:
+        dist.destroy_process_group()
+    except Exception:
+        pass
+    sys.exit(0 if ok_nccl and ok_p2p else (1 if not ok_nccl else 3))
 
 
 if __name__ == "__main__":

@@ -391,7 +391,27 @@ def gp_attention_tc(Qp, Kp, Vp, N, Tk, O=None, Tk_dev=None, splits=1, exact=True
     return O
 
 
-EMULATED = ("image_to_nhwc4", "conv2d", "linear", "layernorm", "window_attention", "patch_merge", "eltwise",
+def separate_labels(mask, out, max_obj, stream=None):
+    """Contract of aotb_separate_labels_f32: engine e keeps ids (e*max_obj, (e+1)*max_obj], renumbered from 1."""
+    for e in range(out.shape[0]):
+        lo, hi = e * max_obj + 1, (e + 1) * max_obj
+        keep = (mask >= lo) & (mask <= hi)
+        out[e].copy_(torch.where(keep, mask - lo + 1, torch.zeros_like(mask)))
+    return out
+
+
+def soft_logit_aggregation(logits, out, max_obj, stream=None):
+    """Contract of aotb_soft_logit_aggregation_f32 (aot_engine.py:565-582)."""
+    probs = [torch.softmax(l, dim=1) for l in logits]
+    bg = torch.ones_like(probs[0][:, 0:1])
+    for p in probs:
+        bg = bg * p[:, 0:1]
+    merged = torch.cat([bg] + [p[:, 1:1 + max_obj] for p in probs], dim=1).clamp(1e-5, 1 - 1e-5)
+    out.copy_(torch.log(merged / (1 - merged)))
+    return out
+
+
+EMULATED = ("separate_labels", "soft_logit_aggregation", "image_to_nhwc4", "conv2d", "linear", "layernorm", "window_attention", "patch_merge", "eltwise",
             "nchw_to_nhwc", "nhwc_to_nchw", "maxpool3x3s2", "dwconv", "bilinear", "groupnorm_workspace", "groupnorm",
             "attention", "attn_merge", "attn_merge_peers", "tc_pack_rows", "lt_attention_tc", "local_attention", "local_attention_tile",
             "id_embed", "id_embed_runs", "logits_postproc", "logits_argmax", "nearest_resize", "bank_append",
@@ -415,5 +435,6 @@ def install_engine(monkeypatch):
     monkeypatch.setattr(plan.Plan, "_require_cuda", staticmethod(lambda dev: None))
     monkeypatch.setattr(engine, "_cur_stream", lambda: 0)
     monkeypatch.setattr(engine, "USE_GRAPHS", False)
+    monkeypatch.setattr(engine, "SUB_ENGINE_STREAMS", False)
     monkeypatch.setattr(engine.AOTEngine, "_check_img", lambda self, img: None)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _FakeStream())

@@ -58,7 +58,12 @@ def test_product_never_imports_oracle():
     assert not bad, bad
 
 
-def test_separate_mask_matches_reference_semantics():
+def test_separate_mask_matches_reference_semantics(monkeypatch):
+    """Host logic of AOTInferEngine.separate_mask (object counts per sub-engine) with the label kernel emulated on CPU; the
+    kernel itself is checked on the GPU (tests/test_gpu_ops.py)."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import emu_ops
+    emu_ops.install_engine(monkeypatch)
     from aot_benchmark_b200 import EngineConfig, build_engine, build_vos_model
     cfg = EngineConfig("t", "aott")
     eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=build_vos_model(cfg.MODEL_VOS, cfg))

@@ -387,3 +387,30 @@ def test_id_embed_runs(align, ln):
                       ln_gamma=ga.to(d) if ln else None, ln_beta=be.to(d) if ln else None)
     err = (out.cpu().double() - ref[0].permute(1, 2, 0).reshape(ho * wo, 256)).abs().max().item()
     assert err < (2e-4 if ln else 3e-6), err
+
+
+def test_soft_logit_aggregation_and_separate_labels_kernels():
+    """Row f.2 kernels vs the reference's tensor expressions (aot_engine.py:515-533, 565-582)."""
+    from aot_benchmark_b200 import ops
+    d = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    E, per, H, W = 3, 10, 37, 53
+    logits = [(torch.randn(1, 1 + per, H, W, generator=g) * 4).to(d) for _ in range(E)]
+    logits[2][:, 6:] = -1e10                                  # unused ids of the last engine (aot_engine.py:368-370)
+    out = torch.empty(1, 1 + E * per, H, W, device=d)
+    ops.soft_logit_aggregation(logits, out, per)
+    fg, bg = [], []
+    for l in logits:
+        p = torch.softmax(l, dim=1)
+        bg.append(p[:, 0:1])
+        fg.append(p[:, 1:1 + per])
+    ref = torch.logit(torch.cat([torch.prod(torch.cat(bg, dim=1), dim=1, keepdim=True)] + fg, dim=1).clamp(1e-5, 1 - 1e-5))
+    assert (out - ref).abs().max().item() < 2e-5
+    assert torch.equal(out.argmax(1), ref.argmax(1))
+    mask = torch.randint(0, 26, (1, 1, H, W), generator=g).float().to(d)
+    sep = torch.empty(3, 1, 1, H, W, device=d)
+    ops.separate_labels(mask, sep, per)
+    for e in range(3):
+        s_id, e_id = e * per + 1, (e + 1) * per
+        fgm = ((mask >= s_id) & (mask <= e_id)).float()
+        assert torch.equal(sep[e], (fgm * mask - s_id + 1) * fgm)

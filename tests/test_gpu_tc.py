@@ -105,25 +105,15 @@ def test_lt_attention_tc_matches_simt_and_splits():
     assert (O4 - ref).abs().max().item() < 1e-4
 
 
-def _variant_enabled(v):
-    """Non-default softmax layouts are tested when they are the configured default or named in AOTB_TEST_VARIANTS
-    (comma-separated), e.g. AOTB_TEST_VARIANTS=groups,ahead."""
-    import os
-    from aot_benchmark_b200 import ops
-    return ops.LT_VARIANT == v or v in os.environ.get("AOTB_TEST_VARIANTS", "").split(",") or \
-        (v == "groups" and os.environ.get("AOTB_TEST_GROUPS", "0") == "1")
-
-
-@pytest.mark.parametrize("variant", ["groups", "ahead"])
+@pytest.mark.parametrize("variant", ["groups", "ahead", "pair"])
 @pytest.mark.parametrize("N,Tk,splits,exact", [(128, 128, 1, True), (300, 700, 1, True), (1674, 5022 + 77, 1, True),
                                                (1674, 1674 * 7, 5, True), (200, 300, 8, True), (300, 700, 1, False),
                                                (1674, 1674 * 3 + 5, 3, False)])
 def test_lt_attention_tc_layouts(N, Tk, splits, exact, variant):
     """The alternative softmax layouts ("groups": 2 threads per row, one TMEM read per tile; "ahead": three score
-    buffers, TMEM read under the ex2 pass) compute the same maxima and the same P as the default one-tile layout; only
+    buffers, TMEM read under the ex2 pass; "pair": two co-resident CTAs per SM, 64-key tiles, packed-fp32 softmax with a
+    truncating hi / lo split of P) compute the same maxima and the same P as the default one-tile layout; only
     the association of the row sums may differ: outputs agree to ~1e-6 and all match the fp64 oracle."""
-    if not _variant_enabled(variant):
-        pytest.skip(f"layout '{variant}' not enabled (AOTB_LT_VARIANT={variant} or AOTB_TEST_VARIANTS={variant})")
     from aot_benchmark_b200 import ops
     d = torch.device("cuda:0")
     g = torch.Generator().manual_seed(N * 7 + Tk)
@@ -145,7 +135,7 @@ def test_lt_attention_tc_layouts(N, Tk, splits, exact, variant):
         outs.append((O, part))
     assert torch.isfinite(outs[1][0]).all()
     assert (outs[0][0] - outs[1][0]).abs().max().item() < 2e-5
-    if splits > 1:
+    if splits > 1 and variant != "pair":                        # ("pair" cuts the key range into 64-key tiles: other split bounds)
         assert torch.equal(outs[0][1][1], outs[1][1][1])          # per-split row maxima are identical
     ref = _ref(Q, K, V)
     assert (outs[1][0].cpu().double() - ref).abs().max().item() < (2e-4 if exact else 5e-2)

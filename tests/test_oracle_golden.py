@@ -99,6 +99,26 @@ def test_video_vs_reference_golden(name, golden_dir):
     assert mism <= 1e-4 * total  # fp32 summation-order ties only
 
 
+@pytest.mark.parametrize("name", ["r50_aotl_480p", "r50_deaotl_480p", "swinb_aotl_592"])
+def test_full_geometry_fixture_pin(name, golden_dir):
+    """BASELINE-geometry goldens of the REAL reference (tests/golden/full_*.pt): the oracle pin recorded at generation time
+    (whole clip, teacher-forced) and, live, the first propagated frame of the oracle against the stored reference logits."""
+    from oracle.fixtures import load_full_labels
+    g = torch.load(os.path.join(golden_dir, f"full_{name}.pt"))
+    assert g["oracle_pin_max_dlogit"] < 1e-4 and g["oracle_pin_label_mismatch"] <= 1e-5 * g["frames"] * g["out_size"][0] * g["out_size"][1]
+    labels = load_full_labels(g)
+    assert len(labels) == g["frames"] - 1 and tuple(labels[0].shape[-2:]) == tuple(g["out_size"])
+    if name != "r50_aotl_480p":
+        return                                   # one live frame is enough for the CPU suite's time budget
+    sd = OW.build_state_dict(g["model"], seed=g["seed"], flavour=g["flavour"])
+    assert OW.checksum(sd) == g["weights_checksum"]
+    frames, mask = O.synthetic_video(2, g["H"], g["W"], g["objs"], seed=1234 + g["seed"])
+    eng = O.OracleEngine(sd, O.OracleConfig(g["model"]), long_term_mem_gap=g["gap"])
+    with torch.no_grad():
+        lo, _ = O.run_video(eng, frames, mask, g["objs"], tuple(g["out_size"]), forced_masks=labels[:1])
+    assert (lo[0] - g["ref_logits_lo"][1]).abs().max().item() < 1e-4
+
+
 def _events_inputs(g):
     frames, full = O.synthetic_video(g["frames"], g["H"], g["W"], 14, seed=g["video_seed"])
     first = torch.where(full <= g["first_objs"], full, torch.zeros_like(full))
