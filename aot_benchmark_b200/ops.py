@@ -406,6 +406,37 @@ def separate_labels(mask, out, max_obj, stream=None):
     return out
 
 
+def preprocess_bgr_u8(img_u8, out, taps=None, flip=False, stream=None):
+    """img_u8 uint8 [H, W, 3] (device); out fp32 [1, 3, Ho, Wo]; taps = (ix, cx, iy, cy) device tables or None (same size)."""
+    if img_u8.dtype != torch.uint8 or not img_u8.is_cuda or not img_u8.is_contiguous() or img_u8.dim() != 3 or img_u8.shape[2] != 3:
+        raise AotbError("preprocess_bgr_u8: image must be a contiguous uint8 CUDA tensor [H, W, 3]")
+    _chk(out)
+    if not out.is_contiguous():
+        raise AotbError("preprocess_bgr_u8: out must be contiguous [1, 3, Ho, Wo]")
+    H, W = int(img_u8.shape[0]), int(img_u8.shape[1])
+    Ho, Wo = int(out.shape[-2]), int(out.shape[-1])
+    if taps is None:
+        ptrs = (None, None, None, None)
+    else:
+        ix, cx, iy, cy = taps
+        if ix.dtype != torch.int32 or iy.dtype != torch.int32 or cx.dtype != torch.float32 or cy.dtype != torch.float32 \
+                or tuple(ix.shape) != (Wo, 4) or tuple(cx.shape) != (Wo, 4) or tuple(iy.shape) != (Ho, 4) or tuple(cy.shape) != (Ho, 4):
+            raise AotbError("preprocess_bgr_u8: taps must be (int32 [Wo,4], fp32 [Wo,4], int32 [Ho,4], fp32 [Ho,4])")
+        ptrs = tuple(t.data_ptr() for t in (ix, cx, iy, cy))
+    check(lib().aotb_preprocess_bgr_u8(img_u8.data_ptr(), H, W, ptrs[0], ptrs[1], ptrs[2], ptrs[3], _p(out), Ho, Wo,
+                                       1 if flip else 0, _st(stream)), "aotb_preprocess_bgr_u8")
+    return out
+
+
+def label_to_u8(label, out_u8, stream=None):
+    _chk(label)
+    if out_u8.dtype != torch.uint8 or not out_u8.is_cuda or not out_u8.is_contiguous() or not label.is_contiguous() \
+            or out_u8.numel() != label.numel():
+        raise AotbError("label_to_u8: contiguous float32 label and uint8 output of the same size on the device")
+    check(lib().aotb_label_to_u8(_p(label), out_u8.data_ptr(), label.numel(), _st(stream)), "aotb_label_to_u8")
+    return out_u8
+
+
 def nearest_resize(x, out, stream=None):
     _chk(x, out)
     H, W = x.shape[-2:]

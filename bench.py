@@ -207,7 +207,6 @@ def run_ours(args):
         # bank append): >= W frames, at least 11 so both memory-update variants have been captured
         run_clip("fused", min(max(Wm, 11), K))
         run_clip("dropin", min(max(Wm, 11), K))
-    e0 = lambda: eng.aot_engines[0]
     peaks, how = _peaks()
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     clips = 1 if shard else world            # shard mode: one clip, total work fixed -> strong scaling
@@ -256,6 +255,8 @@ def run_ours(args):
 
     m = measure(K, True)
     m_full = measure(FULL, False) if want_full else None
+    enc_hw = eng.aot_engines[0].enc_hw
+    h2d_bytes = int(frames_host[1].numel() * 4)
     cfg4 = None
     if args.cfg4_frames > 0 and args.model == "r50_aotl" and not shard:
         del frames_dev, frames_host, frames                 # ~1 GB of cfg2 frames
@@ -279,8 +280,8 @@ def run_ours(args):
     rl.update(lt_roofline(m, K))
     rl.update({"traffic": traffic, "traffic_note": traffic_note,
                "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({how})",
-               "algorithmic": f"FLOPs = 4*N*Tk*C per launch (N={e0().enc_hw}, C=256, Tk={e0().enc_hw}*m)"
-               if cfg.MODEL_VOS == "aot" else f"FLOPs = 2*N*Tk*(128+1024) per launch (N={e0().enc_hw}, Tk={e0().enc_hw}*m)",
+               "algorithmic": f"FLOPs = 4*N*Tk*C per launch (N={enc_hw}, C=256, Tk={enc_hw}*m)"
+               if cfg.MODEL_VOS == "aot" else f"FLOPs = 2*N*Tk*(128+1024) per launch (N={enc_hw}, Tk={enc_hw}*m)",
                "timing": "CUDA events around every launch in an eager (graph-free) probe pass of the same clip"})
     out = {
         "metric": "frames/sec (480p, 10 obj)", "value": round(fps, 3), "unit": "frames/s", "n_gpus": world,
@@ -294,7 +295,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (distinct 4.9 MB frame per step, >126 MB activations per frame)",
                    "parallelism": f"bank-shard{world}" if shard else f"video-dp{world}"},
         "e2e": {"value": round(fps_e2e, 3), "unit": "frames/s",
-                "h2d_bytes_per_step": int(frames_host[1].numel() * 4), "d2h_bytes_per_step": int(label_host.numel()),
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(label_host.numel()),
                 "path": "AOTInferEngine drop-in API as networks/managers/evaluator.py drives it, pinned host frames"},
         "gpu_launches": m["launches"],
         "roofline": rl,

@@ -168,6 +168,15 @@ int aotb_soft_logit_aggregation_f32(const float* const* logits, int n_engines, i
 /* networks/engines/aot_engine.py:515-533 (AOTInferEngine.separate_mask, label-map form): out[e][i] = mask[i] - e*max_obj if
  * e*max_obj < mask[i] <= (e+1)*max_obj else 0, for e in [0, n_engines). */
 int aotb_separate_labels_f32(const float* mask, int n_engines, int max_obj, float* out, int HW, void* stream);
+/* Frame input side: dataloaders/eval_datasets.py:60-61 + dataloaders/video_transforms.py:594-715 (MultiRestrictSize's
+ * cv2.resize(INTER_CUBIC) of the float image, MultiToTensor's / 255, - mean, / std, HWC -> CHW) on the uint8 frame in one pass.
+ * img uint8 [H][W][3]; ix / cx [Wo][4] and iy / cy [Ho][4] = clamped tap indices and Keys-cubic (A = -0.75) weights per output
+ * column / row (all four null when Ho == H and Wo == W); flip != 0 mirrors horizontally after the resize; out fp32 [3][Ho][Wo]. */
+int aotb_preprocess_bgr_u8(const void* img, int H, int W, const int* ix, const float* cx, const int* iy, const float* cy,
+                           float* out, int Ho, int Wo, int flip, void* stream);
+/* Mask output side: utils/image.py:103-105 (`mask_tensor.cpu().numpy().astype('uint8')`): the float label map leaves the
+ * device as uint8 (1 byte per pixel over PCIe instead of 4 or 8). */
+int aotb_label_to_u8(const float* label, void* out_u8, int n, void* stream);
 /* F.interpolate(mode="nearest") of a label map: networks/managers/evaluator.py:418-421. */
 int aotb_nearest_resize_f32(const float* in, float* out, int H, int W, int Ho, int Wo, void* stream);
 

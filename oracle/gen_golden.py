@@ -242,6 +242,47 @@ def op_cases(out_dir):
     torch.save(out, os.path.join(out_dir, "ops_attention.pt"))
 
 
+def io_case(out_dir):
+    """Row f.3: the reference's own MultiRestrictSize + MultiToTensor (dataloaders/video_transforms.py:594-715) on a seeded
+    uint8 frame, and utils.image._save_mask's PNG, as fixtures for the GPU preprocessing kernel and the mask writer."""
+    import io as _io
+    import numpy as np
+    import dataloaders.video_transforms as tr
+    import utils.image as RI
+    from oracle import io_side as IO
+    rng = np.random.default_rng(7)
+    small = rng.integers(0, 256, (23, 31, 3)).astype(np.float32)
+    img = np.clip(np.kron(small, np.ones((5, 5, 1), np.float32)) + rng.normal(0, 6, (115, 155, 3)), 0, 255).astype(np.uint8)
+    cases = {"up_1.3_align": dict(max_short_edge=None, max_long_edge=800, flip=True, multi_scale=[1.0, 1.3], align_corners=True),
+             "down_long96": dict(max_short_edge=None, max_long_edge=96, flip=False, multi_scale=[1.0], align_corners=False),
+             "short_64": dict(max_short_edge=64, max_long_edge=800, flip=False, multi_scale=[1.0], align_corners=True)}
+    out = {"img": torch.from_numpy(img), "cases": {}}
+    for name, kw in cases.items():
+        sample = {"current_img": np.array(img, dtype=np.float32), "meta": {"flip": False}}
+        ref = tr.MultiToTensor()(tr.MultiRestrictSize(kw["max_short_edge"], kw["max_long_edge"], kw["flip"], kw["multi_scale"],
+                                                      kw["align_corners"])(sample))
+        tensors = [r["current_img"].float().contiguous() for r in ref]
+        k, worst = 0, 0.0
+        for sc in kw["multi_scale"]:
+            for fl in ((False, True) if kw["flip"] else (False,)):
+                mine = IO.preprocess(img, kw["max_short_edge"], kw["max_long_edge"], sc, kw["align_corners"], 16, fl)
+                worst = max(worst, (mine - tensors[k]).abs().max().item())
+                k += 1
+        print(f"[io {name}] {[tuple(t.shape) for t in tensors]} oracle vs reference max|d| = {worst:.2e}")
+        out["cases"][name] = {"kw": kw, "ref": tensors}
+    mask = (rng.integers(0, 4, (20, 27)).astype(np.uint8))
+    squeeze = [0, 3, 7, 12]
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        RI._save_mask(mask.copy(), os.path.join(d, "a.png"), None)
+        RI._save_mask(mask.copy(), os.path.join(d, "b.png"), squeeze)
+        out["mask"] = torch.from_numpy(mask)
+        out["squeeze_idx"] = squeeze
+        out["png_plain"] = open(os.path.join(d, "a.png"), "rb").read()
+        out["png_squeezed"] = open(os.path.join(d, "b.png"), "rb").read()
+    torch.save(out, os.path.join(out_dir, "io_side.pt"))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(REPO, "tests", "golden"))
@@ -257,6 +298,8 @@ def main():
     for name in EVENT_CASES:
         if a.only in (None, "events", name):
             events_case(a.out, name)
+    if a.only == "io":
+        io_case(a.out)
     for name in FULL_CASES:
         if a.only in ("full", name):              # not part of the default regeneration (minutes of CPU)
             full_case(name, a.out)

@@ -414,3 +414,40 @@ def test_soft_logit_aggregation_and_separate_labels_kernels():
         s_id, e_id = e * per + 1, (e + 1) * per
         fgm = ((mask >= s_id) & (mask <= e_id)).float()
         assert torch.equal(sep[e], (fgm * mask - s_id + 1) * fgm)
+
+
+def test_frame_preprocess_kernel_vs_reference_fixture(golden_dir):
+    """Row f.3: uint8 frame -> resize (cv2 INTER_CUBIC taps) + normalise + CHW in one kernel, against the tensors the REAL
+    reference's MultiRestrictSize + MultiToTensor produced (tests/golden/io_side.pt)."""
+    import os
+    from aot_benchmark_b200.io_side import FramePreprocessor
+    fx = torch.load(os.path.join(golden_dir, "io_side.pt"))
+    img = fx["img"].numpy()
+    for name, c in fx["cases"].items():
+        kw = c["kw"]
+        fp = FramePreprocessor(kw["max_short_edge"], kw["max_long_edge"], kw["flip"], kw["multi_scale"], kw["align_corners"])
+        outs = fp(img)
+        assert len(outs) == len(c["ref"])
+        for o, r in zip(outs, c["ref"]):
+            assert tuple(o.shape[1:]) == tuple(r.shape), name
+            assert (o[0].cpu() - r).abs().max().item() < 2e-5, name
+    # no-resize path: a frame that already has the network size
+    fp = FramePreprocessor(None, 800, False, [1.0], True)
+    same = torch.from_numpy(img[:113, :145].copy())
+    o = fp(same.numpy())[0]
+    from oracle import io_side as IO
+    assert (o[0].cpu() - IO.preprocess(same.numpy(), None, 800, 1.0, True)).abs().max().item() < 1e-6
+
+
+def test_async_mask_writer_from_device(tmp_path):
+    import numpy as np
+    from PIL import Image
+    from aot_benchmark_b200.io_side import AsyncMaskWriter
+    g = torch.Generator().manual_seed(3)
+    masks = [torch.randint(0, 11, (1, 1, 60, 85), generator=g).float().cuda() for _ in range(5)]
+    wr = AsyncMaskWriter(workers=2, ring=2)
+    for i, m in enumerate(masks):
+        wr.save(m, str(tmp_path / f"{i}.png"))
+    wr.close()
+    for i, m in enumerate(masks):
+        assert np.array_equal(np.array(Image.open(tmp_path / f"{i}.png")), m[0, 0].cpu().numpy().astype(np.uint8))

@@ -134,7 +134,9 @@ def test_lt_attention_tc_layouts(N, Tk, splits, exact, variant):
         torch.cuda.synchronize()
         outs.append((O, part))
     assert torch.isfinite(outs[1][0]).all()
-    assert (outs[0][0] - outs[1][0]).abs().max().item() < 2e-5
+    # exact mode: same P to fp32 rounding.  fast mode keeps one fp16 pass of P, whose rounding depends on the running row
+    # maximum and therefore on the key tiling: layouts with other tiles differ at the 1e-4 level (both within 5e-2 of fp64)
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < (2e-5 if exact else 1e-3)
     if splits > 1 and variant != "pair":                        # ("pair" cuts the key range into 64-key tiles: other split bounds)
         assert torch.equal(outs[0][1][1], outs[1][1][1])          # per-split row maxima are identical
     ref = _ref(Q, K, V)
