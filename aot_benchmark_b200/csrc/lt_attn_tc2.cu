@@ -1,36 +1,33 @@
 // Long-term attention (K1), "pair" layout: TWO co-resident CTAs per SM instead of one wide CTA.
 //
 // Same arithmetic contract as lt_attn_tc.cu (networks/layers/attention.py:82-117; fp16x2 split operands, fp32 accumulate).
-// Round-2 measurements (profiles/r02_summary.md): every single-CTA organisation of the softmax ("tile", "groups", "ahead")
-// lands at ~2400-2800 cycles per 128x128 score tile with no pipe saturated.  ncu (20-frame bank): 53 % of the stall samples
-// sit on MUFU.EX2 with the MUFU queue full (mio_throttle), i.e. during the ex2 pass the pipe IS saturated -- but the 16
-// softmax warps move in lockstep through tcgen05.ld -> max -> exchange -> ex2 -> tcgen05.st, so for the other half of the
-// tile the MUFU pipe (the real bound of a d = 32 head: 128 tensor FLOPs per exponential) idles.  Here the SM is shared by two
-// independent CTAs whose phases drift apart freely -- while one reads TMEM or converts P the other one feeds the MUFU pipe:
-//   CTA        128 queries x 1 head x 1 KV split, 192 threads: warps 0-3 softmax (ONE thread per query row), warp 4 TMA
-//              producer, warp 5 MMA issuer.  Register files are per scheduler and warps are allocated in groups of four, so
-//              two CTAs fit only with <= 8 warps each and <= 128 registers per thread (a first version with 8 softmax warps =
-//              10 warps x 96 registers was limited to ONE resident CTA and ran exactly as fast as the one-CTA layouts).
-//              83 KB of shared memory (Q tile + 4-stage K/V ring of 64-key tiles) and 256 TMEM columns per CTA.
+// Round-2 measurements (profiles/r02_summary.md) showed that every single-CTA organisation of the softmax ("tile",
+// "groups", "ahead") lands at ~2400-2800 cycles per 128x128 score tile although no pipe is saturated: 16 softmax warps
+// that move in lockstep through tcgen05.ld -> max -> exchange -> ex2 -> tcgen05.st leave the MUFU pipe (the real bound of a
+// d = 32 head: 128 tensor FLOPs per exponential) idle for more than half of the tile.  Here the SM is shared by two
+// independent CTAs whose phases drift apart freely -- while one reads TMEM or waits at its row-max barrier the other one
+// feeds the MUFU pipe:
+//   CTA        128 queries x 1 head x 1 KV split, 320 threads: warps 0-7 softmax, warp 8 TMA producer, warp 9 MMA issuer;
+//              __launch_bounds__(320, 2); 80 KB of shared memory and 256 TMEM columns per CTA.
 //   key tile   64 keys.  TMEM: S_0 | S_1 | S_2 (64 fp32 columns each) | O' (64) = 256 columns.  Score tile n lives in buffer
 //              n % 3 and the MMA warp runs up to three tiles ahead (S(0..2) up front, then wait P(n) -> PV(n) -> S(n + 3)), so
 //              a CTA's softmax never waits for the tensor pipe in steady state.
-//   softmax    thread r owns query row r (TMEM lane r): it reads its 64 scores once, the row maximum and the row sum are
-//              thread-local (no exchange through shared memory, no named barrier), then ex2, the fp16 hi / lo split, and P_hi /
-//              P_lo overwrite the thread's own score columns (hi: [0, 32), lo: [32, 64)).
+//   softmax    warp w owns TMEM lanes 32 (w % 4) .. +31 and key columns 32 (w / 4) .. +31 of the tile: two threads share a
+//              query row, each reads its 32 scores once, the half-row maxima are exchanged through shared memory (one
+//              256-thread named barrier), then ex2, row sums and the fp16 hi / lo split.  P_hi and P_lo of a thread's 32
+//              keys overwrite its own 32 score columns (hi: [c, c + 16), lo: [c + 16, c + 32)).
 //   issue diet the scale-and-shift, the row sums and the residuals run as packed fp32 pairs (fma.rn.f32x2 / add.rn.f32x2,
 //              one issue slot per two scores); P_hi is the fp32 value truncated to 11 significant bits (one LOP3), so the
 //              residual p - hi is exact and needs no fp16 -> fp32 unpack: 9.5 instructions per score pair instead of 14.
-//   rescale    O' is rescaled (rarely: only when a row maximum grows) by the row's thread after o_done says PV(n - 1) has
-//              completed; PV(n) is not issued before all 128 threads arrive on p_full(n).
+//   rescale    O' is rescaled (rarely: only when a row maximum grows) by the two threads of the row, 32 columns each, after
+//              o_done says PV(n - 1) has completed; PV(n) is not issued before all 256 threads arrive on p_full(n).
 #include "common.cuh"
 #include "tc_common.cuh"
-#include <cstdlib>
 
 namespace aotb {
 namespace tc {
 
-constexpr int P_BM = 128, P_BN = 64, P_STAGES = 4, P_THREADS = 192, P_TMA_WARP = 4, P_MMA_WARP = 5;
+constexpr int P_BM = 128, P_BN = 64, P_STAGES = 4, P_THREADS = 320, P_TMA_WARP = 8, P_MMA_WARP = 9;
 constexpr int P_QBYTES = P_BM * 128;    // 128 rows x 128 B
 constexpr int P_KVBYTES = P_BN * 128;   // 64 rows x 128 B (one K or V tile)
 constexpr float P_LOG2E = 1.4426950408889634f;
@@ -46,8 +43,6 @@ struct LtArgs2 {
     float* Lpart;
     int splits;
     int spin;
-    int knock;   // diagnostic knock-outs (timing studies only, results are wrong): 1 no ex2, 2 no PV MMAs, 4 no P write-back,
-                 // 8 no max exchange, 16 S issued only for the first three tiles, 32 no hi/lo arithmetic
 };
 
 struct __align__(8) BarriersP {
@@ -55,10 +50,12 @@ struct __align__(8) BarriersP {
     uint64_t kv_full[P_STAGES];
     uint64_t kv_free[P_STAGES];
     uint64_t s_full[3];     // S(n) complete in buffer n % 3; use k = n / 3 of a buffer completes phase k
-    uint64_t p_full[3];     // 128 arrivals: P(n) written over S(n)
+    uint64_t p_full[3];     // 256 arrivals: P(n) written over S(n)
     uint64_t o_done;        // committed after every PV: PV(n) completes phase n
     uint64_t o_final;       // the last PV
     uint32_t tmem_base;
+    float xmax[4][P_BM];    // [(n & 1) * 2 + key half][row]
+    float xsum[2][P_BM];
 };
 
 __device__ __forceinline__ uint64_t pk2(float a, float b) {
@@ -110,7 +107,7 @@ static int make_tmap_rows64_box(CUtensorMap* out, const void* base, int rows, in
 }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(256, 2)      // 192 threads are launched; (256, 2) caps ptxas at 128 registers
+__global__ void __launch_bounds__(P_THREADS, 2)
 lt_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const LtArgs2 a) {
     extern __shared__ uint8_t smem_raw[];
@@ -127,7 +124,7 @@ lt_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (tid == 0) {
         mbar_init(&B->q_full, 1);
         for (int s = 0; s < P_STAGES; ++s) { mbar_init(&B->kv_full[s], 1); mbar_init(&B->kv_free[s], 1); }
-        for (int b = 0; b < 3; ++b) { mbar_init(&B->s_full[b], 1); mbar_init(&B->p_full[b], P_BM); }
+        for (int b = 0; b < 3; ++b) { mbar_init(&B->s_full[b], 1); mbar_init(&B->p_full[b], 2 * P_BM); }
         mbar_init(&B->o_done, 1);
         mbar_init(&B->o_final, 1);
         fence_mbar_init();
@@ -189,12 +186,12 @@ lt_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const uint32_t d = tmem + 192;
                 const uint32_t p = tmem + (n % 3) * 64;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)      // P_hi of keys [16 kk, +16) at columns [8 kk, +8)
-                    mma_ts(d, p + 8 * kk, v + 128 * kk, IDESC_O, (kk > 0 || n > 0) ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk)      // P_hi of keys [16 kk, +16) at columns 32 (kk / 2) + 8 (kk % 2)
+                    mma_ts(d, p + 32 * (kk >> 1) + 8 * (kk & 1), v + 128 * kk, IDESC_O, (kk > 0 || n > 0) ? 1u : 0u);
                 if (EXACT) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)  // P_lo in the upper half of the score columns
-                        mma_ts(d, p + 32 + 8 * kk, v + 128 * kk, IDESC_O, 1);
+                    for (int kk = 0; kk < 4; ++kk)  // P_lo 16 columns further up in the same thread's score columns
+                        mma_ts(d, p + 32 * (kk >> 1) + 16 + 8 * (kk & 1), v + 128 * kk, IDESC_O, 1);
                 }
                 mma_commit(&B->o_done);
                 if (n + 1 == T) mma_commit(&B->o_final);
@@ -206,45 +203,45 @@ lt_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int n = 0; n < T; ++n) {
                 mbar_wait_cp(&B->p_full[n % 3], (n / 3) & 1, a.spin);
                 tc_fence_after();
-                if (!(a.knock & 2)) issue_PV(n);
-                else { mma_commit(&B->o_done); if (n + 1 == T) mma_commit(&B->o_final); mma_commit(&B->kv_free[n % P_STAGES]); }
-                if (n + 3 < T) {
-                    if (!(a.knock & 16)) issue_S(n + 3);
-                    else { mbar_wait_cp(&B->kv_full[(n + 3) % P_STAGES], ((n + 3) / P_STAGES) & 1, a.spin); mma_commit(&B->s_full[(n + 3) % 3]); }
-                }
+                issue_PV(n);
+                if (n + 3 < T) issue_S(n + 3);
             }
         }
     } else {
-        // ======================= softmax (4 warps, one thread per query row) =======================
-        const int row = warp * 32 + lane;                   // warp w owns TMEM lanes 32 w .. 32 w + 31
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        const uint32_t tO = tmem + lane_addr + 192;
+        // ======================= softmax (8 warps, two threads per query row) =======================
+        const int hf = warp >> 2, wq = warp & 3;           // key half of the tile, TMEM lane quadrant
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const uint32_t tO = tmem + lane_addr + 192 + hf * 32;      // this thread's 32 of the 64 O' columns (rescale)
         float m_used = -INFINITY;
         uint64_t lsum = pk2(0.f, 0.f);                              // two partial row sums, packed
         const uint64_t l2e2 = pk2(P_LOG2E, P_LOG2E);
         int b = 0;
         uint32_t par = 0;                                           // bit b: phase parity of the next use of buffer b
         for (int n = 0; n < T; ++n) {
-            const uint32_t tS = tmem + lane_addr + b * 64;
+            const uint32_t tS = tmem + lane_addr + b * 64 + hf * 32;
             mbar_wait_cp(&B->s_full[b], (par >> b) & 1u, a.spin);
             tc_fence_after();
-            uint32_t sr[64];
+            uint32_t sr[32];
             tmem_ld32(tS, sr);
-            tmem_ld32(tS + 32, sr + 32);
             tmem_wait_ld();
-            const int key0 = (tb + n) * P_BN;
-            if (key0 + 64 > Tk) {                    // only the last key tile of the bank is ragged
+            const int key0 = (tb + n) * P_BN + hf * 32;
+            if (key0 + 32 > Tk) {                    // warp-uniform: only the last key tile of the bank is ragged
 #pragma unroll
-                for (int k = 0; k < 64; ++k)
+                for (int k = 0; k < 32; ++k)
                     if (key0 + k >= Tk) sr[k] = __float_as_uint(-INFINITY);
             }
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-            for (int k = 0; k < 64; k += 2) {
+            for (int k = 0; k < 32; k += 2) {
                 mx0 = fmaxf(mx0, __uint_as_float(sr[k]));
                 mx1 = fmaxf(mx1, __uint_as_float(sr[k + 1]));
             }
-            const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
+            const int xb = (n & 1) * 2;
+            B->xmax[xb + hf][row] = fmaxf(mx0, mx1);
+            asm volatile("bar.sync 1, 256;" ::: "memory");                    // the 8 softmax warps
+            const float mt = fmaxf(B->xmax[xb][row], B->xmax[xb + 1][row]);
+            const float m_new = fmaxf(m_used, mt);
             const bool grow = (m_new > m_used) && (n > 0);
             if (__any_sync(0xffffffffu, grow)) {
                 // O' must be quiescent: PV(n - 1) complete (o_done), PV(n) not issued before all threads arrive on p_full
@@ -253,7 +250,7 @@ lt_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const float f = grow ? ex2((m_used - m_new) * P_LOG2E) : 1.f;
                 uint32_t orr[16];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     tmem_ld16(tO + 16 * c, orr);
                     tmem_wait_ld();
 #pragma unroll
@@ -270,17 +267,17 @@ lt_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // p = 2^(s*log2e - m*log2e) two scores per FFMA2; hi = p truncated to 11 significant bits (exactly representable
             // in fp16 for p >= 2^-14), lo = p - hi exact in fp32; both packed to fp16 and written back 16 keys at a time
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t ph[8], pl[8];
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     const int k = 16 * c + 2 * t;
                     float t0, t1;
                     upk2(fma2(pk2(__uint_as_float(sr[k]), __uint_as_float(sr[k + 1])), l2e2, neg2), t0, t1);
-                    const float p0 = (a.knock & 1) ? t0 * 1e-3f : ex2(t0), p1 = (a.knock & 1) ? t1 * 1e-3f : ex2(t1);
+                    const float p0 = ex2(t0), p1 = ex2(t1);
                     const uint64_t p2 = pk2(p0, p1);
                     lsum = add2(lsum, p2);
-                    if (EXACT && !(a.knock & 32)) {
+                    if (EXACT) {
                         const float h0 = __uint_as_float(__float_as_uint(p0) & 0xFFFFE000u);
                         const float h1 = __uint_as_float(__float_as_uint(p1) & 0xFFFFE000u);
                         ph[t] = cvt_h2(h0, h1);
@@ -289,16 +286,10 @@ lt_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         pl[t] = cvt_h2(r0, r1);
                     } else {
                         ph[t] = cvt_h2(p0, p1);
-                        if (EXACT) pl[t] = 0u;
                     }
                 }
-                if (!(a.knock & 4)) {
-                    tmem_st8(tS + 8 * c, ph);            // keys [16 c, +16) -> columns [8 c, +8)
-                    if (EXACT) tmem_st8(tS + 32 + 8 * c, pl);
-                } else if (ph[0] == 0x12345678u && pl[1] == 0x9abcdef0u) {
-                    tmem_st8(tS + 8 * c, ph);            // (keeps the values live)
-                    tmem_st8(tS + 32 + 8 * c, pl);
-                }
+                tmem_st8(tS + 8 * c, ph);                // keys [32 hf + 16 c, +16) -> columns [32 hf + 8 c, +8)
+                if (EXACT) tmem_st8(tS + 16 + 8 * c, pl);
             }
             tmem_wait_st();
             tc_fence_before();
@@ -307,40 +298,44 @@ lt_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             b = b == 2 ? 0 : b + 1;
         }
 
-        // ---- epilogue: this thread finishes the 32 output channels of its row
+        // ---- epilogue: this thread finishes output channels [16 hf, 16 hf + 16) of its row
         float s0, s1;
         upk2(lsum, s0, s1);
-        const float l = s0 + s1;
+        B->xsum[hf][row] = s0 + s1;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float l = B->xsum[0][row] + B->xsum[1][row];          // same order in both threads of the row
         const int q = q0 + row;
+        float o[16];
         if (T > 0) {
             mbar_wait(&B->o_final, 0);
             tc_fence_after();
+            uint32_t o0[16], o1[16];
+            tmem_ld16(tmem + lane_addr + 192 + hf * 16, o0);
+            tmem_ld16(tmem + lane_addr + 192 + 32 + hf * 16, o1);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = __uint_as_float(o0[k]) + __uint_as_float(o1[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = 0.f;
         }
-        float* dst = a.splits == 1 ? a.O + (size_t)q * a.ldo + h * 32 : a.Opart + ((size_t)z * a.N + q) * (a.H * 32) + h * 32;
-        const float inv = a.splits == 1 ? 1.f / l : 1.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {                        // 16 channels at a time: O'[:, 16c..] + O'[:, 32 + 16c..]
-            float o[16];
-            if (T > 0) {
-                uint32_t o0[16], o1[16];
-                tmem_ld16(tO + 16 * c, o0);
-                tmem_ld16(tO + 32 + 16 * c, o1);
-                tmem_wait_ld();
-#pragma unroll
-                for (int k = 0; k < 16; ++k) o[k] = (__uint_as_float(o0[k]) + __uint_as_float(o1[k])) * inv;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) o[k] = 0.f;
-            }
-            if (q < a.N) {
+        if (q < a.N) {
+            if (a.splits == 1) {
+                const float inv = 1.f / l;
+                float* dst = a.O + (size_t)q * a.ldo + h * 32 + hf * 16;
 #pragma unroll
                 for (int k = 0; k < 16; k += 4)
-                    *reinterpret_cast<float4*>(dst + 16 * c + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+                    *reinterpret_cast<float4*>(dst + k) = make_float4(o[k] * inv, o[k + 1] * inv, o[k + 2] * inv, o[k + 3] * inv);
+            } else {
+                float* dst = a.Opart + ((size_t)z * a.N + q) * (a.H * 32) + h * 32 + hf * 16;
+#pragma unroll
+                for (int k = 0; k < 16; k += 4)
+                    *reinterpret_cast<float4*>(dst + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+                if (hf == 0) {
+                    a.Mpart[((size_t)z * a.H + h) * a.N + q] = m_used;
+                    a.Lpart[((size_t)z * a.H + h) * a.N + q] = l;
+                }
             }
-        }
-        if (q < a.N && a.splits > 1) {
-            a.Mpart[((size_t)z * a.H + h) * a.N + q] = m_used;
-            a.Lpart[((size_t)z * a.H + h) * a.N + q] = l;
         }
     }
 
@@ -355,8 +350,6 @@ static size_t pair_smem_bytes() { return (size_t)P_QBYTES + 2 * P_STAGES * P_KVB
 int launch_lt_attn_pair(const void* Qp, int Nq_cap, const void* Kp, const void* Vp, int kv_cap, int N, int Tk,
                         const int* Tk_dev, int H, float* O, int ldo, float* Opart, float* Mpart, float* Lpart, int splits,
                         int exact, int spin, cudaStream_t st) {
-    static int knock = -1;
-    if (knock < 0) { const char* e = getenv("AOTB_LT_KNOCK"); knock = e ? atoi(e) : 0; }
     CUtensorMap tq, tk, tv;
     int rc;
     if ((rc = make_tmap_rows64_box(&tq, Qp, Nq_cap, H, P_BM)) != AOTB_OK) return rc;
@@ -373,15 +366,10 @@ int launch_lt_attn_pair(const void* Qp, int Nq_cap, const void* Kp, const void* 
             return AOTB_ERR_CUDA;
         }
         configured = true;
-        if (getenv("AOTB_LT_KNOCK")) {
-            int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lt_attn_pair_kernel<true>, P_THREADS, smem);
-            fprintf(stderr, "lt_attn_pair_kernel: %d CTAs / SM resident (smem %zu B)\n", nb, smem);
-        }
     }
     LtArgs2 a;
     a.N = N; a.Tk = Tk; a.Tk_dev = Tk_dev; a.H = H; a.O = O; a.ldo = ldo;
-    a.Opart = Opart; a.Mpart = Mpart; a.Lpart = Lpart; a.splits = splits; a.spin = spin; a.knock = knock;
+    a.Opart = Opart; a.Mpart = Mpart; a.Lpart = Lpart; a.splits = splits; a.spin = spin;
     dim3 grid(cdiv(N, P_BM), H, splits);
     if (exact) launch(lt_attn_pair_kernel<true>, grid, dim3(P_THREADS), smem, st, tq, tk, tv, a);
     else launch(lt_attn_pair_kernel<false>, grid, dim3(P_THREADS), smem, st, tq, tk, tv, a);

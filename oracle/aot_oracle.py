@@ -425,7 +425,7 @@ def local_attention(q2d, k2d, v2d, relk_w, relk_b, relv, H, chunk: int = 256) ->
     inside = F.unfold(torch.ones(1, 1, h, w, dtype=q2d.dtype, device=q2d.device), WINDOW, padding=MAX_DIS).view(1, 1, P, h * w)
     s = s - (1 - inside) * 1e8
     p = torch.softmax(s, dim=2)
-    o = torch.empty(n, H, dv, h * w, dtype=v2d.dtype)
+    o = torch.empty(n, H, dv, h * w, dtype=v2d.dtype, device=v2d.device)
     v5 = v2d.view(n, H, dv, h, w)
     for c0 in range(0, dv, chunk):
         c1 = min(dv, c0 + chunk)
