@@ -168,6 +168,28 @@ int aotb_soft_logit_aggregation_f32(const float* const* logits, int n_engines, i
 /* networks/engines/aot_engine.py:515-533 (AOTInferEngine.separate_mask, label-map form): out[e][i] = mask[i] - e*max_obj if
  * e*max_obj < mask[i] <= (e+1)*max_obj else 0, for e in [0, n_engines). */
 int aotb_separate_labels_f32(const float* mask, int n_engines, int max_obj, float* out, int HW, void* stream);
+/* A chain of tensor-core convolutions as ONE persistent kernel with tile-level dataflow (csrc/conv_chain.cu): replaces the
+ * per-layer launches of networks/encoders/resnet.py:34-54,140-157 (Bottleneck stacks, FrozenBN folded) by a program of 128-pixel
+ * tiles that start as soon as the tiles of the producing layer they read are complete.  Every layer follows the contract of
+ * aotb_conv2d_nhwc_tc (fp32 NHWC in / out, pre-split fp16 weights [Cout][KH*KW*Cin], bias, optional residual, activation) with
+ * Cin % 64 == 0 and Cout % 64 == 0; in_layer / res_layer name the chain layer that produces `in` / `res` (-1: complete before
+ * the launch).  Every output buffer must be written by exactly one layer of the chain (the SMs' L1 caches are not coherent:
+ * no address may change its value twice inside one launch).  aotb_conv_chain_plan sizes the device-resident program,
+ * aotb_conv_chain_build writes it (once per geometry, outside stream capture), aotb_conv_chain_run clears the dependency
+ * counters and launches the kernel (capturable); aotb_conv_chain_dump exposes the tile program to host-side tests. */
+typedef struct aotb_chain_layer {
+    const float* in;
+    const void* wh;
+    const void* wl;
+    const float* bias;
+    const float* res;
+    float* out;
+    int H, W, Cin, ldin, Cout, ldout, ldres, KH, KW, stride, pad, act, in_layer, res_layer;
+} aotb_chain_layer;
+int aotb_conv_chain_plan(const void* layers, int nlayers, size_t* program_bytes, int* ntiles, int* ncounters);
+int aotb_conv_chain_dump(const void* layers, int nlayers, int* tiles5, int max_tiles, int* layers7);
+int aotb_conv_chain_build(const void* layers, int nlayers, void* program, size_t program_bytes, void* stream);
+int aotb_conv_chain_run(void* program, int nlayers, int ntiles, int ncounters, void* stream);
 /* Frame input side: dataloaders/eval_datasets.py:60-61 + dataloaders/video_transforms.py:594-715 (MultiRestrictSize's
  * cv2.resize(INTER_CUBIC) of the float image, MultiToTensor's / 255, - mean, / std, HWC -> CHW) on the uint8 frame in one pass.
  * img uint8 [H][W][3]; ix / cx [Wo][4] and iy / cy [Ho][4] = clamped tap indices and Keys-cubic (A = -0.75) weights per output

@@ -15,4 +15,4 @@ timeout 600 python bench.py --gpus 1 --steps 99 --warmup 3 --cfg4-frames 200 --s
 echo "== cfg4 with the peer-memory exchange"
 AOTB_SHARD_XCHG=p2p timeout 400 $TR --master-port 29545 bench.py --gpus 2 --steps 20 --warmup 3 --no-full-clip --cfg4-frames 200 --skip-cpu-baseline 2>&1 | grep -v "$F" | tail -2 | tee gpurun_out/g2_bench_2gpu_p2p.json
 echo "== reference arm under torchrun"
-timeout 300 $TR --master-port 29543 bench.py --impl reference --gpus 2 --steps 4 --warmup 1 2>&1 | grep -v "$F" | tail -1 | cut -c1-400 | tee gpurun_out/g2_bench_ref_2gpu.log
+timeout 300 $TR --master-port 29543 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>&1 | grep -v "$F" | tail -1 | cut -c1-400 | tee gpurun_out/g2_bench_ref_2gpu.log
