@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -45,9 +46,14 @@ struct ChainLayer {                 // device copy of one layer (64-byte aligned
     int in_done, res_done;          // offset of the producing layer's counters in `done`, -1 = ready before the launch
     int in_need, res_need;          // n-tiles per m-tile of the producing layer
     int done_off;                   // this layer's counters
-    int pad0;
+    int splits;                     // split-K factor S of this layer (1 = none)
+    float* scratch;                 // S > 1: raw fp32 partial tiles [S - 1][M][Cout] of splits 0 .. S-2
+    int part_off;                   // S > 1: counters [m-tiles * n-tiles] of published partials
+    int ntn;                        // n-tiles per m-tile
 };
-struct ChainTile { int layer, mt, nt, dep_lo, dep_hi, pad0, pad1, pad2; };
+// k0 / k1: chunk range of this work item; split s of S (s == S - 1 finishes the tile: it adds the partials of the others in
+// split order, so the result does not depend on which CTA finishes first)
+struct ChainTile { int layer, mt, nt, dep_lo, dep_hi, k0, k1, split; };
 
 struct ChainArgs {
     const ChainLayer* layers;
@@ -55,6 +61,7 @@ struct ChainArgs {
     const CUtensorMap* tmaps;       // [2 * nlayers]: Wh, Wl
     int* done;
     int ntiles;
+    unsigned long long* prof;       // diagnostic (AOTB_CHAIN_PROF=1): 4 globaltimer stamps per work item, or null
 };
 
 constexpr int CH_STAGES = 3, CH_THREADS = 448;
@@ -66,11 +73,17 @@ constexpr int CH_STG_BYTES = 4 * 32 * CH_STG_LD * 4;
 
 struct ChRowInfo { int pix_base, iy0, ix0, valid; };
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+// Dependency counters.  Publishing: the 128 epilogue threads meet at a CTA barrier after their stores, then ONE thread does a
+// gpu-scope release-add (the release is cumulative over the writes it has observed through the barrier).  Waiting: ONE thread
+// polls with relaxed loads and issues a single gpu-scope acquire fence once the counters are there, then a CTA barrier hands
+// the data to the other threads.  (A first version fenced in every thread and polled with ld.acquire: at gpu scope each of
+// those invalidates the SM's L1 -- profiles/r02_summary.md, trip 7: 8.7 us to publish a 32 KB tile.)
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -78,11 +91,17 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
 __device__ __forceinline__ void wait_done(const int* done, int lo, int hi, int need) {
     for (int m = lo; m <= hi; ++m) {
         uint32_t spins = 0;
-        while (ld_acquire_gpu(done + m) < need) {
-            __nanosleep(40);
+        while (ld_relaxed_gpu(done + m) < need) {
+            __nanosleep(64);
             if (++spins > (1u << 23)) __trap();
         }
     }
+    fence_acq_rel_gpu();
+}
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ void tma_load_2d_g(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
     asm volatile(
@@ -126,7 +145,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
             const ChainTile t = a.tiles[ti];
             const ChainLayer& L = a.layers[t.layer];
             const float* in = L.in;
-            const int H = L.H, W = L.W, Cin = L.Cin, ldin = L.ldin, KW = L.KW, taps = L.KH * L.KW, nchunks = L.nchunks;
+            const int H = L.H, W = L.W, Cin = L.Cin, ldin = L.ldin, KW = L.KW, taps = L.KH * L.KW;
+            const int kbeg = t.k0, nchunks = t.k1 - t.k0;
             ChRowInfo* ri = rinfo + (seq & 1) * 128;
             if (tid < 128) {
                 const int m = t.mt * 128 + tid;
@@ -139,7 +159,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
                 }
                 ri[tid] = r;
             }
+            if (tid == 0 && a.prof) a.prof[4 * (size_t)ti] = gtime();
             if (tid == 0 && L.in_done >= 0) wait_done(a.done + L.in_done, t.dep_lo, t.dep_hi, L.in_need);
+            if (tid == 0 && a.prof) a.prof[4 * (size_t)ti + 1] = gtime();
             asm volatile("bar.sync 2, 256;" ::: "memory");
             const int cpt = Cin >> 6;                                          // 64-wide chunks per filter tap
             int rowoff[8];                                                     // element offset of the row's pixel, -1 = zero padding
@@ -181,17 +203,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
                 mbar_arrive(&a_full[s]);
             };
             float4 v0[8], v1[8], v2[8];
-            if (nchunks > 0) load_chunk(0, v0);
-            if (nchunks > 1) load_chunk(1, v1);
+            if (nchunks > 0) load_chunk(kbeg, v0);
+            if (nchunks > 1) load_chunk(kbeg + 1, v1);
             for (int it = 0; it < nchunks; it += 3) {
-                if (it + 2 < nchunks) load_chunk(it + 2, v2);
+                if (it + 2 < nchunks) load_chunk(kbeg + it + 2, v2);
                 store_chunk(it, v0);
                 if (it + 1 < nchunks) {
-                    if (it + 3 < nchunks) load_chunk(it + 3, v0);
+                    if (it + 3 < nchunks) load_chunk(kbeg + it + 3, v0);
                     store_chunk(it + 1, v1);
                 }
                 if (it + 2 < nchunks) {
-                    if (it + 4 < nchunks) load_chunk(it + 4, v1);
+                    if (it + 4 < nchunks) load_chunk(kbeg + it + 4, v1);
                     store_chunk(it + 2, v2);
                 }
             }
@@ -199,25 +221,39 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
         }
     } else if (warp < 12) {
         // ======================= epilogue (4 warps: TMEM lane quadrants) =======================
+        // Shared memory is addressed through explicit ld.shared / st.shared and every load of a 32-column step (staging rows,
+        // residual rows, split-K partials) is issued before the first global store: with generic pointers the compiler has to
+        // assume that a store to `out` may alias the staging buffer and serialises load -> store -> load, one L2 round trip per
+        // row (measured: 4 us per 32-column step, profiles/r02_summary.md trip 8).
         const int ew = warp - 8, etid = tid - 256;
-        float* stg = staging + ew * 32 * CH_STG_LD;
+        const uint32_t stg_s = smem_u32(staging + ew * 32 * CH_STG_LD);
         const uint32_t trow = tmem + ((uint32_t)(ew * 32) << 16);
         const int r4 = lane >> 3, c4 = (lane & 7) * 4;          // coalesced phase: 4 rows per instruction, 8 lanes per row
         int seq = 0;
         for (int ti = blockIdx.x; ti < a.ntiles; ti += gridDim.x, ++seq) {
             const ChainTile t = a.tiles[ti];
             const ChainLayer& L = a.layers[t.layer];
-            const int acc = seq & 1, BN = L.BN, M = L.M, act = L.act, ldout = L.ldout, ldres = L.ldres;
-            const float* bias = L.bias;
-            const float* res = L.res;
-            float* out = L.out;
+            const int acc = seq & 1, BN = L.BN, M = L.M, act = L.act, ldout = L.ldout, ldres = L.ldres, S = L.splits, Cout = L.Cout;
+            const int res_done = L.res_done, res_need = L.res_need, done_off = L.done_off;
+            const float* __restrict__ bias = L.bias;
+            const float* __restrict__ res = L.res;
+            const float* __restrict__ scratch = L.scratch;
+            float* __restrict__ out = L.out;
             const int m0 = t.mt * 128 + ew * 32, n0 = t.nt * BN;
-            if (res && L.res_done >= 0) {            // uniform over the 128 epilogue threads
-                if (etid == 0) wait_done(a.done + L.res_done, t.mt, t.mt, L.res_need);
+            const bool last = t.split == S - 1;                  // this work item finishes the tile
+            if (last && res && res_done >= 0) {                  // uniform over the 128 epilogue threads
+                if (etid == 0) wait_done(a.done + res_done, t.mt, t.mt, res_need);
+                asm volatile("bar.sync 3, 128;" ::: "memory");
+            }
+            int* pcount = a.done + L.part_off + t.mt * L.ntn + t.nt;
+            if (last && S > 1) {                                 // the other splits' partial tiles (earlier in program order)
+                if (etid == 0) wait_done(pcount, 0, 0, S - 1);
                 asm volatile("bar.sync 3, 128;" ::: "memory");
             }
             mbar_wait(&acc_full[acc], (seq >> 1) & 1);
             tc_fence_after();
+            if (etid == 0 && a.prof) a.prof[4 * (size_t)ti + 2] = gtime();
+            const size_t plane = (size_t)M * Cout;
             for (int c = 0; c < BN; c += 32) {
                 uint32_t r[32];
                 tmem_ld32(trow + acc * 128 + c, r);
@@ -226,34 +262,77 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
                     tc_fence_before();
                     mbar_arrive(&acc_free[acc]);
                 }
-                float* srow = stg + lane * CH_STG_LD;
+                const uint32_t srow = stg_s + lane * (CH_STG_LD * 4);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(srow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + j * 4), "r"(r[j]), "r"(r[j + 1]),
+                                 "r"(r[j + 2]), "r"(r[j + 3]) : "memory");
                 __syncwarp();
                 const int n = n0 + c + c4;
-                const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 b4 = (last && bias) ? *reinterpret_cast<const float4*>(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int row = it * 4 + r4, m = m0 + row;
-                    float4 o = *reinterpret_cast<const float4*>(stg + row * CH_STG_LD + c4);
-                    if (m < M) {
-                        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-                        if (res) {
-                            const float4 rs = *reinterpret_cast<const float4*>(res + (size_t)m * ldres + n);
-                            o.x += rs.x; o.y += rs.y; o.z += rs.z; o.w += rs.w;
+                for (int hh = 0; hh < 2; ++hh) {     // 16 rows at a time (4 per instruction): all loads first, then the stores
+                    float4 o[4];
+#pragma unroll
+                    for (int it = 0; it < 4; ++it)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[it].x), "=f"(o[it].y), "=f"(o[it].z), "=f"(o[it].w)
+                                     : "r"(stg_s + (((hh * 4 + it) * 4 + r4) * CH_STG_LD + c4) * 4));
+                    if (!last) {
+                        // raw partial accumulator -> scratch[split][m][n] (coalesced), no bias / residual / activation
+                        float* dst = L.scratch + (size_t)t.split * plane;
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int m = m0 + (hh * 4 + it) * 4 + r4;
+                            if (m < M) *reinterpret_cast<float4*>(dst + (size_t)m * Cout + n) = o[it];
                         }
-                        o.x = apply_act(o.x, act); o.y = apply_act(o.y, act);
-                        o.z = apply_act(o.z, act); o.w = apply_act(o.w, act);
-                        *reinterpret_cast<float4*>(out + (size_t)m * ldout + n) = o;
+                    } else {
+                        float4 rs[4];
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int m = m0 + (hh * 4 + it) * 4 + r4;
+                            rs[it] = (res && m < M) ? *reinterpret_cast<const float4*>(res + (size_t)m * ldres + n)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        if (S > 1) {                 // partials of splits 0 .. S-2 first, in split order, then this split's own sum
+                            float4 p[4];
+#pragma unroll
+                            for (int it = 0; it < 4; ++it) {
+                                const int m = m0 + (hh * 4 + it) * 4 + r4;
+                                p[it] = m < M ? *reinterpret_cast<const float4*>(scratch + (size_t)m * Cout + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                            for (int j = 1; j < S - 1; ++j) {
+                                float4 q[4];
+#pragma unroll
+                                for (int it = 0; it < 4; ++it) {
+                                    const int m = m0 + (hh * 4 + it) * 4 + r4;
+                                    q[it] = m < M ? *reinterpret_cast<const float4*>(scratch + (size_t)j * plane + (size_t)m * Cout + n)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+#pragma unroll
+                                for (int it = 0; it < 4; ++it) { p[it].x += q[it].x; p[it].y += q[it].y; p[it].z += q[it].z; p[it].w += q[it].w; }
+                            }
+#pragma unroll
+                            for (int it = 0; it < 4; ++it) {
+                                o[it].x = p[it].x + o[it].x; o[it].y = p[it].y + o[it].y; o[it].z = p[it].z + o[it].z; o[it].w = p[it].w + o[it].w;
+                            }
+                        }
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int m = m0 + (hh * 4 + it) * 4 + r4;
+                            float4 v = o[it];
+                            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                            v.x += rs[it].x; v.y += rs[it].y; v.z += rs[it].z; v.w += rs[it].w;
+                            v.x = apply_act(v.x, act); v.y = apply_act(v.y, act);
+                            v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+                            if (m < M) *reinterpret_cast<float4*>(out + (size_t)m * ldout + n) = v;
+                        }
                     }
                 }
                 __syncwarp();
             }
-            __threadfence();                         // this thread's stores are visible at gpu scope ...
-            asm volatile("bar.sync 3, 128;" ::: "memory");
-            if (etid == 0) red_release_gpu_add(a.done + L.done_off + t.mt, 1);        // ... before the tile is published
+            asm volatile("bar.sync 3, 128;" ::: "memory");       // every epilogue thread's stores happen before ...
+            if (etid == 0) red_release_gpu_add(last ? a.done + done_off + t.mt : pcount, 1);   // ... the gpu-scope release
+            if (etid == 0 && a.prof) a.prof[4 * (size_t)ti + 3] = gtime();
         }
     } else if (warp == 12) {
         // ======================= weight TMA producer =======================
@@ -263,14 +342,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
                 const ChainTile t = a.tiles[ti];
                 const ChainLayer& L = a.layers[t.layer];
                 const CUtensorMap* th = a.tmaps + 2 * t.layer;
-                const int nchunks = L.nchunks, BN = L.BN, n0 = t.nt * BN;
+                const int nchunks = t.k1 - t.k0, BN = L.BN, n0 = t.nt * BN;
                 for (int kc = 0; kc < nchunks; ++kc) {
                     const int g = g0 + kc, s = g % CH_STAGES;
                     if (g >= CH_STAGES) mbar_wait(&s_free[s], ((g / CH_STAGES) - 1) & 1);
                     uint8_t* Bh = smem + s * CH_STAGE_BYTES + 2 * CH_A_BYTES;
                     mbar_arrive_expect_tx(&b_full[s], 2 * BN * 128);
-                    tma_load_2d_g(Bh, th, &b_full[s], kc * 64, n0);
-                    tma_load_2d_g(Bh + CH_B_BYTES, th + 1, &b_full[s], kc * 64, n0);
+                    tma_load_2d_g(Bh, th, &b_full[s], (t.k0 + kc) * 64, n0);
+                    tma_load_2d_g(Bh + CH_B_BYTES, th + 1, &b_full[s], (t.k0 + kc) * 64, n0);
                 }
                 g0 += nchunks;
             }
@@ -287,7 +366,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
             for (int ti = blockIdx.x; ti < a.ntiles; ti += gridDim.x, ++seq) {
                 const ChainTile t = a.tiles[ti];
                 const ChainLayer& L = a.layers[t.layer];
-                const int nchunks = L.nchunks, acc = seq & 1;
+                const int nchunks = t.k1 - t.k0, acc = seq & 1;
                 const uint32_t idesc = L.BN == 128 ? IDESC128 : IDESC64;
                 const uint32_t d = tmem + acc * 128;
                 if (seq >= 2) { mbar_wait(&acc_free[acc], ((seq >> 1) - 1) & 1); tc_fence_after(); }
@@ -345,7 +424,8 @@ struct ChainPlan {
     std::vector<tc::ChainLayer> layers;
     std::vector<tc::ChainTile> tiles;
     int ndone = 0;
-    size_t off_tiles = 0, off_tmaps = 0, off_done = 0, bytes = 0;
+    std::vector<size_t> scratch_floats;          // per layer: floats of its split-K scratch (0 = none)
+    size_t off_tiles = 0, off_tmaps = 0, off_done = 0, off_prof = 0, off_scratch = 0, bytes = 0;
 };
 
 int plan_chain(const aotb_chain_layer* ls, int n, ChainPlan& P) {
@@ -372,6 +452,19 @@ int plan_chain(const aotb_chain_layer* ls, int n, ChainPlan& P) {
         ntn[i] = l.Cout / d.BN;
         d.done_off = P.ndone;
         P.ndone += mtiles[i];
+        // split-K: layers with few tiles and a long K loop (the 31x54 maps of ResNet layer3) would leave most SMs idle and put
+        // 20+ us of chunks on the dependency chain of every block: cut K into S work items of >= 8 chunks while the layer has
+        // fewer than ~one work item per SM
+        d.ntn = ntn[i];
+        d.splits = 1;
+        while (d.splits < 4 && mtiles[i] * ntn[i] * d.splits < 120 && d.nchunks / (d.splits + 1) >= 8) ++d.splits;
+        d.part_off = -1;
+        d.scratch = nullptr;
+        if (d.splits > 1) {
+            d.part_off = P.ndone;
+            P.ndone += mtiles[i] * ntn[i];
+        }
+        P.scratch_floats.push_back(d.splits > 1 ? (size_t)(d.splits - 1) * d.M * d.Cout : 0);
         d.in_done = d.res_done = -1;
         d.in_need = d.res_need = 0;
         if (l.in_layer >= 0) {
@@ -396,13 +489,22 @@ int plan_chain(const aotb_chain_layer* ls, int n, ChainPlan& P) {
                 const int iy0 = std::max(0, oy0 * d.stride - d.pad), iy1 = std::min(d.H - 1, oy1 * d.stride - d.pad + d.KH - 1);
                 lo = (iy0 * d.W) / 128; hi = (iy1 * d.W + d.W - 1) / 128;
             }
-            for (int nt = 0; nt < ntn[i]; ++nt) P.tiles.push_back(tc::ChainTile{i, mt, nt, lo, hi, 0, 0, 0});
+            for (int nt = 0; nt < ntn[i]; ++nt)
+                for (int sp = 0; sp < d.splits; ++sp) {             // split sp covers chunks [k0, k1); the last one finishes the tile
+                    const int per = cdiv(d.nchunks, d.splits);
+                    const int k0 = sp * per, k1 = std::min(d.nchunks, k0 + per);
+                    P.tiles.push_back(tc::ChainTile{i, mt, nt, lo, hi, k0, k1, sp});
+                }
         }
     }
     P.off_tiles = tc::align_up(P.layers.size() * sizeof(tc::ChainLayer), 256);
     P.off_tmaps = tc::align_up(P.off_tiles + P.tiles.size() * sizeof(tc::ChainTile), 256);
     P.off_done = tc::align_up(P.off_tmaps + 2 * (size_t)n * sizeof(CUtensorMap), 256);
-    P.bytes = P.off_done + tc::align_up((size_t)P.ndone * sizeof(int), 256);
+    P.off_prof = P.off_done + tc::align_up((size_t)P.ndone * sizeof(int), 256);
+    P.off_scratch = P.off_prof + tc::align_up(P.tiles.size() * 4 * sizeof(unsigned long long), 256);
+    size_t fl = 0;
+    for (size_t v : P.scratch_floats) fl += tc::align_up(v, 64);
+    P.bytes = P.off_scratch + fl * sizeof(float);
     return AOTB_OK;
 }
 
@@ -443,23 +545,25 @@ extern "C" int aotb_conv_chain_plan(const void* layers, int nlayers, size_t* pro
     return AOTB_OK;
 }
 
-// Host-only view of the tile program (tests / diagnostics): 5 ints per tile (layer, m-tile, n-tile, dep_lo, dep_hi) and per layer
-// (M, BN, counters offset, producer counters offset or -1, residual counters offset or -1, in_need, res_need).
-extern "C" int aotb_conv_chain_dump(const void* layers, int nlayers, int* tiles5, int max_tiles, int* layers7) {
-    AOTB_REQUIRE(layers && nlayers > 0 && tiles5 && layers7, "aotb_conv_chain_dump: bad args");
+// Host-only view of the tile program (tests / diagnostics): 8 ints per work item (layer, m-tile, n-tile, dep_lo, dep_hi, k0, k1,
+// split) and 10 per layer (M, BN, counters offset, producer counters offset or -1, residual counters offset or -1, in_need,
+// res_need, splits, partial counters offset or -1, chunks).
+extern "C" int aotb_conv_chain_dump(const void* layers, int nlayers, int* tiles8, int max_tiles, int* layers10) {
+    AOTB_REQUIRE(layers && nlayers > 0 && tiles8 && layers10, "aotb_conv_chain_dump: bad args");
     ChainPlan P;
     int rc = plan_chain((const aotb_chain_layer*)layers, nlayers, P);
     if (rc != AOTB_OK) return rc;
     AOTB_REQUIRE((int)P.tiles.size() <= max_tiles, "aotb_conv_chain_dump: %zu tiles exceed the buffer", P.tiles.size());
     for (size_t i = 0; i < P.tiles.size(); ++i) {
         const tc::ChainTile& t = P.tiles[i];
-        int* o = tiles5 + 5 * i;
-        o[0] = t.layer; o[1] = t.mt; o[2] = t.nt; o[3] = t.dep_lo; o[4] = t.dep_hi;
+        int* o = tiles8 + 8 * i;
+        o[0] = t.layer; o[1] = t.mt; o[2] = t.nt; o[3] = t.dep_lo; o[4] = t.dep_hi; o[5] = t.k0; o[6] = t.k1; o[7] = t.split;
     }
     for (int i = 0; i < nlayers; ++i) {
         const tc::ChainLayer& d = P.layers[i];
-        int* o = layers7 + 7 * i;
+        int* o = layers10 + 10 * i;
         o[0] = d.M; o[1] = d.BN; o[2] = d.done_off; o[3] = d.in_done; o[4] = d.res_done; o[5] = d.in_need; o[6] = d.res_need;
+        o[7] = d.splits; o[8] = d.part_off; o[9] = d.nchunks;
     }
     return AOTB_OK;
 }
@@ -473,7 +577,14 @@ extern "C" int aotb_conv_chain_build(const void* layers, int nlayers, void* prog
     int rc = plan_chain(ls, nlayers, P);
     if (rc != AOTB_OK) return rc;
     AOTB_REQUIRE(program_bytes >= P.bytes, "aotb_conv_chain_build: program buffer too small (%zu < %zu)", program_bytes, P.bytes);
-    std::vector<uint8_t> host(P.bytes, 0);
+    {
+        size_t fl = 0;
+        for (int i = 0; i < nlayers; ++i) {
+            if (P.scratch_floats[i]) P.layers[i].scratch = (float*)((uint8_t*)program + P.off_scratch) + fl;
+            fl += tc::align_up(P.scratch_floats[i], 64);
+        }
+    }
+    std::vector<uint8_t> host(P.off_scratch, 0);               // the scratch region itself is never initialised
     memcpy(host.data(), P.layers.data(), P.layers.size() * sizeof(tc::ChainLayer));
     memcpy(host.data() + P.off_tiles, P.tiles.data(), P.tiles.size() * sizeof(tc::ChainTile));
     for (int i = 0; i < nlayers; ++i) {
@@ -485,13 +596,21 @@ extern "C" int aotb_conv_chain_build(const void* layers, int nlayers, void* prog
         memcpy(host.data() + P.off_tmaps + (2 * (size_t)i + 1) * sizeof(CUtensorMap), &tl, sizeof(CUtensorMap));
     }
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemcpyAsync(program, host.data(), P.bytes, cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(program, host.data(), P.off_scratch, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         set_error("aotb_conv_chain_build: %s", cudaGetErrorString(e));
         return AOTB_ERR_CUDA;
     }
     return AOTB_OK;
+}
+
+// Byte offset of the diagnostic time stamps (4 x uint64 per work item, written when AOTB_CHAIN_PROF=1) inside a program buffer.
+extern "C" size_t aotb_conv_chain_prof_offset(int nlayers, int ntiles, int ncounters) {
+    const size_t off_tiles = tc::align_up((size_t)nlayers * sizeof(tc::ChainLayer), 256);
+    const size_t off_tmaps = tc::align_up(off_tiles + (size_t)ntiles * sizeof(tc::ChainTile), 256);
+    const size_t off_done = tc::align_up(off_tmaps + 2 * (size_t)nlayers * sizeof(CUtensorMap), 256);
+    return off_done + tc::align_up((size_t)ncounters * sizeof(int), 256);
 }
 
 // Run a built program: clears the dependency counters and launches the persistent kernel (graph-capturable).
@@ -507,6 +626,9 @@ extern "C" int aotb_conv_chain_run(void* program, int nlayers, int ntiles, int n
     a.tmaps = (const CUtensorMap*)(base + off_tmaps);
     a.done = (int*)(base + off_done);
     a.ntiles = ntiles;
+    static int prof = -1;
+    if (prof < 0) { const char* e = getenv("AOTB_CHAIN_PROF"); prof = (e && atoi(e)) ? 1 : 0; }
+    a.prof = prof ? (unsigned long long*)(base + off_done + tc::align_up((size_t)ncounters * sizeof(int), 256)) : nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int smem = tc::CH_STAGES * tc::CH_STAGE_BYTES + tc::CH_STG_BYTES + 256 * (int)sizeof(tc::ChRowInfo) + 16 * 8 + 16 + 1024;
     static bool configured = false;

@@ -135,18 +135,19 @@ def conv_chain_layers(layers):
 
 
 def conv_chain_dump(layers):
-    """Host-only: -> (tiles [n, 5] = layer, m-tile, n-tile, dep_lo, dep_hi; layer table [L, 7])."""
+    """Host-only: -> (work items [n, 8] = layer, m-tile, n-tile, dep_lo, dep_hi, k0, k1, split; layer table [L, 10] = M, BN,
+    counters offset, producer / residual counters offset (-1: none), in_need, res_need, splits, partial counters offset, chunks)."""
     import ctypes
     arr = layers if not isinstance(layers, list) else conv_chain_layers(layers)
     n = len(arr)
     nbytes, ntiles, ncnt = ctypes.c_size_t(), ctypes.c_int(), ctypes.c_int()
     check(lib().aotb_conv_chain_plan(ctypes.addressof(arr), n, ctypes.addressof(nbytes), ctypes.addressof(ntiles),
                                      ctypes.addressof(ncnt)), "aotb_conv_chain_plan")
-    tiles = (ctypes.c_int * (5 * ntiles.value))()
-    lay = (ctypes.c_int * (7 * n))()
+    tiles = (ctypes.c_int * (8 * ntiles.value))()
+    lay = (ctypes.c_int * (10 * n))()
     check(lib().aotb_conv_chain_dump(ctypes.addressof(arr), n, ctypes.addressof(tiles), ntiles.value, ctypes.addressof(lay)),
           "aotb_conv_chain_dump")
-    return [list(tiles[5 * i:5 * i + 5]) for i in range(ntiles.value)], [list(lay[7 * i:7 * i + 7]) for i in range(n)]
+    return [list(tiles[8 * i:8 * i + 8]) for i in range(ntiles.value)], [list(lay[10 * i:10 * i + 10]) for i in range(n)]
 
 
 class ConvChain:
@@ -168,6 +169,12 @@ class ConvChain:
 
     def run(self, stream=None):
         check(lib().aotb_conv_chain_run(self._base, self.n, self.ntiles, self.ncounters, _st(stream)), "aotb_conv_chain_run")
+
+    def profile(self):
+        """AOTB_CHAIN_PROF=1: per work item [picked up, inputs complete, accumulator complete, published] in ns (globaltimer)."""
+        off = lib().aotb_conv_chain_prof_offset(self.n, self.ntiles, self.ncounters) + (self._base - self.program.data_ptr())
+        torch.cuda.synchronize()
+        return self.program[off:off + self.ntiles * 32].view(torch.int64).view(self.ntiles, 4).cpu()
 
 
 def conv2d_tc(x, wh, wl, bias, out, res=None, KH=1, KW=1, stride=1, pad=0, act=ACT_NONE, stream=None):

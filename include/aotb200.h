@@ -176,7 +176,9 @@ int aotb_separate_labels_f32(const float* mask, int n_engines, int max_obj, floa
  * the launch).  Every output buffer must be written by exactly one layer of the chain (the SMs' L1 caches are not coherent:
  * no address may change its value twice inside one launch).  aotb_conv_chain_plan sizes the device-resident program,
  * aotb_conv_chain_build writes it (once per geometry, outside stream capture), aotb_conv_chain_run clears the dependency
- * counters and launches the kernel (capturable); aotb_conv_chain_dump exposes the tile program to host-side tests. */
+ * counters and launches the kernel (capturable); aotb_conv_chain_dump exposes the tile program to host-side tests.  Layers with
+ * few tiles and a long K loop are cut into up to 4 split-K work items; the item that holds the last K range adds the others'
+ * partial tiles (kept in a scratch area of the program buffer) in split order, so results are deterministic. */
 typedef struct aotb_chain_layer {
     const float* in;
     const void* wh;
@@ -187,9 +189,10 @@ typedef struct aotb_chain_layer {
     int H, W, Cin, ldin, Cout, ldout, ldres, KH, KW, stride, pad, act, in_layer, res_layer;
 } aotb_chain_layer;
 int aotb_conv_chain_plan(const void* layers, int nlayers, size_t* program_bytes, int* ntiles, int* ncounters);
-int aotb_conv_chain_dump(const void* layers, int nlayers, int* tiles5, int max_tiles, int* layers7);
+int aotb_conv_chain_dump(const void* layers, int nlayers, int* tiles8, int max_tiles, int* layers10);
 int aotb_conv_chain_build(const void* layers, int nlayers, void* program, size_t program_bytes, void* stream);
 int aotb_conv_chain_run(void* program, int nlayers, int ntiles, int ncounters, void* stream);
+size_t aotb_conv_chain_prof_offset(int nlayers, int ntiles, int ncounters);
 /* Frame input side: dataloaders/eval_datasets.py:60-61 + dataloaders/video_transforms.py:594-715 (MultiRestrictSize's
  * cv2.resize(INTER_CUBIC) of the float image, MultiToTensor's / 255, - mean, / std, HWC -> CHW) on the uint8 frame in one pass.
  * img uint8 [H][W][3]; ix / cx [Wo][4] and iy / cy [Ho][4] = clamped tap indices and Keys-cubic (A = -0.75) weights per output
