@@ -10,12 +10,40 @@ import torch.multiprocessing as mp
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+class P:
+    """Reference formulation of the two ways the path shards, used only to check the arithmetic of the exact merge
+    under gloo: round-robin ownership of clips / memory frames, all-gather of (O, m, l), max over ranks of the device time."""
+
+    @staticmethod
+    def partition_videos(num_videos, rank, world):
+        return list(range(rank, num_videos, world))
+
+    @staticmethod
+    def local_frames(num_mem_frames, rank, world):
+        return [f for f in range(num_mem_frames) if f % world == rank]
+
+    @staticmethod
+    def gather_partials(dist, Opart, Mpart, Lpart):
+        world = dist.get_world_size()
+        outs = []
+        for t in (Opart, Mpart, Lpart):
+            buf = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(buf, t.contiguous())
+            outs.append(torch.stack(buf, dim=0))
+        return outs
+
+    @staticmethod
+    def reduce_max_ms(dist, ms, device):
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
 def _worker(rank, world, port, ret):
     sys.path.insert(0, REPO)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from aot_benchmark_b200 import parallel as P
     torch.manual_seed(0)                      # replicated inputs on every rank
     H, d, N, frames, per = 8, 32, 50, 5, 40
     Q = torch.randn(N, H * d) * 3
