@@ -235,22 +235,27 @@ __global__ void attn_merge_kernel(const float* __restrict__ Opart, const float* 
                                   const float* __restrict__ Lpart, float* __restrict__ O, int R, int N, int H,
                                   int dv, int ldo) {
     pdl_sync();
-    // Opart [R][N][H*dv], Mpart/Lpart [R][H][N]
-    const size_t total = (size_t)N * H * dv;
+    // Opart [R][N][H*dv], Mpart/Lpart [R][H][N]; one thread per 4 channels (dv % 4 == 0): the weights of a (query, head) are
+    // computed once per float4 instead of once per scalar (same arithmetic and order per element as the scalar form)
+    const int dv4 = dv >> 2;
+    const size_t total = (size_t)N * H * dv4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = i % dv;
-        const int h = (i / dv) % H;
-        const int q = i / ((size_t)dv * H);
+        const int c = (i % dv4) * 4;
+        const int h = (i / dv4) % H;
+        const int q = i / ((size_t)dv4 * H);
         float m = -INFINITY;
         for (int r = 0; r < R; ++r) m = fmaxf(m, Mpart[((size_t)r * H + h) * N + q]);
-        float num = 0.f, den = 0.f;
+        float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+        float den = 0.f;
         for (int r = 0; r < R; ++r) {
             const float mr = Mpart[((size_t)r * H + h) * N + q];
             const float w = (mr == -INFINITY) ? 0.f : expf(mr - m);
-            num += w * Opart[((size_t)r * N + q) * H * dv + (size_t)h * dv + c];
+            const float4 o = *reinterpret_cast<const float4*>(Opart + ((size_t)r * N + q) * H * dv + (size_t)h * dv + c);
+            num.x += w * o.x; num.y += w * o.y; num.z += w * o.z; num.w += w * o.w;
             den += w * Lpart[((size_t)r * H + h) * N + q];
         }
-        O[(size_t)q * ldo + (size_t)h * dv + c] = num / den;
+        *reinterpret_cast<float4*>(O + (size_t)q * ldo + (size_t)h * dv + c) =
+            make_float4(num.x / den, num.y / den, num.z / den, num.w / den);
     }
 }
 }  // namespace aotb
@@ -266,32 +271,49 @@ struct MergePeers { const float* O[8]; const float* M[8]; const float* L[8]; };
 __global__ void attn_merge_peers_kernel(const MergePeers p, float* __restrict__ O, int R, int S, int N, int H, int dv,
                                         int ldo) {
     pdl_sync();
-    const size_t total = (size_t)N * H * dv;
+    const int dv4 = dv >> 2;                       // one thread per 4 channels, as in attn_merge_kernel
+    const size_t total = (size_t)N * H * dv4;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = i % dv;
-        const int h = (i / dv) % H;
-        const int q = i / ((size_t)dv * H);
+        const int c = (i % dv4) * 4;
+        const int h = (i / dv4) % H;
+        const int q = i / ((size_t)dv4 * H);
         float m = -INFINITY;
         for (int r = 0; r < R; ++r)
             for (int s = 0; s < S; ++s) m = fmaxf(m, p.M[r][((size_t)s * H + h) * N + q]);
-        float num = 0.f, den = 0.f;
+        float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+        float den = 0.f;
         for (int r = 0; r < R; ++r)
             for (int s = 0; s < S; ++s) {
                 const float mr = p.M[r][((size_t)s * H + h) * N + q];
                 const float w = (mr == -INFINITY) ? 0.f : expf(mr - m);
-                num += w * p.O[r][((size_t)s * N + q) * H * dv + (size_t)h * dv + c];
+                const float4 o = *reinterpret_cast<const float4*>(p.O[r] + ((size_t)s * N + q) * H * dv + (size_t)h * dv + c);
+                num.x += w * o.x; num.y += w * o.y; num.z += w * o.z; num.w += w * o.w;
                 den += w * p.L[r][((size_t)s * H + h) * N + q];
             }
-        O[(size_t)q * ldo + (size_t)h * dv + c] = num / den;
+        *reinterpret_cast<float4*>(O + (size_t)q * ldo + (size_t)h * dv + c) =
+            make_float4(num.x / den, num.y / den, num.z / den, num.w / den);
     }
 }
 }  // namespace aotb
 
-// Oparts / Mparts / Lparts: HOST arrays of `ranks` device pointers (local buffer + peer mappings), ranks <= 8.
+using namespace aotb;
+
+extern "C" int aotb_attn_merge_f32(const float* Opart, const float* Mpart, const float* Lpart, float* O, int R,
+                                   int N, int H, int d_v, int ldo, void* stream) {
+    AOTB_REQUIRE(Opart && Mpart && Lpart && O && R > 0 && N > 0 && H > 0 && d_v > 0, "aotb_attn_merge_f32: bad args");
+    AOTB_REQUIRE(d_v % 4 == 0 && ldo % 4 == 0 && ((uintptr_t)Opart | (uintptr_t)O) % 16 == 0, "aotb_attn_merge_f32: d_v, ldo %% 4, 16-byte alignment");
+    const size_t total = (size_t)N * H * (d_v / 4);
+    int g = (int)((total + 255) / 256);
+    if (g > 148 * 8) g = 148 * 8;
+    launch(attn_merge_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, Opart, Mpart, Lpart, O, R, N, H, d_v, ldo);
+    return check_launch("aotb_attn_merge_f32");
+}
+
 extern "C" int aotb_attn_merge_peers_f32(const void* const* Oparts, const void* const* Mparts, const void* const* Lparts,
                                          int ranks, int splits, float* O, int N, int H, int d_v, int ldo, void* stream) {
     AOTB_REQUIRE(Oparts && Mparts && Lparts && O && ranks > 0 && ranks <= 8 && splits > 0 && N > 0 && H > 0 && d_v > 0,
                  "aotb_attn_merge_peers_f32: bad args (at most 8 ranks)");
+    AOTB_REQUIRE(d_v % 4 == 0 && ldo % 4 == 0, "aotb_attn_merge_peers_f32: d_v and ldo must be multiples of 4");
     MergePeers p;
     for (int r = 0; r < 8; ++r) {
         p.O[r] = r < ranks ? (const float*)Oparts[r] : nullptr;
@@ -299,19 +321,9 @@ extern "C" int aotb_attn_merge_peers_f32(const void* const* Oparts, const void* 
         p.L[r] = r < ranks ? (const float*)Lparts[r] : nullptr;
         AOTB_REQUIRE(r >= ranks || (p.O[r] && p.M[r] && p.L[r]), "aotb_attn_merge_peers_f32: null peer pointer");
     }
-    const size_t total = (size_t)N * H * d_v;
+    const size_t total = (size_t)N * H * (d_v / 4);
     int g = (int)((total + 255) / 256);
     if (g > 148 * 8) g = 148 * 8;
     launch(attn_merge_peers_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, p, O, ranks, splits, N, H, d_v, ldo);
     return check_launch("aotb_attn_merge_peers_f32");
-}
-
-extern "C" int aotb_attn_merge_f32(const float* Opart, const float* Mpart, const float* Lpart, float* O, int R,
-                                   int N, int H, int d_v, int ldo, void* stream) {
-    AOTB_REQUIRE(Opart && Mpart && Lpart && O && R > 0 && N > 0 && H > 0 && d_v > 0, "aotb_attn_merge_f32: bad args");
-    const size_t total = (size_t)N * H * d_v;
-    int g = (int)((total + 255) / 256);
-    if (g > 148 * 8) g = 148 * 8;
-    launch(attn_merge_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, Opart, Mpart, Lpart, O, R, N, H, d_v, ldo);
-    return check_launch("aotb_attn_merge_f32");
 }

@@ -190,14 +190,14 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             for (int j = 0; j < T; ++j) {
                 const int s = j % STAGES;
                 for (int i = 0; i < 2; ++i) {
-                    mbar_wait_cp(&B->p_full[i], j & 1, a.spin & 1);
+                    mbar_wait_cp(&B->p_full[i], j & 1, a.spin);
                     tc_fence_after();
-                    if (!(a.spin & 32)) issue_PV(i, s, j > 0 ? 1u : 0u);       // (spin >> 4: diagnostic knock-outs, timing only)
+                    issue_PV(i, s, j > 0 ? 1u : 0u);
                     if (i == 1) mma_commit(&B->kv_free[s]);
                     if (j + 1 < T) {
                         const int s2 = (j + 1) % STAGES;
-                        if (i == 0) { mbar_wait_cp(&B->kv_full[s2], ((j + 1) / STAGES) & 1, a.spin & 1); tc_fence_after(); }
-                        if (!(a.spin & 256)) issue_S(i, s2);
+                        if (i == 0) { mbar_wait_cp(&B->kv_full[s2], ((j + 1) / STAGES) & 1, a.spin); tc_fence_after(); }
+                        issue_S(i, s2);
                         mma_commit(&B->s_full[i]);
                     } else {
                         mma_commit(&B->o_final[i]);
@@ -354,17 +354,12 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 const uint32_t tO = tmem + lane_addr + 256 + i * 64 + qt * 16;  // its 16 of the 64 O' columns
                 const uint32_t tPl = tmem + lane_addr + 384 + i * 64 + qt * 16;
                 const bool dump = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i == 0;
-                mbar_wait_cp(&B->s_full[i], j & 1, a.spin & 1);
+                mbar_wait_cp(&B->s_full[i], j & 1, a.spin);
                 tc_fence_after();
                 const int key0 = (tb + j) * BN + qt * 32;
                 uint32_t sr[32];
-                if (!(a.spin & 128)) {
-                    tmem_ld32(tS, sr);
-                    tmem_wait_ld();
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) sr[k] = __float_as_uint((float)((row * 7 + k * 3 + j) & 15));
-                }
+                tmem_ld32(tS, sr);
+                tmem_wait_ld();
                 if (dump && j == 0) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) a.dbg[row * 128 + qt * 32 + k] = __uint_as_float(sr[k]);
@@ -402,27 +397,38 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 }
                 m_used[i] = m_new;
                 const float neg = m_new * LOG2E;
-                // p = 2^(s*log2e - m*log2e), partial row sum, fp16 hi / lo split, back into TMEM
+                // p = 2^(s*log2e - m*log2e) two scores per FFMA2, packed partial row sums (FADD2); fp16 split of P: hi = p
+                // truncated to 11 significant bits (one LOP3; exactly representable in fp16 for p >= 2^-14), lo = p - hi exact
+                // in fp32 -- no fp16 -> fp32 unpack: 9.5 instead of 14 instructions per score pair
                 uint32_t ph[16], pl[16];
-                float s0 = 0.f, s1 = 0.f;
+                const float negs = -neg;
+                const uint64_t l2e2 = pk2(LOG2E, LOG2E), neg2 = pk2(negs, negs);
+                uint64_t ls = pk2(0.f, 0.f);
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
-                    const float a0 = fmaf(__uint_as_float(sr[2 * t]), LOG2E, -neg), a1 = fmaf(__uint_as_float(sr[2 * t + 1]), LOG2E, -neg);
-                    const float p0 = (a.spin & 16) ? a0 * 1e-3f : ex2(a0);
-                    const float p1 = (a.spin & 16) ? a1 * 1e-3f : ex2(a1);
-                    s0 += p0; s1 += p1;
-                    const __half2 hi = __floats2half2_rn(p0, p1);
-                    ph[t] = *reinterpret_cast<const uint32_t*>(&hi);
+                    float a0, a1;
+                    upk2(fma2(pk2(__uint_as_float(sr[2 * t]), __uint_as_float(sr[2 * t + 1])), l2e2, neg2), a0, a1);
+                    const float p0 = ex2(a0), p1 = ex2(a1);
+                    const uint64_t p2 = pk2(p0, p1);
+                    ls = add2(ls, p2);
                     if (EXACT) {
-                        const __half2 lo = __floats2half2_rn(p0 - __low2float(hi), p1 - __high2float(hi));
-                        pl[t] = *reinterpret_cast<const uint32_t*>(&lo);
+                        const float h0 = __uint_as_float(__float_as_uint(p0) & 0xFFFFE000u);
+                        const float h1 = __uint_as_float(__float_as_uint(p1) & 0xFFFFE000u);
+                        ph[t] = cvt_h2(h0, h1);
+                        float r0, r1;
+                        upk2(add2(p2, pk2(-h0, -h1)), r0, r1);
+                        pl[t] = cvt_h2(r0, r1);
+                    } else {
+                        ph[t] = cvt_h2(p0, p1);
                     }
                 }
-                l0[i] += s0; l1[i] += s1;
-                if (!(a.spin & 64) || (ph[0] == 0x12345678u && pl[1] == 0x9abcdef0u)) {
-                    tmem_st16(tS, ph);
-                    if (EXACT) tmem_st16(tPl, pl);
+                {
+                    float s0, s1;
+                    upk2(ls, s0, s1);
+                    l0[i] += s0; l1[i] += s1;
                 }
+                tmem_st16(tS, ph);
+                if (EXACT) tmem_st16(tPl, pl);
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(&B->p_full[i]);
@@ -875,12 +881,6 @@ extern "C" int aotb_lt_attn_tc_f16x2(const void* Qp, int Nq_cap, const void* Kp,
     tc::LtArgs a;
     a.N = N; a.Tk = Tk; a.Tk_dev = Tk_dev; a.H = H; a.O = O; a.ldo = ldo;
     a.Opart = Opart; a.Mpart = Mpart; a.Lpart = Lpart; a.splits = splits; a.exact = exact & 1; a.spin = (exact >> 2) & 1; a.dbg = dbg;
-    {   // diagnostic knock-outs of the default layout (timing studies only): AOTB_LT_KNOCK bits 1 no ex2, 2 no PV MMAs, 4 no P
-        // write-back, 8 no score read from TMEM, 16 no S MMAs after the first tile
-        static int knock = -1;
-        if (knock < 0) { const char* e = getenv("AOTB_LT_KNOCK"); knock = e ? atoi(e) : 0; }
-        a.spin |= knock << 4;
-    }
     dim3 grid(cdiv(N, 2 * tc::BM), H, splits);
     const dim3 block(tc::NTHREADS);
     cudaStream_t st = (cudaStream_t)stream;

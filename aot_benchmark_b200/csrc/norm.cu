@@ -97,16 +97,30 @@ __global__ void groupnorm_apply_kernel(const float* __restrict__ x, int ldx, con
     pdl_sync();
     extern __shared__ float stat[];  // [G][2] mean, rstd for this batch element
     const int b = blockIdx.y;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        const double* pp = partial + ((size_t)b * G + g) * GN_CHUNKS * 2;
+    // 8 threads per group: thread `sub` sums chunks [8 sub, 8 sub + 8) in order, the 8 sub-sums are combined by a fixed xor
+    // tree (deterministic; the same in every block).  A single thread per group walking all 64 double partials -- the first
+    // version -- put ~20 k cycles of dependent L2 loads in front of every block (19.6 us per launch for 14 MB of traffic).
+    for (int g0 = 0; g0 < G; g0 += blockDim.x / 8) {
+        const int g = g0 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
         double s = 0, q = 0;
-        for (int c = 0; c < GN_CHUNKS; ++c) { s += pp[2 * c]; q += pp[2 * c + 1]; }
-        const double n = (double)P * Cg;
-        const double mean = s / n;
-        double var = q / n - mean * mean;
-        if (var < 0) var = 0;
-        stat[2 * g] = (float)mean;
-        stat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+        if (g < G) {
+            const double* pp = partial + (((size_t)b * G + g) * GN_CHUNKS + sub * (GN_CHUNKS / 8)) * 2;
+#pragma unroll
+            for (int c = 0; c < GN_CHUNKS / 8; ++c) { s += pp[2 * c]; q += pp[2 * c + 1]; }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (g < G && sub == 0) {
+            const double n = (double)P * Cg;
+            const double mean = s / n;
+            double var = q / n - mean * mean;
+            if (var < 0) var = 0;
+            stat[2 * g] = (float)mean;
+            stat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+        }
     }
     __syncthreads();
     const int C4 = C >> 2;
