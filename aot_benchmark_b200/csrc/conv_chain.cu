@@ -62,6 +62,8 @@ struct ChainArgs {
     int* done;
     int ntiles;
     unsigned long long* prof;       // diagnostic (AOTB_CHAIN_PROF=1): 4 globaltimer stamps per work item, or null
+    int knock;                      // diagnostic (AOTB_CHAIN_KNOCK, timing only, results wrong): 1 no output stores, 2 no TMEM read,
+                                    // 4 relaxed instead of release publish, 8 no bias / residual / partial loads
 };
 
 constexpr int CH_STAGES = 3, CH_THREADS = 448;
@@ -256,8 +258,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
             const size_t plane = (size_t)M * Cout;
             for (int c = 0; c < BN; c += 32) {
                 uint32_t r[32];
-                tmem_ld32(trow + acc * 128 + c, r);
-                tmem_wait_ld();
+                if (!(a.knock & 2)) {
+                    tmem_ld32(trow + acc * 128 + c, r);
+                    tmem_wait_ld();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = (uint32_t)(lane + j);
+                }
                 if (c + 32 >= BN) {                  // the accumulator has been read completely: hand it back to the MMA warp
                     tc_fence_before();
                     mbar_arrive(&acc_free[acc]);
@@ -269,7 +276,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
                                  "r"(r[j + 2]), "r"(r[j + 3]) : "memory");
                 __syncwarp();
                 const int n = n0 + c + c4;
-                const float4 b4 = (last && bias) ? *reinterpret_cast<const float4*>(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool noload = a.knock & 8;
+                const float4 b4 = (last && bias && !noload) ? *reinterpret_cast<const float4*>(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {     // 16 rows at a time (4 per instruction): all loads first, then the stores
                     float4 o[4];
@@ -283,17 +291,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
 #pragma unroll
                         for (int it = 0; it < 4; ++it) {
                             const int m = m0 + (hh * 4 + it) * 4 + r4;
-                            if (m < M) *reinterpret_cast<float4*>(dst + (size_t)m * Cout + n) = o[it];
+                            if (m < M && !(a.knock & 1)) *reinterpret_cast<float4*>(dst + (size_t)m * Cout + n) = o[it];
                         }
                     } else {
                         float4 rs[4];
 #pragma unroll
                         for (int it = 0; it < 4; ++it) {
                             const int m = m0 + (hh * 4 + it) * 4 + r4;
-                            rs[it] = (res && m < M) ? *reinterpret_cast<const float4*>(res + (size_t)m * ldres + n)
+                            rs[it] = (res && m < M && !noload) ? *reinterpret_cast<const float4*>(res + (size_t)m * ldres + n)
                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
-                        if (S > 1) {                 // partials of splits 0 .. S-2 first, in split order, then this split's own sum
+                        if (S > 1 && !noload) {      // partials of splits 0 .. S-2 first, in split order, then this split's own sum
                             float4 p[4];
 #pragma unroll
                             for (int it = 0; it < 4; ++it) {
@@ -324,14 +332,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
                             v.x += rs[it].x; v.y += rs[it].y; v.z += rs[it].z; v.w += rs[it].w;
                             v.x = apply_act(v.x, act); v.y = apply_act(v.y, act);
                             v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
-                            if (m < M) *reinterpret_cast<float4*>(out + (size_t)m * ldout + n) = v;
+                            if (m < M && !(a.knock & 1)) *reinterpret_cast<float4*>(out + (size_t)m * ldout + n) = v;
                         }
                     }
                 }
                 __syncwarp();
             }
             asm volatile("bar.sync 3, 128;" ::: "memory");       // every epilogue thread's stores happen before ...
-            if (etid == 0) red_release_gpu_add(last ? a.done + done_off + t.mt : pcount, 1);   // ... the gpu-scope release
+            if (etid == 0) {                                                                   // ... the gpu-scope release
+                int* cnt = last ? a.done + done_off + t.mt : pcount;
+                if (a.knock & 4) asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(cnt), "r"(1) : "memory");
+                else red_release_gpu_add(cnt, 1);
+            }
             if (etid == 0 && a.prof) a.prof[4 * (size_t)ti + 3] = gtime();
         }
     } else if (warp == 12) {
@@ -457,7 +469,13 @@ int plan_chain(const aotb_chain_layer* ls, int n, ChainPlan& P) {
         // fewer than ~one work item per SM
         d.ntn = ntn[i];
         d.splits = 1;
-        while (d.splits < 4 && mtiles[i] * ntn[i] * d.splits < 120 && d.nchunks / (d.splits + 1) >= 8) ++d.splits;
+        static int min_chunks = -1, max_split = -1, want_items = -1;
+        if (min_chunks < 0) {
+            const char* e1 = getenv("AOTB_CHAIN_MINCHUNKS"); min_chunks = e1 ? atoi(e1) : 8;
+            const char* e2 = getenv("AOTB_CHAIN_MAXSPLIT"); max_split = e2 ? atoi(e2) : 4;
+            const char* e3 = getenv("AOTB_CHAIN_ITEMS"); want_items = e3 ? atoi(e3) : 120;
+        }
+        while (d.splits < max_split && mtiles[i] * ntn[i] * d.splits < want_items && d.nchunks / (d.splits + 1) >= min_chunks) ++d.splits;
         d.part_off = -1;
         d.scratch = nullptr;
         if (d.splits > 1) {
@@ -629,6 +647,9 @@ extern "C" int aotb_conv_chain_run(void* program, int nlayers, int ntiles, int n
     static int prof = -1;
     if (prof < 0) { const char* e = getenv("AOTB_CHAIN_PROF"); prof = (e && atoi(e)) ? 1 : 0; }
     a.prof = prof ? (unsigned long long*)(base + off_done + tc::align_up((size_t)ncounters * sizeof(int), 256)) : nullptr;
+    static int knock = -1;
+    if (knock < 0) { const char* e = getenv("AOTB_CHAIN_KNOCK"); knock = e ? atoi(e) : 0; }
+    a.knock = knock;
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int smem = tc::CH_STAGES * tc::CH_STAGE_BYTES + tc::CH_STG_BYTES + 256 * (int)sizeof(tc::ChRowInfo) + 16 * 8 + 16 + 1024;
     static bool configured = false;

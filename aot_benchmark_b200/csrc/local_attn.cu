@@ -383,6 +383,216 @@ static int launch_local_tile(const LocalArgs& a, const float* relv_t, cudaStream
     return check_launch("aotb_local_attention_tile_f32");
 }
 
+
+// Tiled kernel for the DeAOT head shape (1 head, d_att = 128, d_v = 1024, no relative_emb_v; attention.py:789-861): the same
+// four passes as local_attn_tile_kernel, with the channel dimensions walked in chunks of 32 through the SAME shared-memory
+// halo buffer:
+//   scores    for every 32-channel chunk of q / k: the R pass adds q_chunk . relative_emb_k[tap]_chunk (bias with chunk 0) and
+//             the dot pass adds q_chunk . k_chunk[pos] / T (the -1e8 of out-of-frame taps with chunk 0) into the score tile;
+//   softmax   once;
+//   aggregate blockIdx.y selects a group of VC x 32 value channels; for each 32-channel chunk the V halo is staged and every
+//             warp accumulates its 3 queries with the channels on lanes.
+// The generic per-warp kernel (local_attn_kernel<128, 1024>) re-reads K / V rows from L1 / L2 for every query: 226 us per launch
+// at 31 x 54 (19.6 % of the R50-DeAOTL frame).  Here a CTA re-computes the scores of its query tile for its channel group
+// (VC = 8: 4 groups of 256 channels -> 144 CTAs, one wave) and reads every halo row once per chunk.
+template <int TY, int TX, int KC, int VC>
+__global__ void __launch_bounds__(512, 1) local_gated_tile_kernel(const LocalArgs p) {
+    pdl_sync();
+    constexpr int C = 32, HH = TY + 2 * LR, HWD = TX + 2 * LR, NPOS = HH * HWD, LD = 36;
+    constexpr int NT = 512, NQ = TY * TX, PLD = LW * 16, DQ = KC * C;
+    static_assert(TX % 3 == 0 && TY * (TX / 3) == NT / 32, "aggregate pass: one warp per 3 queries");
+    static_assert(LW * HWD <= NT && 2 * LTAPS <= NT && NQ % 2 == 0, "pass mappings");
+    extern __shared__ __align__(16) float smem[];
+    float* halo = smem;                   // [NPOS][LD]   one 32-channel chunk of K, later of V
+    float* qs = halo + NPOS * LD;         // [NQ][DQ]
+    float* prob = qs + NQ * DQ;           // [NQ][15][16] scores, then probabilities (slot 15 of each row is padding)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_x = (p.w + TX - 1) / TX;
+    const int ty0 = (blockIdx.x / tiles_x) * TY, tx0 = (blockIdx.x % tiles_x) * TX;
+    const int cg = blockIdx.y;            // value-channel group
+
+    auto load_halo = [&](const float* src, int ld, int c0) {
+        for (int f = tid; f < NPOS * 8; f += NT) {
+            const int pos = f >> 3, c4 = (f & 7) * 4;
+            const int hy = pos / HWD, hx = pos - hy * HWD;
+            const int yy = ty0 - LR + hy, xx = tx0 - LR + hx;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w)
+                v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(yy * p.w + xx) * ld + c0 + c4));
+            *reinterpret_cast<float4*>(halo + pos * LD + c4) = v;
+        }
+    };
+    for (int f = tid; f < NQ * (DQ / 4); f += NT) {
+        const int ql = f / (DQ / 4), c4 = (f % (DQ / 4)) * 4;
+        const int ly = ql / TX, lx = ql - ly * TX;
+        const int y = ty0 + ly, x = tx0 + lx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y < p.h && x < p.w) v = __ldg(reinterpret_cast<const float4*>(p.q + (size_t)(y * p.w + x) * p.ldq + c4));
+        *reinterpret_cast<float4*>(qs + ql * DQ + c4) = v;
+    }
+    load_halo(p.k, p.ldk, 0);
+    __syncthreads();
+
+    // ---- R pass: r[tap] = relative_emb_k(q)[tap] on the unscaled q (attention.py:814-816), all chunks
+    if (tid < 2 * LTAPS) {
+        const int half = tid / LTAPS, tap = tid - half * LTAPS;
+        const float bias = __ldg(p.relk_b + tap);
+        const int slot = (tap / LW) * 16 + tap % LW;
+#pragma unroll 1
+        for (int kc = 0; kc < KC; ++kc) {
+            float wk[C];
+            const float4* wp = reinterpret_cast<const float4*>(p.relk_w + (size_t)tap * DQ + kc * C);
+#pragma unroll
+            for (int c = 0; c < C / 4; ++c) {
+                const float4 t = __ldg(wp + c);
+                wk[4 * c] = t.x; wk[4 * c + 1] = t.y; wk[4 * c + 2] = t.z; wk[4 * c + 3] = t.w;
+            }
+#pragma unroll 2
+            for (int qi = 0; qi < NQ / 2; ++qi) {
+                const int ql = half * (NQ / 2) + qi;
+                const float4* q4 = reinterpret_cast<const float4*>(qs + ql * DQ + kc * C);
+                float r0 = kc == 0 ? bias : prob[ql * PLD + slot], r1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < C / 4; ++c) {
+                    const float4 t = q4[c];
+                    r0 = fmaf(wk[4 * c], t.x, r0); r1 = fmaf(wk[4 * c + 1], t.y, r1);
+                    r0 = fmaf(wk[4 * c + 2], t.z, r0); r1 = fmaf(wk[4 * c + 3], t.w, r1);
+                }
+                prob[ql * PLD + slot] = r0 + r1;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- dot pass per 32-channel chunk: s[tap] += (q_chunk . k_chunk[pos]) / T in frame;  r[tap] - 1e8 outside (:844)
+#pragma unroll 1
+    for (int kc = 0; kc < KC; ++kc) {
+        if (kc > 0) {
+            load_halo(p.k, p.ldk, kc * C);
+            __syncthreads();
+        }
+        if (tid < LW * HWD) {
+            const int dy = tid / HWD, hx = tid - dy * HWD;
+            const float invT = 1.f / p.T;
+            const int xx = tx0 + hx - LR;
+            const bool xin = (xx >= 0 && xx < p.w);
+#pragma unroll 1
+            for (int ly = 0; ly < TY; ++ly) {
+                const int yy = ty0 + ly + dy - LR;
+                const bool inside = xin && yy >= 0 && yy < p.h;
+                float kv[C];
+                const float4* kp = reinterpret_cast<const float4*>(halo + ((ly + dy) * HWD + hx) * LD);
+#pragma unroll
+                for (int c = 0; c < C / 4; ++c) {
+                    const float4 t = kp[c];
+                    kv[4 * c] = t.x; kv[4 * c + 1] = t.y; kv[4 * c + 2] = t.z; kv[4 * c + 3] = t.w;
+                }
+#pragma unroll
+                for (int lx = 0; lx < TX; ++lx) {
+                    const int dx = hx - lx;
+                    const float4* q4 = reinterpret_cast<const float4*>(qs + (ly * TX + lx) * DQ + kc * C);
+                    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < C / 4; ++c) {
+                        const float4 t = q4[c];
+                        d0 = fmaf(kv[4 * c], t.x, d0); d1 = fmaf(kv[4 * c + 1], t.y, d1);
+                        d0 = fmaf(kv[4 * c + 2], t.z, d0); d1 = fmaf(kv[4 * c + 3], t.w, d1);
+                    }
+                    if (dx >= 0 && dx < LW) {
+                        float* sp = prob + (ly * TX + lx) * PLD + dy * 16 + dx;
+                        if (inside) *sp += (d0 + d1) * invT;
+                        else if (kc == 0) *sp += -1e8f;
+                    }
+                }
+            }
+        }
+        __syncthreads();      // this chunk of the K halo is dead
+    }
+    load_halo(p.v, p.ldv, (cg * VC) * C);      // first V chunk, overlapped with the softmax below
+
+    // ---- softmax over the 225 taps of each query (padding slots excluded)
+    for (int ql = warp; ql < NQ; ql += NT / 32) {
+        float* pq = prob + ql * PLD;
+        float sc[8];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = lane + 32 * j;
+            const bool valid = i < PLD && (i & 15) != 15;
+            sc[j] = valid ? pq[i] : -INFINITY;
+            mx = fmaxf(mx, sc[j]);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = expf(sc[j] - mx);         // exp(-inf) = 0 for the padding slots
+            sum += sc[j];
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = lane + 32 * j;
+            if (i < PLD) pq[i] = sc[j] * inv;
+        }
+    }
+    __syncthreads();
+
+    // ---- aggregate: o[c] = sum_tap p[tap] * v[pos][c], channels on lanes, one 32-channel chunk at a time
+    const int ly = warp / (TX / 3), lx0 = (warp % (TX / 3)) * 3;
+#pragma unroll 1
+    for (int vc = 0; vc < VC; ++vc) {
+        if (vc > 0) {
+            __syncthreads();                  // everybody is done with the previous chunk
+            load_halo(p.v, p.ldv, (cg * VC + vc) * C);
+            __syncthreads();
+        }
+        float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int dy = 0; dy < LW; ++dy) {
+            const float* vrow = halo + ((ly + dy) * HWD + lx0) * LD + lane;   // zero outside the frame
+            float vv[LW + 2];
+#pragma unroll
+            for (int j = 0; j < LW + 2; ++j) vv[j] = vrow[j * LD];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float4* pp = reinterpret_cast<const float4*>(prob + (ly * TX + lx0 + i) * PLD + dy * 16);
+                const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2], p3 = pp[3];
+                const float pa[16] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w,
+                                      p2.x, p2.y, p2.z, p2.w, p3.x, p3.y, p3.z, p3.w};
+#pragma unroll
+                for (int dx = 0; dx < LW; ++dx) acc[i] = fmaf(pa[dx], vv[i + dx], acc[i]);
+            }
+        }
+        const int y = ty0 + ly;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int x = tx0 + lx0 + i;
+            if (y < p.h && x < p.w) p.out[(size_t)(y * p.w + x) * p.ldo + (cg * VC + vc) * C + lane] = acc[i];
+        }
+    }
+}
+
+static int launch_local_gated_tile(const LocalArgs& a, cudaStream_t st) {
+    constexpr int TY = 8, TX = 6, KC = 4, VC = 8;       // d_att = 128; 1024 value channels = 4 groups of 8 chunks
+    const size_t smem = sizeof(float) * (size_t)((TY + 14) * (TX + 14) * 36 + TY * TX * KC * 32 + TY * TX * LW * 16);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(local_gated_tile_kernel<TY, TX, KC, VC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) {
+            set_error("aotb_local_gated_tile_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return AOTB_ERR_CUDA;
+        }
+        configured = true;
+    }
+    dim3 grid(cdiv(a.h, TY) * cdiv(a.w, TX), 1024 / (VC * 32));
+    launch(local_gated_tile_kernel<TY, TX, KC, VC>, dim3(grid), dim3(512), smem, st, a);
+    return check_launch("aotb_local_gated_tile_f32");
+}
+
 }  // namespace aotb
 
 using namespace aotb;
@@ -416,4 +626,17 @@ extern "C" int aotb_local_attention_tile_f32(const float* q, int ldq, const floa
     a.relk_w = relk_w; a.relk_b = relk_b; a.relv = nullptr; a.out = out; a.ldo = ldo;
     a.h = h; a.w = w; a.H = H; a.T = sqrtf(32.f);
     return launch_local_tile(a, relv_t, (cudaStream_t)stream);
+}
+
+// Tiled kernel for the DeAOT head shape (one head, d_att = 128, d_v = 1024, no relative_emb_v): networks/layers/attention.py:789-861.
+extern "C" int aotb_local_gated_tile_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                                         const float* relk_w, const float* relk_b, float* out, int ldo, int h, int w,
+                                         void* stream) {
+    AOTB_REQUIRE(q && k && v && relk_w && relk_b && out && h > 0 && w > 0, "aotb_local_gated_tile_f32: bad args");
+    AOTB_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, "aotb_local_gated_tile_f32: ld %% 4");
+    LocalArgs a;
+    a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv;
+    a.relk_w = relk_w; a.relk_b = relk_b; a.relv = nullptr; a.out = out; a.ldo = ldo;
+    a.h = h; a.w = w; a.H = 1; a.T = sqrtf(128.f);
+    return launch_local_gated_tile(a, (cudaStream_t)stream);
 }

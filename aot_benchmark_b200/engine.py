@@ -1153,7 +1153,10 @@ class DeAOTEngine(AOTEngine):
                 e1.record()
                 probe.append((e0, e1, 2.0 * N * Tk * (d + C4)))      # FLOPs = 2*N*Tk*(d_qk + d_v), SURVEY 8d
             self._gated_tail(ws.core, ws.catU, Lw.lt_dw, ws.dw[:, :C4], h, w, st)
-            ops.local_attention(cQ, stK[li], stV[li], Lw.relk_w, Lw.relk_b, None, ws.core, h, w, 1, d, C4, stream=st)
+            if LOCAL_IMPL == "tile" and d == 128 and C4 == 1024:
+                ops.local_gated_tile(cQ, stK[li], stV[li], Lw.relk_w, Lw.relk_b, ws.core, h, w, stream=st)
+            else:
+                ops.local_attention(cQ, stK[li], stV[li], Lw.relk_w, Lw.relk_b, None, ws.core, h, w, 1, d, C4, stream=st)
             self._gated_tail(ws.core, ws.catU, Lw.st_dw, ws.dw[:, C4:], h, w, st)
             # [tgt | tgt_id] += proj_lt(.) + proj_st(.)   (transformer.py:633-641) as one K = 8C GEMM
             ops.linear(ws.dw, Lw.lst_proj_w, Lw.lst_proj_b, ws.xz, res=ws.xz, stream=st)

@@ -416,6 +416,16 @@ def local_attention(q, k, v, relk_w, relk_b, relv, out, h, w, H, d_att, d_v, str
     return out
 
 
+def local_gated_tile(q, k, v, relk_w, relk_b, out, h, w, stream=None):
+    """DeAOT head shape (1 x 128 / 1024, no relative_emb_v): halo-in-shared-memory kernel; q, k [hw, 128], v / out [hw, 1024]."""
+    _chk(q, k, v, relk_w, relk_b, out)
+    if q.shape[1] != 128 or k.shape[1] != 128 or v.shape[1] != 1024 or out.shape[1] != 1024 or not relk_w.is_contiguous():
+        raise AotbError("local_gated_tile: q / k [hw, 128], v / out [hw, 1024], contiguous relative_emb_k weights [225, 128]")
+    check(lib().aotb_local_gated_tile_f32(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(relk_w), _p(relk_b),
+                                          _p(out), out.stride(0), h, w, _st(stream)), "aotb_local_gated_tile_f32")
+    return out
+
+
 def local_attention_tile(q, k, v, relk_w, relk_b, relv_t, out, h, w, H, stream=None):
     """AOT head shape (d = 32): halo-in-shared-memory kernel; relv_t [H, 225, 32]."""
     _chk(q, k, v, relk_w, relk_b, relv_t, out)

@@ -142,6 +142,11 @@ int aotb_local_attention_tile_f32(const float* q, int ldq, const float* k, int l
                                   const float* relk_w, const float* relk_b, const float* relv_t, float* out, int ldo,
                                   int h, int w, int H, void* stream);
 
+/* Same computation for the DeAOT head shape (one head, d_att 128, d_v 1024, no relative_emb_v; attention.py:789-861) with the
+ * window halos staged in shared memory per 8x6 query tile and the channels walked in chunks of 32. */
+int aotb_local_gated_tile_f32(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                              const float* relk_w, const float* relk_b, float* out, int ldo, int h, int w, void* stream);
+
 /* one_hot_mask + patch_wise_id_bank conv as a gather-sum (+ LayerNorm for DeAOT):
  * utils/image.py:69-74; networks/models/aot.py:50-63,76-79; networks/models/deaot.py:51-55.
  * mask [Hm][Wm] float ids; wt [(ky*KS+kx)*nid + id][C]. */

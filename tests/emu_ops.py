@@ -411,7 +411,12 @@ def soft_logit_aggregation(logits, out, max_obj, stream=None):
     return out
 
 
-EMULATED = ("separate_labels", "soft_logit_aggregation", "image_to_nhwc4", "conv2d", "linear", "layernorm", "window_attention", "patch_merge", "eltwise",
+def local_gated_tile(q, k, v, relk_w, relk_b, out, h, w, stream=None):
+    """Contract of aotb_local_gated_tile_f32 == aotb_local_attention_f32 for the DeAOT head shape."""
+    return local_attention(q, k, v, relk_w, relk_b, None, out, h, w, 1, 128, 1024, stream=stream)
+
+
+EMULATED = ("local_gated_tile", "separate_labels", "soft_logit_aggregation", "image_to_nhwc4", "conv2d", "linear", "layernorm", "window_attention", "patch_merge", "eltwise",
             "nchw_to_nhwc", "nhwc_to_nchw", "maxpool3x3s2", "dwconv", "bilinear", "groupnorm_workspace", "groupnorm",
             "attention", "attn_merge", "attn_merge_peers", "tc_pack_rows", "lt_attention_tc", "local_attention", "local_attention_tile",
             "id_embed", "id_embed_runs", "logits_postproc", "logits_argmax", "nearest_resize", "bank_append",

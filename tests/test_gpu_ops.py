@@ -265,6 +265,30 @@ def test_local_attention_deaot():
     assert (out.cpu().double() - ref).abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize("h,w", [(9, 17), (31, 54), (8, 6), (13, 5)])
+def test_local_gated_tile_deaot(h, w):
+    """Tiled DeAOT short-term kernel (8x6 query tiles, channels in chunks of 32) vs the fp64 oracle (attention.py:789-861 in the
+    unfold form) and vs the generic per-warp kernel, incl. ragged tiles and maps smaller than the window."""
+    from aot_benchmark_b200 import ops
+    from oracle import aot_oracle as O
+    d = _dev()
+    g = torch.Generator().manual_seed(100 + h)
+    q = torch.randn(1, 128, h, w, generator=g)
+    k = torch.randn(1, 128, h, w, generator=g)
+    v = torch.randn(1, 1024, h, w, generator=g)
+    rkw = torch.randn(225, 128, 1, 1, generator=g) * 0.1
+    rkb = torch.randn(225, generator=g) * 0.1
+    ref = O.local_attention(q.double(), k.double(), v.double(), rkw.double(), rkb.double(), None, 1)[:, 0]
+    tok = lambda t: t[0].permute(1, 2, 0).reshape(h * w, -1).contiguous().to(d)
+    out = torch.full((h * w, 1024), float("nan"), device=d)
+    ops.local_gated_tile(tok(q), tok(k), tok(v), rkw.view(225, 128).contiguous().to(d), rkb.to(d), out, h, w)
+    gen = torch.empty(h * w, 1024, device=d)
+    ops.local_attention(tok(q), tok(k), tok(v), rkw.view(225, 128).contiguous().to(d), rkb.to(d), None, gen, h, w, 1, 128, 1024)
+    assert torch.isfinite(out).all()
+    assert (out.cpu().double() - ref).abs().max().item() < 2e-5
+    assert (out - gen).abs().max().item() < 2e-5
+
+
 @pytest.mark.parametrize("align,ln", [(True, False), (True, True), (False, False)])
 def test_id_embed(align, ln):
     from aot_benchmark_b200 import ops
