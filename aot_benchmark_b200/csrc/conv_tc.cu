@@ -96,6 +96,68 @@ __device__ __forceinline__ void conv_finish_tile(const ConvTcArgs& a, const uint
     }
 }
 
+// Finish without split-K with the global loads taken off its critical path: the bias and the residual rows of the FIRST batch are
+// already in registers (`pre`, loaded by finish_prefetch before the thread waited for the accumulator, i.e. under the tail of the
+// K loop), and inside the loop the residual rows of batch k+1 are requested before batch k is computed and stored.  The staging
+// tile is read with ld.shared so that the compiler does not have to order those reads behind the global stores.
+template <int BN>
+struct FinishPre { float4 b4; float4 rs[8]; };
+
+template <int BN>
+__device__ __forceinline__ void finish_prefetch(const ConvTcArgs& a, int tid, int m0, int n0, FinishPre<BN>& pre) {
+    constexpr int C4 = BN / 4, RSTEP = 256 / C4;
+    const int n = n0 + (tid % C4) * 4, r0 = tid / C4;
+    pre.b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const int m = m0 + r0 + b * RSTEP;
+        pre.rs[b] = (a.res && m < a.M) ? *reinterpret_cast<const float4*>(a.res + (size_t)m * a.ldres + n)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int BN>
+__device__ __forceinline__ void conv_finish_tile_pre(const ConvTcArgs& a, const uint8_t* smem, int tid, int m0, int n0,
+                                                     const FinishPre<BN>& pre) {
+    constexpr int LD = BN + 4, C4 = BN / 4, RSTEP = 256 / C4, ITERS = 128 / RSTEP, B = 8;
+    static_assert(ITERS % B == 0, "finish tiling");
+    const int c = (tid % C4) * 4, n = n0 + c, r0 = tid / C4;
+    const uint32_t sbase = smem_u32(reinterpret_cast<const float*>(smem) + r0 * LD + c);
+    float4 rs[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) rs[b] = pre.rs[b];
+#pragma unroll 1
+    for (int i0 = 0; i0 < ITERS; i0 += B) {
+        float4 v[B], nx[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[b].x), "=f"(v[b].y), "=f"(v[b].z), "=f"(v[b].w)
+                         : "r"(sbase + (uint32_t)((i0 + b) * RSTEP * LD) * 4u));
+        if (i0 + B < ITERS) {                      // residual rows of the next batch, in flight while this one is stored
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const int m = m0 + r0 + (i0 + B + b) * RSTEP;
+                nx[b] = (a.res && m < a.M) ? *reinterpret_cast<const float4*>(a.res + (size_t)m * a.ldres + n)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            float4 o = v[b];
+            o.x += pre.b4.x; o.y += pre.b4.y; o.z += pre.b4.z; o.w += pre.b4.w;
+            o.x += rs[b].x; o.y += rs[b].y; o.z += rs[b].z; o.w += rs[b].w;
+            o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act);
+            o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
+            const int m = m0 + r0 + (i0 + b) * RSTEP;
+            if (m < a.M) *reinterpret_cast<float4*>(a.out + (size_t)m * a.ldout + n) = o;
+        }
+        if (i0 + B < ITERS) {
+#pragma unroll
+            for (int b = 0; b < B; ++b) rs[b] = nx[b];
+        }
+    }
+}
+
 template <int BN, int STAGES>
 struct ConvSmem {
     static constexpr int A_BYTES = 128 * 128;          // one 128 x 64 half tile
@@ -163,6 +225,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     const int kbeg = blockIdx.z * per;
     const int nloc = max(0, min(per, a.nchunks - kbeg));     // chunks of this CTA (local index it <-> chunk kbeg + it)
 
+    FinishPre<BN> pre;
     if (warp < 8) {
         // ======================= A producers (8 warps, register double-buffered) =======================
         const int q = tid & 15, rsub = tid >> 4;      // rsub 0..15; this thread serves rows i*16 + rsub, i = 0..7
@@ -232,6 +295,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
             }
         }
         // ======================= epilogue (warps 0-3: columns [0, BN/2), warps 4-7: [BN/2, BN)) =======================
+        if (a.splits == 1) finish_prefetch<BN>(a, tid, m0, n0, pre);      // bias + first residual rows: under the last MMAs
         if (nloc > 0) {
             W(acc_full, 0);
             tc_fence_after();
@@ -316,7 +380,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     if (tid == 0) stamp(8);
     if (warp < 8) {
         const int zr = a.splits > 1 ? (int)blockIdx.z : 0;
-        if (a.splits == 1) conv_finish_tile<BN, 1, 8>(a, smem, tid, m0, n0, zr);
+        if (a.splits == 1) conv_finish_tile_pre<BN>(a, smem, tid, m0, n0, pre);
         else if (a.splits == 2) conv_finish_tile<BN, 2, 4>(a, smem, tid, m0, n0, zr);
         else if (a.splits == 4) conv_finish_tile<BN, 4, 2>(a, smem, tid, m0, n0, zr);
         else conv_finish_tile<BN, 8, 2>(a, smem, tid, m0, n0, zr);
