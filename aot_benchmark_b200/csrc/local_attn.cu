@@ -20,6 +20,15 @@ namespace aotb {
 
 constexpr int LW = 15, LR = 7, LTAPS = 225;
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); bytes = 0 zero-fills the destination (out-of-frame halo positions).  All
+// copies of a halo are issued back to back and completed by one wait: the register-staged loop they replace paid one L2 round
+// trip per iteration (7 per halo and thread).
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src),
+                 "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
 struct LocalArgs {
     const float* q; int ldq;
     const float* k; int ldk;
@@ -212,15 +221,13 @@ __global__ void __launch_bounds__(512, 1) local_attn_tile_kernel(const LocalArgs
     const int ty0 = (blockIdx.x / tiles_x) * TY, tx0 = (blockIdx.x % tiles_x) * TX;
     const int g = blockIdx.y;
 
-    auto load_halo = [&](const float* src, int ld) {
+    auto load_halo = [&](const float* src, int ld) {          // asynchronous: complete after cp_async_wait_all() + barrier
         for (int f = tid; f < NPOS * 8; f += NT) {
             const int pos = f >> 3, c4 = (f & 7) * 4;
             const int hy = pos / HWD, hx = pos - hy * HWD;
             const int yy = ty0 - LR + hy, xx = tx0 - LR + hx;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w)
-                v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(yy * p.w + xx) * ld + g * D + c4));
-            *reinterpret_cast<float4*>(halo + pos * LD + c4) = v;
+            const bool in = yy >= 0 && yy < p.h && xx >= 0 && xx < p.w;
+            cp_async16(halo + pos * LD + c4, in ? src + (size_t)(yy * p.w + xx) * ld + g * D + c4 : src, in ? 16 : 0);
         }
     };
     for (int f = tid; f < NQ * 8; f += NT) {
@@ -232,10 +239,11 @@ __global__ void __launch_bounds__(512, 1) local_attn_tile_kernel(const LocalArgs
         *reinterpret_cast<float4*>(qs + ql * D + c4) = v;
     }
     {
-        const float4* src = reinterpret_cast<const float4*>(relv_t + (size_t)g * LTAPS * D);
-        for (int f = tid; f < LTAPS * 8; f += NT) reinterpret_cast<float4*>(rvs)[f] = __ldg(src + f);
+        const float* src = relv_t + (size_t)g * LTAPS * D;
+        for (int f = tid; f < LTAPS * 8; f += NT) cp_async16(rvs + 4 * f, src + 4 * f, 16);
     }
     load_halo(p.k, p.ldk);
+    cp_async_wait_all();
     __syncthreads();
 
     // ---- R pass: r[tap] = relative_emb_k(q)[tap] on the unscaled q (attention.py:327)
@@ -331,6 +339,7 @@ __global__ void __launch_bounds__(512, 1) local_attn_tile_kernel(const LocalArgs
             if (i < PLD) pq[i] = sc[j] * inv;
         }
     }
+    cp_async_wait_all();      // the V halo, requested before the softmax
     __syncthreads();
 
     // ---- aggregate: o[c] = sum_tap p[tap] * (v[pos][c] + relative_emb_v[tap][c]), channels on lanes
@@ -412,15 +421,13 @@ __global__ void __launch_bounds__(512, 1) local_gated_tile_kernel(const LocalArg
     const int ty0 = (blockIdx.x / tiles_x) * TY, tx0 = (blockIdx.x % tiles_x) * TX;
     const int cg = blockIdx.y;            // value-channel group
 
-    auto load_halo = [&](const float* src, int ld, int c0) {
+    auto load_halo = [&](const float* src, int ld, int c0) {   // asynchronous: complete after cp_async_wait_all() + barrier
         for (int f = tid; f < NPOS * 8; f += NT) {
             const int pos = f >> 3, c4 = (f & 7) * 4;
             const int hy = pos / HWD, hx = pos - hy * HWD;
             const int yy = ty0 - LR + hy, xx = tx0 - LR + hx;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (yy >= 0 && yy < p.h && xx >= 0 && xx < p.w)
-                v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(yy * p.w + xx) * ld + c0 + c4));
-            *reinterpret_cast<float4*>(halo + pos * LD + c4) = v;
+            const bool in = yy >= 0 && yy < p.h && xx >= 0 && xx < p.w;
+            cp_async16(halo + pos * LD + c4, in ? src + (size_t)(yy * p.w + xx) * ld + c0 + c4 : src, in ? 16 : 0);
         }
     };
     for (int f = tid; f < NQ * (DQ / 4); f += NT) {
@@ -432,6 +439,7 @@ __global__ void __launch_bounds__(512, 1) local_gated_tile_kernel(const LocalArg
         *reinterpret_cast<float4*>(qs + ql * DQ + c4) = v;
     }
     load_halo(p.k, p.ldk, 0);
+    cp_async_wait_all();
     __syncthreads();
 
     // ---- R pass: r[tap] = relative_emb_k(q)[tap] on the unscaled q (attention.py:814-816), all chunks
@@ -470,6 +478,7 @@ __global__ void __launch_bounds__(512, 1) local_gated_tile_kernel(const LocalArg
     for (int kc = 0; kc < KC; ++kc) {
         if (kc > 0) {
             load_halo(p.k, p.ldk, kc * C);
+            cp_async_wait_all();
             __syncthreads();
         }
         if (tid < LW * HWD) {
@@ -538,6 +547,7 @@ __global__ void __launch_bounds__(512, 1) local_gated_tile_kernel(const LocalArg
             if (i < PLD) pq[i] = sc[j] * inv;
         }
     }
+    cp_async_wait_all();      // the first V chunk, requested before the softmax
     __syncthreads();
 
     // ---- aggregate: o[c] = sum_tap p[tap] * v[pos][c], channels on lanes, one 32-channel chunk at a time
@@ -547,6 +557,7 @@ __global__ void __launch_bounds__(512, 1) local_gated_tile_kernel(const LocalArg
         if (vc > 0) {
             __syncthreads();                  // everybody is done with the previous chunk
             load_halo(p.v, p.ldv, (cg * VC + vc) * C);
+            cp_async_wait_all();
             __syncthreads();
         }
         float acc[3] = {0.f, 0.f, 0.f};

@@ -10,6 +10,7 @@
 // GroupNorm statistics are reduced deterministically (fixed partial layout, double precision
 // partials) so replicated ranks stay bit-identical.
 #include "common.cuh"
+#include <cstdint>
 
 namespace aotb {
 
@@ -61,7 +62,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const flo
 constexpr int GN_CHUNKS = 64;
 
 __global__ void groupnorm_stats_kernel(const float* __restrict__ x, int ldx, int P, int G, int Cg,
-                                       double* __restrict__ partial) {
+                                       double* __restrict__ partial, float* __restrict__ stat, unsigned* __restrict__ counter,
+                                       float eps) {
     pdl_sync();
     const int chunk = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
     const int per = (P + GN_CHUNKS - 1) / GN_CHUNKS;
@@ -77,6 +79,7 @@ __global__ void groupnorm_stats_kernel(const float* __restrict__ x, int ldx, int
         q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
     }
     __shared__ double sh[2][8];
+    __shared__ unsigned last;
     double ds = (double)warp_sum(s), dq = (double)warp_sum(q);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) { sh[0][wid] = ds; sh[1][wid] = dq; }
@@ -86,42 +89,49 @@ __global__ void groupnorm_stats_kernel(const float* __restrict__ x, int ldx, int
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; c += sh[1][w]; }
         double* o = partial + (((size_t)b * G + g) * GN_CHUNKS + chunk) * 2;
         o[0] = a; o[1] = c;
+        __threadfence();
+        last = atomicAdd(counter, 1u) == gridDim.x * gridDim.y * gridDim.z - 1 ? 1u : 0u;
     }
+    __syncthreads();
+    if (!last) return;
+    // The block that arrives last turns the partials into (mean, rstd) per (b, g) -- ONCE, in a fixed order (8 threads per group
+    // sum 8 chunks each in order, then a fixed xor tree), whichever block it is.  The apply kernel used to redo this in every one
+    // of its ~1200 blocks (32 KB of double partials each: 17 us per launch for 14 MB of payload).
+    __threadfence();
+    const int BG = gridDim.z * G;
+    for (int g0 = 0; g0 < BG; g0 += blockDim.x / 8) {
+        const int bg = g0 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
+        double ss = 0, qq = 0;
+        if (bg < BG) {
+            const volatile double* pp = partial + ((size_t)bg * GN_CHUNKS + sub * (GN_CHUNKS / 8)) * 2;
+#pragma unroll
+            for (int c = 0; c < GN_CHUNKS / 8; ++c) { ss += pp[2 * c]; qq += pp[2 * c + 1]; }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            qq += __shfl_xor_sync(0xffffffffu, qq, o);
+        }
+        if (bg < BG && sub == 0) {
+            const double nn = (double)P * Cg;
+            const double mean = ss / nn;
+            double var = qq / nn - mean * mean;
+            if (var < 0) var = 0;
+            stat[2 * bg] = (float)mean;
+            stat[2 * bg + 1] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+    }
+    if (threadIdx.x == 0) *counter = 0u;          // ready for the next launch
 }
 
 // ---- stage 2: normalise + affine + activation
 __global__ void groupnorm_apply_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, const double* __restrict__ partial,
-                                       float* __restrict__ out, int ldo, int P, int C, int G, int Cg, int act,
-                                       float eps) {
+                                       const float* __restrict__ beta, const float* __restrict__ gstat,
+                                       float* __restrict__ out, int ldo, int P, int C, int G, int Cg, int act) {
     pdl_sync();
-    extern __shared__ float stat[];  // [G][2] mean, rstd for this batch element
+    extern __shared__ float stat[];  // [G][2] mean, rstd for this batch element (finalised by the stats kernel's last block)
     const int b = blockIdx.y;
-    // 8 threads per group: thread `sub` sums chunks [8 sub, 8 sub + 8) in order, the 8 sub-sums are combined by a fixed xor
-    // tree (deterministic; the same in every block).  A single thread per group walking all 64 double partials -- the first
-    // version -- put ~20 k cycles of dependent L2 loads in front of every block (19.6 us per launch for 14 MB of traffic).
-    for (int g0 = 0; g0 < G; g0 += blockDim.x / 8) {
-        const int g = g0 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
-        double s = 0, q = 0;
-        if (g < G) {
-            const double* pp = partial + (((size_t)b * G + g) * GN_CHUNKS + sub * (GN_CHUNKS / 8)) * 2;
-#pragma unroll
-            for (int c = 0; c < GN_CHUNKS / 8; ++c) { s += pp[2 * c]; q += pp[2 * c + 1]; }
-        }
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            q += __shfl_xor_sync(0xffffffffu, q, o);
-        }
-        if (g < G && sub == 0) {
-            const double n = (double)P * Cg;
-            const double mean = s / n;
-            double var = q / n - mean * mean;
-            if (var < 0) var = 0;
-            stat[2 * g] = (float)mean;
-            stat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
-        }
-    }
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) stat[i] = gstat[(size_t)b * 2 * G + i];
     __syncthreads();
     const int C4 = C >> 2;
     const size_t total = (size_t)P * C4;
@@ -158,8 +168,12 @@ extern "C" int aotb_layernorm_f32(const float* x, int ldx, const float* gamma, c
     return check_launch("aotb_layernorm_f32");
 }
 
+// workspace = [launch counter, 256 B][(mean, rstd) floats: 8 KB per batch element][double partials]; it must be ZERO when first
+// used (the counter) and is left ready for the next call.
+static constexpr size_t GN_HDR = 256, GN_STAT = 8192;
+
 extern "C" size_t aotb_groupnorm_workspace_bytes(int B, int G) {
-    return (size_t)B * G * GN_CHUNKS * 2 * sizeof(double);
+    return GN_HDR + (size_t)B * GN_STAT + (size_t)B * G * GN_CHUNKS * 2 * sizeof(double);
 }
 
 extern "C" int aotb_groupnorm_nhwc_f32(const float* x, int ldx, const float* gamma, const float* beta, float* out,
@@ -170,12 +184,14 @@ extern "C" int aotb_groupnorm_nhwc_f32(const float* x, int ldx, const float* gam
                  "aotb_groupnorm_nhwc_f32: unsupported channel/group configuration");
     const int Cg = C / G;
     cudaStream_t st = (cudaStream_t)stream;
-    launch(groupnorm_stats_kernel, dim3(dim3(GN_CHUNKS, G, B)), dim3(256), 0, st, x, ldx, P, G, Cg, (double*)workspace);
+    unsigned* counter = (unsigned*)workspace;
+    float* stat = (float*)((uint8_t*)workspace + GN_HDR);
+    double* partial = (double*)((uint8_t*)workspace + GN_HDR + (size_t)B * GN_STAT);
+    launch(groupnorm_stats_kernel, dim3(dim3(GN_CHUNKS, G, B)), dim3(256), 0, st, x, ldx, P, G, Cg, partial, stat, counter, 1e-5f);
     const size_t total = (size_t)P * (C / 4);
     int gx = (int)((total + 255) / 256);
     if (gx > 148 * 8) gx = 148 * 8;
     launch(groupnorm_apply_kernel, dim3(dim3(gx, B)), dim3(256), 2 * G * sizeof(float), st, x, ldx, gamma, beta,
-                                                                             (const double*)workspace, out, ldo, P, C,
-                                                                             G, Cg, act, 1e-5f);
+                                                                             (const float*)stat, out, ldo, P, C, G, Cg, act);
     return check_launch("aotb_groupnorm_nhwc_f32", 2);
 }

@@ -364,7 +364,7 @@ def patch_merge(x, out, H, W, stream=None):
 
 def groupnorm_workspace(B, G, device):
     n = lib().aotb_groupnorm_workspace_bytes(B, G)
-    return torch.empty(n // 8, dtype=torch.float64, device=device)
+    return torch.zeros((n + 7) // 8, dtype=torch.float64, device=device)      # zero: the launch counter lives in it
 
 
 def groupnorm(x, gamma, beta, out, G, act, workspace, stream=None):

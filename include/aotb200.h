@@ -106,7 +106,9 @@ int aotb_window_attention_f32(const float* qkv, int ldqkv, const float* qkv_bias
  * 4C channels ordered [(0,0) | (1,0) | (0,1) | (1,1)] of each 2x2 block, zeros outside H x W. */
 int aotb_patch_merge_f32(const float* x, int ldx, float* out, int ldo, int H, int W, int C, void* stream);
 
-/* nn.GroupNorm(G, C) over [B][P pixels][C] + activation: networks/layers/basic.py:6-12,18,30-32,75-85. */
+/* nn.GroupNorm(G, C) over [B][P pixels][C] + activation: networks/layers/basic.py:6-12,18,30-32,75-85.  The workspace
+ * (aotb_groupnorm_workspace_bytes(B, G) bytes, reusable for any smaller G) must be zero-filled before its first use: it holds
+ * the launch counter with which the last block of the statistics kernel finalises (mean, rstd) once, in a fixed order. */
 size_t aotb_groupnorm_workspace_bytes(int B, int G);
 int aotb_groupnorm_nhwc_f32(const float* x, int ldx, const float* gamma, const float* beta, float* out, int ldo,
                             int B, int P, int C, int G, int act, void* workspace, void* stream);
