@@ -61,12 +61,14 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const flo
 // x [B][P][ldx] (P pixels), group g covers channels [g*Cg, (g+1)*Cg)
 constexpr int GN_CHUNKS = 64;
 
+// `chunks` (a multiple of 8, <= GN_CHUNKS) pixel ranges per (b, g): enough blocks to fill the GPU on the large decoder maps, few
+// enough on the 31 x 54 token maps that a block has more than one load per thread (2 048 blocks of 208 float4 took 9.8 us).
 __global__ void groupnorm_stats_kernel(const float* __restrict__ x, int ldx, int P, int G, int Cg,
                                        double* __restrict__ partial, float* __restrict__ stat, unsigned* __restrict__ counter,
                                        float eps) {
     pdl_sync();
-    const int chunk = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
-    const int per = (P + GN_CHUNKS - 1) / GN_CHUNKS;
+    const int chunk = blockIdx.x, g = blockIdx.y, b = blockIdx.z, chunks = gridDim.x;
+    const int per = (P + chunks - 1) / chunks;
     const int p0 = chunk * per, p1 = min(P, p0 + per);
     const float* xb = x + (size_t)b * P * ldx + (size_t)g * Cg;
     const int Cg4 = Cg >> 2;
@@ -103,9 +105,9 @@ __global__ void groupnorm_stats_kernel(const float* __restrict__ x, int ldx, int
         const int bg = g0 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
         double ss = 0, qq = 0;
         if (bg < BG) {
-            const volatile double* pp = partial + ((size_t)bg * GN_CHUNKS + sub * (GN_CHUNKS / 8)) * 2;
-#pragma unroll
-            for (int c = 0; c < GN_CHUNKS / 8; ++c) { ss += pp[2 * c]; qq += pp[2 * c + 1]; }
+            const int cps = chunks / 8;                      // chunks per summing thread
+            const volatile double* pp = partial + ((size_t)bg * GN_CHUNKS + sub * cps) * 2;
+            for (int c = 0; c < cps; ++c) { ss += pp[2 * c]; qq += pp[2 * c + 1]; }
         }
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {
@@ -187,7 +189,10 @@ extern "C" int aotb_groupnorm_nhwc_f32(const float* x, int ldx, const float* gam
     unsigned* counter = (unsigned*)workspace;
     float* stat = (float*)((uint8_t*)workspace + GN_HDR);
     double* partial = (double*)((uint8_t*)workspace + GN_HDR + (size_t)B * GN_STAT);
-    launch(groupnorm_stats_kernel, dim3(dim3(GN_CHUNKS, G, B)), dim3(256), 0, st, x, ldx, P, G, Cg, partial, stat, counter, 1e-5f);
+    int chunks = (int)(((size_t)P * (Cg / 4) + 1023) / 1024);          // ~4 float4 loads per thread and block
+    chunks = ((chunks + 7) / 8) * 8;
+    chunks = chunks < 8 ? 8 : (chunks > GN_CHUNKS ? GN_CHUNKS : chunks);
+    launch(groupnorm_stats_kernel, dim3(dim3(chunks, G, B)), dim3(256), 0, st, x, ldx, P, G, Cg, partial, stat, counter, 1e-5f);
     const size_t total = (size_t)P * (C / 4);
     int gx = (int)((total + 255) / 256);
     if (gx > 148 * 8) gx = 148 * 8;
