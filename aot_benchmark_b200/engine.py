@@ -84,14 +84,15 @@ USE_GRAPHS = _os.environ.get("AOTB_GRAPHS", "1") == "1"
 # programmatic dependent launch: kernel N+1's prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps
 # kernel N's tail; every kernel waits (griddepcontrol.wait) before reading its inputs
 USE_PDL = _os.environ.get("AOTB_PDL", "1") == "1"     # programmatic dependent launch: +2 % (profiles/r01_trip14)
-CONV_TILING = _os.environ.get("AOTB_CONV_TILING", "model")   # "model" (fitted cost model) | "narrow" (old heuristic)
+CONV_TILING = _os.environ.get("AOTB_CONV_TILING", "model")   # "model" (fitted cost model) | "narrow" (old heuristic) | "bulk" (model + bulk-copy finish)
+_CONV_TILING_MASK = {"model": 0, "narrow": 1, "bulk": 8}
 
 
 def _apply_pdl():
     """Push the launch-policy knobs into the library (cheap; called at the start of every clip)."""
     from ._lib import lib, check
     lib().aotb_set_pdl(1 if USE_PDL else 0)
-    check(lib().aotb_set_conv_tiling(1 if CONV_TILING == "narrow" else 0), "aotb_set_conv_tiling")
+    check(lib().aotb_set_conv_tiling(_CONV_TILING_MASK[CONV_TILING]), "aotb_set_conv_tiling")
 BANK_INIT_FRAMES = int(_os.environ.get("AOTB_BANK_FRAMES", "24"))   # initial long-term bank capacity (memory frames)
 
 
