@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     pdl_trigger();
     if (tid == 0) {
-        for (int s = 0; s < CH_STAGES; ++s) { mbar_init(&a_full[s], 256); mbar_init(&b_full[s], 1); mbar_init(&s_free[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 128); }
+        for (int s = 0; s < CH_STAGES; ++s) { mbar_init(&a_full[s], 8); mbar_init(&b_full[s], 1); mbar_init(&s_free[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 4); }
         fence_mbar_init();
     }
     if (warp == 13) tmem_alloc<256>(tmem_slot);
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
                     *reinterpret_cast<uint2*>(Al + i * 2048) = pl;
                 }
                 fence_proxy_async();
-                mbar_arrive(&a_full[s]);
+                mbar_arrive_warp(&a_full[s]);
             };
             float4 v0[8], v1[8], v2[8];
             if (nchunks > 0) load_chunk(kbeg, v0);
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_chain_kernel(const ChainAr
                 }
                 if (c + 32 >= BN) {                  // the accumulator has been read completely: hand it back to the MMA warp
                     tc_fence_before();
-                    mbar_arrive(&acc_free[acc]);
+                    mbar_arrive_warp(&acc_free[acc]);
                 }
                 const uint32_t srow = stg_s + lane * (CH_STG_LD * 4);
 #pragma unroll

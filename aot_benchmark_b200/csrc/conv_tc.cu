@@ -42,7 +42,6 @@ struct ConvTcArgs {
     int act;
     int splits;          // split-K: the `splits` CTAs (blockIdx.z) of one output tile form a thread-block cluster; CTA z
                          // handles chunks [z*per, (z+1)*per) and the partial tiles are summed over distributed smem
-    int bulk;            // 1: finish writes the tile with one bulk async copy per row (smem -> global) instead of per-thread stores
     int spin;            // 1: mbarrier waits without the suspend hint
     long long* prof;     // diagnostic: 12 clock64 stamps per CTA (see aotb_set_conv_tiling), or null
 };
@@ -159,64 +158,6 @@ __device__ __forceinline__ void conv_finish_tile_pre(const ConvTcArgs& a, const 
     }
 }
 
-// Variant of conv_finish_tile_pre: bias / residual / activation are applied IN PLACE in the staging tile, then one thread per
-// output row hands its BN x 4 bytes to the bulk-copy engine (cp.async.bulk shared -> global).  The per-thread float4 stores of
-// the other variant move a 128 x 128 tile at 18-25 GB/s per SM (3.5 us, profiles/r02_trip17_conv_microbench.json) although no
-// load is left on their path; the bulk engine is not bound by the LSU's outstanding-store window.
-template <int BN>
-__device__ __forceinline__ void conv_finish_tile_bulk(const ConvTcArgs& a, uint8_t* smem, int tid, int m0, int n0,
-                                                      const FinishPre<BN>& pre) {
-    constexpr int LD = BN + 4, C4 = BN / 4, RSTEP = 256 / C4, ITERS = 128 / RSTEP, B = 8;
-    static_assert(ITERS % B == 0, "finish tiling");
-    const int c = (tid % C4) * 4, n = n0 + c, r0 = tid / C4;
-    const uint32_t sbase = smem_u32(reinterpret_cast<const float*>(smem) + r0 * LD + c);
-    float4 rs[B];
-#pragma unroll
-    for (int b = 0; b < B; ++b) rs[b] = pre.rs[b];
-#pragma unroll 1
-    for (int i0 = 0; i0 < ITERS; i0 += B) {
-        float4 v[B], nx[B];
-#pragma unroll
-        for (int b = 0; b < B; ++b)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[b].x), "=f"(v[b].y), "=f"(v[b].z), "=f"(v[b].w)
-                         : "r"(sbase + (uint32_t)((i0 + b) * RSTEP * LD) * 4u));
-        if (i0 + B < ITERS) {
-#pragma unroll
-            for (int b = 0; b < B; ++b) {
-                const int m = m0 + r0 + (i0 + B + b) * RSTEP;
-                nx[b] = (a.res && m < a.M) ? *reinterpret_cast<const float4*>(a.res + (size_t)m * a.ldres + n)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-            float4 o = v[b];
-            o.x += pre.b4.x; o.y += pre.b4.y; o.z += pre.b4.z; o.w += pre.b4.w;
-            o.x += rs[b].x; o.y += rs[b].y; o.z += rs[b].z; o.w += rs[b].w;
-            o.x = apply_act(o.x, a.act); o.y = apply_act(o.y, a.act);
-            o.z = apply_act(o.z, a.act); o.w = apply_act(o.w, a.act);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (uint32_t)((i0 + b) * RSTEP * LD) * 4u),
-                         "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
-        }
-        if (i0 + B < ITERS) {
-#pragma unroll
-            for (int b = 0; b < B; ++b) rs[b] = nx[b];
-        }
-    }
-    fence_proxy_async();                                  // generic-proxy writes of the tile -> visible to the bulk-copy engine
-    asm volatile("bar.sync 1, 256;" ::: "memory");        // the 8 epilogue warps
-    if (tid < 128) {
-        const int m = m0 + tid;
-        if (m < a.M) {
-            const uint32_t src = smem_u32(reinterpret_cast<const float*>(smem) + tid * LD);
-            float* dst = a.out + (size_t)m * a.ldout + n0;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "n"(BN * 4) : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the staging rows may be released
-    }
-}
-
 template <int BN, int STAGES>
 struct ConvSmem {
     static constexpr int A_BYTES = 128 * 128;          // one 128 x 64 half tile
@@ -252,7 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     pdl_trigger();      // the next kernel may start its prologue; it waits for this grid before reading our output
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 256); mbar_init(&b_full[s], 1); mbar_init(&s_free[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 8); mbar_init(&b_full[s], 1); mbar_init(&s_free[s], 1); }
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
@@ -333,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
                 *reinterpret_cast<uint2*>(Al + i * 2048) = pl;
             }
             fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            mbar_arrive(&a_full[s]);
+            mbar_arrive_warp(&a_full[s]);
             if (tid == 0 && it == 0) stamp(2);
         };
         // three chunks of global loads in flight per thread (register ring), so the ~L2 latency of a chunk is
@@ -439,8 +380,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__
     if (tid == 0) stamp(8);
     if (warp < 8) {
         const int zr = a.splits > 1 ? (int)blockIdx.z : 0;
-        if (a.splits == 1 && a.bulk) conv_finish_tile_bulk<BN>(a, smem, tid, m0, n0, pre);
-        else if (a.splits == 1) conv_finish_tile_pre<BN>(a, smem, tid, m0, n0, pre);
+        if (a.splits == 1) conv_finish_tile_pre<BN>(a, smem, tid, m0, n0, pre);
         else if (a.splits == 2) conv_finish_tile<BN, 2, 4>(a, smem, tid, m0, n0, zr);
         else if (a.splits == 4) conv_finish_tile<BN, 4, 2>(a, smem, tid, m0, n0, zr);
         else conv_finish_tile<BN, 8, 2>(a, smem, tid, m0, n0, zr);
@@ -581,7 +521,6 @@ extern "C" int aotb_conv2d_nhwc_tc(const float* in, const void* wh, const void* 
         a.splits = force_s;
     }
     a.spin = (tc::g_conv_tiling & 2) ? 1 : 0;
-    a.bulk = (tc::g_conv_tiling & 8) ? 1 : 0;            // experimental: bulk-copy finish (mask bit 3)
     a.prof = nullptr;
     if (tc::g_conv_tiling & 4) {      // diagnostic stamps go to the caller's workspace
         const size_t need = (size_t)ctas * a.splits * 12 * sizeof(long long);

@@ -52,7 +52,7 @@ struct __align__(8) GpBarriers {
     uint64_t k_full[2], k_free[2];
     uint64_t v_full[2], v_free[2];
     uint64_t s_full[3];     // S(n) complete in buffer n % 3; use k = n / 3 of a buffer completes phase k
-    uint64_t p_full[3];     // 512 arrivals: P(n) written over S(n)
+    uint64_t p_full[3];     // 16 arrivals (one per softmax warp): P(n) written over S(n)
     uint64_t o_done[2];     // PV(n) complete, on barrier n & 1 (phase n >> 1).  Two barriers because a parity wait is only
                             // sound when the waiter is at most one phase behind: at tile n the softmax knows PV(n - 3) is
                             // complete (S(n) was issued behind it), i.e. barrier (n - 1) & 1 is at most one phase short.
@@ -118,7 +118,7 @@ gp_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             mbar_init(&B->k_full[s], 1); mbar_init(&B->k_free[s], 1);
             mbar_init(&B->v_full[s], 1); mbar_init(&B->v_free[s], 1);
         }
-        for (int b = 0; b < 3; ++b) { mbar_init(&B->s_full[b], 1); mbar_init(&B->p_full[b], 4 * GP_BM); }
+        for (int b = 0; b < 3; ++b) { mbar_init(&B->s_full[b], 1); mbar_init(&B->p_full[b], 4 * GP_BM / 32); }
         mbar_init(&B->o_done[0], 1);
         mbar_init(&B->o_done[1], 1);
         mbar_init(&B->o_final, 1);
@@ -297,7 +297,7 @@ gp_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             if (EXACT) tmem_st8(tS + 8, pl);         //                   -> columns [16 qt + 8, 16 qt + 16)
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&B->p_full[b]);
+            mbar_arrive_warp(&B->p_full[b]);
             if (has_next) tmem_wait_ld16(srn);
         };
         if (T > 0) {

@@ -112,7 +112,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (tid == 0) {
         mbar_init(&B->q_full, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&B->kv_full[s], 1); mbar_init(&B->kv_free[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&B->s_full[i], 1); mbar_init(&B->p_full[i], GROUPS ? 2 * BM : 4 * BM); mbar_init(&B->o_final[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&B->s_full[i], 1); mbar_init(&B->p_full[i], GROUPS ? 2 * BM / 32 : 4 * BM / 32); mbar_init(&B->o_final[i], 1); }
         fence_mbar_init();
     }
     if (warp == MMA_WARP) tmem_alloc<512>(&B->tmem_base);
@@ -293,7 +293,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&B->p_full[wg]);
+            mbar_arrive_warp(&B->p_full[wg]);
         }
 
         // ---- epilogue: this thread finishes output channels [16*half, 16*half+16) of its row
@@ -431,7 +431,7 @@ lt_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 if (EXACT) tmem_st16(tPl, pl);
                 tmem_wait_st();
                 tc_fence_before();
-                mbar_arrive(&B->p_full[i]);
+                mbar_arrive_warp(&B->p_full[i]);
             }
         }
 
@@ -540,7 +540,7 @@ lt_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (tid == 0) {
         mbar_init(&B->q_full, 1);
         for (int s = 0; s < STAGES3; ++s) { mbar_init(&B->kv_full[s], 1); mbar_init(&B->kv_free[s], 1); }
-        for (int b = 0; b < 3; ++b) { mbar_init(&B->s_full[b], 1); mbar_init(&B->p_full[b], 4 * BM); }
+        for (int b = 0; b < 3; ++b) { mbar_init(&B->s_full[b], 1); mbar_init(&B->p_full[b], 4 * BM / 32); }
         for (int i = 0; i < 2; ++i) { mbar_init(&B->o_done[i], 1); mbar_init(&B->o_final[i], 1); }
         fence_mbar_init();
     }
@@ -704,7 +704,7 @@ lt_attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             l0[i] += s0; l1[i] += s1;
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&B->p_full[b]);
+            mbar_arrive_warp(&B->p_full[b]);
             if (has_next) tmem_wait_ld32(srn);
         };
         if (T > 0) {

@@ -50,7 +50,7 @@ struct __align__(8) BarriersP {
     uint64_t kv_full[P_STAGES];
     uint64_t kv_free[P_STAGES];
     uint64_t s_full[3];     // S(n) complete in buffer n % 3; use k = n / 3 of a buffer completes phase k
-    uint64_t p_full[3];     // 256 arrivals: P(n) written over S(n)
+    uint64_t p_full[3];     // 8 arrivals (one per softmax warp): P(n) written over S(n)
     uint64_t o_done;        // committed after every PV: PV(n) completes phase n
     uint64_t o_final;       // the last PV
     uint32_t tmem_base;
@@ -102,7 +102,7 @@ lt_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (tid == 0) {
         mbar_init(&B->q_full, 1);
         for (int s = 0; s < P_STAGES; ++s) { mbar_init(&B->kv_full[s], 1); mbar_init(&B->kv_free[s], 1); }
-        for (int b = 0; b < 3; ++b) { mbar_init(&B->s_full[b], 1); mbar_init(&B->p_full[b], 2 * P_BM); }
+        for (int b = 0; b < 3; ++b) { mbar_init(&B->s_full[b], 1); mbar_init(&B->p_full[b], 2 * P_BM / 32); }
         mbar_init(&B->o_done, 1);
         mbar_init(&B->o_final, 1);
         fence_mbar_init();
@@ -271,7 +271,7 @@ lt_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&B->p_full[b]);
+            mbar_arrive_warp(&B->p_full[b]);
             par ^= 1u << b;
             b = b == 2 ? 0 : b + 1;
         }

@@ -28,6 +28,13 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per WARP: every lane has made its own writes visible (tcgen05.wait::st + fence, or fence.proxy.async), the warp
+// converges, lane 0 signals.  512 per-thread arrivals on one barrier word are 512 serialised shared-memory atomics per tile in
+// the same MIO queue the MUFU and TMEM instructions go through; the barrier is initialised with the number of warps instead.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -84,8 +84,8 @@ USE_GRAPHS = _os.environ.get("AOTB_GRAPHS", "1") == "1"
 # programmatic dependent launch: kernel N+1's prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps
 # kernel N's tail; every kernel waits (griddepcontrol.wait) before reading its inputs
 USE_PDL = _os.environ.get("AOTB_PDL", "1") == "1"     # programmatic dependent launch: +2 % (profiles/r01_trip14)
-CONV_TILING = _os.environ.get("AOTB_CONV_TILING", "model")   # "model" (fitted cost model) | "narrow" (old heuristic) | "bulk" (model + bulk-copy finish)
-_CONV_TILING_MASK = {"model": 0, "narrow": 1, "bulk": 8}
+CONV_TILING = _os.environ.get("AOTB_CONV_TILING", "model")   # "model" (fitted cost model) | "narrow" (old heuristic)
+_CONV_TILING_MASK = {"model": 0, "narrow": 1}
 
 
 def _apply_pdl():
