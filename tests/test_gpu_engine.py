@@ -206,13 +206,20 @@ def test_cuda_graph_replay_matches_eager():
         finally:
             engine_mod.USE_GRAPHS = old
         res[use] = outs
+    def diff(what, A, B):
+        bad = []
+        for f, (a, b) in enumerate(zip(A, B)):
+            if not torch.equal(a, b):
+                d = (a.float() - b.float()).abs()
+                bad.append(f"frame {f + 1}: {int((d != 0).sum())} of {d.numel()} differ, max {d.max().item():.3e}, "
+                           f"NaNs {int(torch.isnan(a.float()).sum())}/{int(torch.isnan(b.float()).sum())}")
+        assert not bad, what + ": " + "; ".join(bad)
+
     for rep in range(2):
-        for a, b in zip(res[False][rep][0], res[True][rep][0]):
-            assert torch.equal(a, b)
-        for a, b in zip(res[False][rep][1], res[True][rep][1]):
-            assert torch.equal(a, b)
-    for a, b in zip(res[True][0][0], res[True][1][0]):
-        assert torch.equal(a, b)
+        diff(f"logits, eager vs graphs, video {rep + 1}", res[False][rep][0], res[True][rep][0])
+        diff(f"labels, eager vs graphs, video {rep + 1}", res[False][rep][1], res[True][rep][1])
+    diff("logits, graphs, video 1 vs video 2", res[True][0][0], res[True][1][0])
+    diff("logits, eager, video 1 vs video 2", res[False][0][0], res[False][1][0])
 
 
 def test_full_size_cfg2_tensor_core_vs_fp32_cuda_core_paths():
