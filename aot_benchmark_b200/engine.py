@@ -692,7 +692,11 @@ class AOTEngine(nn.Module):
             self._alloc()
         self.curr_enc_embs = img_embs
         if self.pos_emb is None:
-            self.pos_emb = _pos_emb_sine(*self.enc_size_2d, npf=self._plan().C // 2).to(self._plan().device)
+            # the table lives in the workspace, i.e. exactly as long as the captured graphs that read it: re-creating it per
+            # video left the graphs of the previous video replaying a freed address (same block again only by allocator luck)
+            if getattr(self._ws, "pos_emb", None) is None:
+                self._ws.pos_emb = _pos_emb_sine(*self.enc_size_2d, npf=self._plan().C // 2).to(self._plan().device)
+            self.pos_emb = self._ws.pos_emb
         id_emb = self.assign_identity_from_mask(mask, st)
         self.curr_id_embs = id_emb
         self._lstt_forward(img_embs, id_emb, st)

@@ -195,11 +195,15 @@ def test_cuda_graph_replay_matches_eager():
         engine_mod.USE_GRAPHS = use
         try:
             eng = _build_cuda_engine("r50_aotl", sd, 2)
-            outs = []
+            outs, ptrs = [], []
             for rep in range(2):                      # second video reuses buffers and captured graphs
                 with torch.no_grad():
                     lo, labels = O.run_video(eng, frames, mask, 6, (160, 240))
                 outs.append(([t.clone() for t in lo], labels))
+                ptrs.append(eng.aot_engines[0].pos_emb.data_ptr())
+            # tensors the captured graphs read must survive restart_engine(): a per-video position table made video-2
+            # replays read a freed block (right only while the allocator handed the same block back)
+            assert ptrs[-1] == ptrs[-2]
             if use:
                 e0 = eng.aot_engines[0]
                 assert any(slot[1] is not None for slot in e0.graphs.slots.values()), "no graph was captured"
