@@ -105,7 +105,8 @@ def _engine_worker(rank, world, port, ret):
     from aot_benchmark_b200 import EngineConfig, build_engine, build_vos_model
     from oracle import aot_oracle as O
     from oracle import weights as OW
-    emu_ops.install_engine(_MP())
+    import test_cpu_graph_static as gs
+    gs._install(_MP())            # emulated entry points + a tracer in place of GraphCache: "replays" must repeat the captured launches
     name, H, W, objs, T = "aott", 65, 81, 2, 6
     sd = OW.build_state_dict(name, seed=1)
     cfg = EngineConfig("t", name)
@@ -117,15 +118,18 @@ def _engine_worker(rank, world, port, ret):
         eng = build_engine(cfg.MODEL_ENGINE, phase="eval", aot_model=model, gpu_id=0, long_term_mem_gap=1)
         if mode == "sharded":
             eng.enable_kv_sharding(rank, world)
-        with torch.no_grad():
-            lo, labels = O.run_video(eng, frames, mask, objs, (H, W),
-                                     forced_masks=outs["plain"][1] if mode == "sharded" else None)
-        outs[mode] = (lo, labels)
+        for video in range(2 if mode == "sharded" else 1):       # second video: kept workspace, kept "graphs", bank restarted
+            with torch.no_grad():
+                lo, labels = O.run_video(eng, frames, mask, objs, (H, W),
+                                         forced_masks=outs["plain"][1] if mode == "sharded" else None)
+            if video == 1:
+                assert all(torch.equal(a, b) for a, b in zip(lo, outs[mode][0]))
+            outs[mode] = (lo, labels)
         if mode == "sharded":
             e0 = eng.aot_engines[0]
             local_rows, mem_frames, n = e0.bank_len, e0._mem_frames, e0.enc_hw
     d = max((a[:, :objs + 1] - b[:, :objs + 1]).abs().max().item() for a, b in zip(outs["plain"][0], outs["sharded"][0]))
-    ret[rank] = (d, local_rows, mem_frames, n)
+    ret[rank] = (d, local_rows, mem_frames, n, gs.TracingGraphCache.replays)
     dist.destroy_process_group()
 
 
@@ -140,7 +144,8 @@ def test_two_rank_sharded_engine_matches_unsharded():
     assert len(ret) == 2
     rows = 0
     for rank in range(world):
-        d, local_rows, mem_frames, n = ret[rank]
+        d, local_rows, mem_frames, n, replays = ret[rank]
+        assert replays > 10                          # the sharded LSTT / update / decode bodies were "replayed" and matched
         assert d < 1e-4, f"rank {rank}: sharded vs unsharded max |dlogit| = {d}"
         assert mem_frames == 6                       # reference frame + 5 propagated frames at gap 1
         rows += local_rows
