@@ -311,7 +311,8 @@ def run_ours(args):
     rl.update(lt_roofline(m, K))
     rl.update({"traffic": traffic, "traffic_note": traffic_note,
                "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({how})",
-               "algorithmic": f"FLOPs = 4*N*Tk*C per launch (N={enc_hw}, C=256, Tk={enc_hw}*m)"
+               "algorithmic": f"FLOPs = 4*N*Tk*C per launch (N={enc_hw}, C=256, Tk={enc_hw}*m); the exact fp16x2 mode executes 3.5x "
+                              f"these on the tensor pipe (6+16 MMAs per 128x128 tile), the fast mode 1.75x (DESIGN.md 3.1)"
                if cfg.MODEL_VOS == "aot" else f"FLOPs = 2*N*Tk*(128+1024) per launch (N={enc_hw}, Tk={enc_hw}*m)",
                "timing": "CUDA events around every launch in an eager (graph-free) probe pass of the same clip"})
     out = {
