@@ -29,8 +29,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // One arrival per WARP: every lane has made its own writes visible (tcgen05.wait::st + fence, or fence.proxy.async), the warp
-// converges, lane 0 signals.  512 per-thread arrivals on one barrier word are 512 serialised shared-memory atomics per tile in
-// the same MIO queue the MUFU and TMEM instructions go through; the barrier is initialised with the number of warps instead.
+// converges, lane 0 signals; the barrier is initialised with the number of warps.  (Measured against one arrival per thread --
+// 512 per score tile, 256 per conv K chunk -- it changes neither kernel's time: profiles/r02_summary.md, trip 22.)
 __device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
