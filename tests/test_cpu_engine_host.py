@@ -23,17 +23,19 @@ def _engine(model_name, sd, gap, skip=None):
     return eng
 
 
-@pytest.mark.parametrize("lt_impl", ["tc_exact", "simt"])
-@pytest.mark.parametrize("name", ["aott_raw_257", "r50_aotl_small", "r50_deaotl_small", "deaott_small",
-                                  "swinb_aotl_small", "swinb_deaotl_small", "aott_skip2", "deaott_skip3"])
+_GOLDEN_CLIPS = ["aott_raw_257", "r50_aotl_small", "r50_deaotl_small", "deaott_small", "swinb_aotl_small", "swinb_deaotl_small",
+                 "aott_skip2", "deaott_skip3"]
+# the fp32 CUDA-core long-term attention (LT_IMPL=simt) is a separate orchestration only for the AOT models; Swin clips run once
+_SIMT_CLIPS = ["aott_raw_257", "r50_aotl_small", "aott_skip2"]
+
+
+@pytest.mark.parametrize("name,lt_impl", [(n, "tc_exact") for n in _GOLDEN_CLIPS] + [(n, "simt") for n in _SIMT_CLIPS])
 def test_engine_orchestration_vs_reference_golden(monkeypatch, golden_dir, name, lt_impl):
     import emu_ops
     from aot_benchmark_b200 import engine
     emu_ops.install_engine(monkeypatch)
     monkeypatch.setattr(engine, "LT_IMPL", lt_impl)
     g = torch.load(os.path.join(golden_dir, f"video_{name}.pt"))
-    if lt_impl == "simt" and (g["model"].endswith(("deaotl", "deaott")) or g["model"].startswith("swinb")):
-        pytest.skip("DeAOT always uses the fp32 SIMT attention; the Swin clips are covered once")
     T = min(g["frames"], 3 if g["model"].startswith("swinb") else 6)
     sd = OW.build_state_dict(g["model"], seed=g["seed"], flavour=g["flavour"])
     frames, mask = O.synthetic_video(g["frames"], g["H"], g["W"], g["objs"], seed=1234 + g["seed"])
